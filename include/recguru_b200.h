@@ -1,0 +1,194 @@
+/*
+ * recguru_b200.h -- C ABI of the B200-native RecGURU embedding-and-scoring hot path.
+ *
+ * This is the drop-in boundary.  The reference (Chain123/RecGURU)
+ * is pure PyTorch and has no FFI of its own; each entry point below names the reference
+ * call site (file:line under /root/reference/GURU) whose ATen op sequence it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  Every pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host.
+ *   - the caller owns every buffer (inputs, outputs, scratch).  No allocation, no global
+ *     state, no implicit synchronisation inside; work is enqueued on `stream`.
+ *   - scratch: call the matching *_workspace_bytes() first and pass a buffer of at least
+ *     that size, 256-byte aligned.
+ *   - return value: 0 on success, negative on error
+ *       RECGURU_E_SHAPE      (-1)  bad shape / alignment / null pointer
+ *       RECGURU_E_UNSUPPORTED(-2)  unsupported d / K / size
+ *       RECGURU_E_CUDA       (-3)  CUDA launch error (see recguru_last_error())
+ *       RECGURU_E_WORKSPACE  (-4)  workspace too small
+ *   - row-major fp32 tables; ids are int64 on arrival (numpy int64 -> default_collate,
+ *     data/data_loader.py:36,418-421) and are narrowed to int32 internally (V1 < 2^31).
+ */
+#ifndef RECGURU_B200_H_
+#define RECGURU_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RECGURU_OK 0
+#define RECGURU_E_SHAPE (-1)
+#define RECGURU_E_UNSUPPORTED (-2)
+#define RECGURU_E_CUDA (-3)
+#define RECGURU_E_WORKSPACE (-4)
+
+/* loss kinds for the sampled-scoring ops */
+#define RECGURU_LOSS_BPR 0     /* tools/lossfunctions.py:52-72  BPRLoss               */
+#define RECGURU_LOSS_BPR_SAS 1 /* tools/lossfunctions.py:75-96  BPRLoss_sas           */
+#define RECGURU_LOSS_SCE 2     /* tools/lossfunctions.py:29-49  SampledCrossEntropyLoss (label 0) */
+
+typedef void* recguru_stream_t; /* cudaStream_t */
+
+/* ABI version of this header (bumped on any signature change). */
+int recguru_abi_version(void);
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* recguru_last_error(void);
+/* Number of kernels this library has launched since load (all threads). */
+int64_t recguru_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Piece 1 -- fused item-embedding gather + positional add + pad mask      (K1: G1,M1,P1)
+ *   replaces  src_emb(ids) ; mask = 1-(ids==pad) ; pos_emb(x, mask)  before dropout
+ *             AutoEnc4Rec.py:71-75,:89-93,:176-181,:189-193
+ *             AutoEnc4Rec_cross.py:98-102,:124-128,:156-160 ; Transformer/transformer.py:104-106
+ *   out[t,:]  = (weight[ids[t],:] + pe[t % L,:]) * mask[t]      (fp32, add then mul: bit-exact)
+ *   mask[t]   = ids[t] != pad_index ? 1 : 0   when mask_in == NULL, else mask_in[t]
+ *   pe == NULL  -> plain gather  out[t,:] = weight[ids[t],:]   (S1/S2/E1 gathers)
+ *   mask_out may be NULL.  d % 4 == 0, weight/pe/out 16-byte aligned.
+ * ---------------------------------------------------------------------------------- */
+int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d,
+                           const int64_t* ids, int64_t n_tokens, int64_t L,
+                           const float* pe, const float* mask_in, int64_t pad_index,
+                           float* out, float* mask_out, recguru_stream_t stream);
+
+/* PositionalEncoding.forward(x, mask) before dropout (Transformer/transformer.py:104-106;
+ * learned variant :337-342 by passing the learned table as pe):
+ *   out[t,:] = (x[t,:] + pe[t % L,:]) * mask[t]                                        */
+int recguru_pe_mask(const float* x, const float* pe, const float* mask, int64_t n_tokens,
+                    int64_t L, int64_t d, float* out, recguru_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Piece 2 -- deterministic embedding-table backward                               (K2: B1)
+ *   replaces  ATen embedding_dense_backward at every lookup site + the dense add_
+ *             accumulation (loss.backward(): train_auto.py:124, gan_training.py:491-564)
+ *   A lookup *site* s contributes, for each of its `count` gathered indices j,
+ *       dW[ids[j],:] += coef[j] * (*scale) * (*scale2) * X[j / group, :]
+ *   (coef NULL -> 1, scale/scale2 NULL -> 1).  Input sites use X = upstream grad, group = 1,
+ *   coef = pad mask; scoring sites use X = h, group = K, coef = dLoss/dlogit.
+ *   Indices equal to padding_idx are skipped (nn.Embedding padding_idx; pass -1 for none).
+ *   Algorithm: stable LSD radix sort of (id, occurrence) over all sites in one pass,
+ *   run-length segments, fixed-order segmented sum (no atomics) -> bit-reproducible.
+ *   dW is dense [V1,d]; zero_fill != 0 zero-fills it first (dense-grad contract of the
+ *   reference's Adam), zero_fill == 0 accumulates (+=) into the touched rows only.
+ * ---------------------------------------------------------------------------------- */
+#define RECGURU_MAX_SITES 8
+typedef struct {
+  const int64_t* ids; /* [count] */
+  int64_t count;
+  const float* X;     /* [count / group, d] */
+  const float* coef;  /* [count] or NULL */
+  const float* scale; /* device scalar or NULL (e.g. upstream grad of the scalar loss) */
+  const float* scale2;/* second device scalar or NULL (e.g. 1/sum(mask), loss_out[1]) */
+  int64_t group;      /* gathered indices per row of X (1, or K) */
+} recguru_lookup_site_t;
+
+int64_t recguru_embedding_bwd_workspace_bytes(int64_t total_count, int64_t V1, int64_t d);
+int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites, int64_t d,
+                          int64_t V1, int64_t padding_idx, float* dW, int zero_fill,
+                          void* workspace, int64_t workspace_bytes, recguru_stream_t stream);
+
+/* The sort stage on its own (parity: bit-exact vs torch.sort(ids, stable=True)).
+ *   sorted_ids[i] = ids[perm[i]], ascending, ties in ascending perm.  ids in [0, V1).   */
+int64_t recguru_sort_ids_workspace_bytes(int64_t count, int64_t V1);
+int recguru_sort_ids(const int64_t* ids, int64_t count, int64_t V1, int64_t* sorted_ids,
+                     int64_t* perm, void* workspace, int64_t workspace_bytes,
+                     recguru_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Piece 3 -- sampled-negative scoring: fused gather-dot(-loss)               (K3: S1,S2,S3,L*)
+ *   replaces  src_emb(dec_out).view(-1,L,1,d), src_emb(n_items).view(-1,L,K,d), the two
+ *             batched matmuls and the loss module
+ *             AutoEnc4Rec.py:115-131,:219-227 ; AutoEnc4Rec_cross.py:203-215 ;
+ *             tools/utils.py:103-126 ; tools/lossfunctions.py:36-49,:56-72,:79-96
+ *   p[i]   = h[i,:] . weight[pos[i],:]            i in [0, n_pos)   (n_pos = B*L)
+ *   n[i,k] = h[i,:] . weight[neg[i*K+k],:]
+ *   loss   = sum_i l_i * mask[i] / sum_i mask[i]   (mask NULL -> mean)
+ *   loss_out[0] = loss, loss_out[1] = 1 / sum_i mask[i]  (two floats).
+ *   dp_unit[i] = mask[i] * d l_i / d p[i], dn_unit likewise: the per-position derivatives
+ *   WITHOUT the 1/sum(mask) factor; consumers pass loss_out+1 as `scale2`.
+ *   kind < 0: scores only (loss, dp_unit, dn_unit may be NULL).
+ * ---------------------------------------------------------------------------------- */
+int64_t recguru_sampled_workspace_bytes(int64_t n_pos, int64_t K);
+int recguru_sampled_score_loss_fwd(const float* h, const float* weight, int64_t V1, int64_t d,
+                                   const int64_t* pos, const int64_t* neg, int64_t n_pos,
+                                   int64_t K, const float* mask, int kind, float* p_out,
+                                   float* n_out, float* loss_out, float* dp_unit,
+                                   float* dn_unit, void* workspace, int64_t workspace_bytes,
+                                   recguru_stream_t stream);
+/* Loss only, from logits (drop-in for loss_bpr(p,n,mask) / loss_s_ce(logits,...)). */
+int recguru_sampled_loss_fwd(const float* p, const float* n, int64_t n_pos, int64_t K,
+                             const float* mask, int kind, float* loss_out, float* dp_unit,
+                             float* dn_unit, void* workspace, int64_t workspace_bytes,
+                             recguru_stream_t stream);
+/* dh[i,:] = s * (dp[i] * weight[pos[i],:] + sum_k dn[i,k] * weight[neg[i*K+k],:]),
+ * s = (*scale) * (*scale2), device scalars, each NULL -> 1.  The table gradient goes through
+ * recguru_embedding_bwd with sites (pos, X=h, coef=dp, group 1), (neg, h, dn, K).        */
+int recguru_sampled_score_bwd_dh(const float* dp, const float* dn, const float* scale,
+                                 const float* scale2, const float* weight, int64_t V1, int64_t d, const int64_t* pos,
+                                 const int64_t* neg, int64_t n_pos, int64_t K, float* dh,
+                                 recguru_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Piece 4 -- full-catalog scoring: tcgen05/TMEM GEMM + running top-K + target rank
+ *                                                                     (K4: E1', R1, R2)
+ *   replaces  torch.matmul(u, src_emb.weight.T)  (AutoEnc4Rec.py:230) followed by
+ *             argsort(argsort(-score))[:,0]      (train_auto.py:234-237; gan_training.py:130-133)
+ *   Operands are bf16 (cast once with recguru_cast_bf16), accumulation fp32 in TMEM.
+ *   items_bf16 holds n_items rows; row r is catalog id  id_lo + r.  Candidates are all of
+ *   them (caller excludes pad row 0 / EOS row by choosing the slice, data_loader.py:117-118).
+ *   target_score[u] = score of (u, target[u]) from recguru_catalog_target_scores (same
+ *   tensor-core data path => exact ties stay exact).
+ *   rank_count[u] = #{j in slice: s_j > s_t} + #{j in slice, j < t: s_j == s_t}
+ *   topk: descending score, ties -> lower id; padded with (-inf, -1) if n_items < k.
+ *   The logit matrix [U x n_items] is never written.  d in {64,128}; 1 <= k <= 32.
+ * ---------------------------------------------------------------------------------- */
+int recguru_cast_bf16(const float* in, int64_t n, void* out_bf16, recguru_stream_t stream);
+int recguru_catalog_target_scores(const void* users_bf16, int64_t U, const void* items_bf16,
+                                  int64_t id_lo, int64_t n_items, int64_t d,
+                                  const int64_t* target, float* target_score,
+                                  recguru_stream_t stream);
+int64_t recguru_catalog_workspace_bytes(int64_t U, int64_t n_items, int64_t d, int64_t k);
+int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, const void* items_bf16,
+                              int64_t id_lo, int64_t n_items, int64_t d, const int64_t* target,
+                              const float* target_score, int64_t k, float* topk_val,
+                              int64_t* topk_id, int64_t* rank_count, void* workspace,
+                              int64_t workspace_bytes, recguru_stream_t stream);
+/* Debug/parity only: dense scores [U, n_items] fp32 through the same tcgen05 path. */
+int recguru_catalog_scores_dense(const void* users_bf16, int64_t U, const void* items_bf16,
+                                 int64_t n_items, int64_t d, float* scores,
+                                 recguru_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Piece 5 -- merge of per-shard results (after the NCCL all-gather)                 (K5)
+ *   vals/ids [G,U,k], counts [G,U]  ->  top-k [U,k] (desc score, asc id), rank[U] = sum counts
+ * ---------------------------------------------------------------------------------- */
+int recguru_topk_merge(const float* vals, const int64_t* ids, const int64_t* counts, int64_t G,
+                       int64_t U, int64_t k, float* out_val, int64_t* out_id, int64_t* out_rank,
+                       recguru_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * H1 -- rank -> HR/NDCG/MRR                                    (tools/metrics.py:26-68)
+ *   hist[r] = #{u: rank[u] == r} for r < kmax, hist[kmax] = #{u: rank[u] >= kmax}
+ *   (exact integer histogram; the host folds it into HR@k / NDCG@k / MRR@k in fp64).
+ *   hist must be zeroed by the caller if accumulate == 0 is not requested.
+ * ---------------------------------------------------------------------------------- */
+int recguru_rank_histogram(const int64_t* rank, int64_t U, int64_t kmax, int64_t* hist,
+                           int accumulate, recguru_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECGURU_B200_H_ */

@@ -1,0 +1,184 @@
+"""Full-catalog evaluation: fused scoring + top-K + target rank, single GPU or row-sharded.
+
+Host side of pieces 4 and 5 (SURVEY.md section 8a rows E1', R1, R2, H1 and section 8e).
+The reference ranks a target among sampled candidates with a double argsort
+(train_auto.py:234-237); here every user is ranked against the *whole* catalog
+[id_lo, id_lo + N) by one tcgen05 GEMM sweep that never writes the logits.
+
+Sharding (the only place the path is partitioned): the item table is row-sharded, rank g owns
+ids ``[id_lo + g*ceil(N/G), ...)``; users arrive data-parallel (U/G per rank) and are
+all-gathered; per-shard results are exchanged with NCCL and merged by a small kernel.
+d is never split, so every score is computed entirely on one GPU by the same kernel and the
+results are shard-count independent.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------
+# H1: rank -> HR / NDCG / MRR   (tools/metrics.py:26-68)
+# --------------------------------------------------------------------------------------
+def metrics_from_histogram(hist, n_users: int, ks: Sequence[int]) -> Dict[int, Dict[str, float]]:
+    """Fold an exact integer rank histogram into HR@k, NDCG@k, MRR@k in fp64, using the same
+    per-rank terms as the reference: hit = r<k, ndcg = 1/log2(r+2), mrr = 1/(r+1)."""
+    h = np.asarray(hist.cpu() if isinstance(hist, torch.Tensor) else hist, dtype=np.float64)
+    kmax = len(h) - 1
+    r = np.arange(kmax, dtype=np.float64)
+    ndcg_w = 1.0 / np.log2(r + 2.0)
+    mrr_w = 1.0 / (r + 1.0)
+    out = {}
+    for k in ks:
+        if k > kmax:
+            raise ValueError(f"k={k} exceeds histogram range {kmax}")
+        out[int(k)] = {
+            "hr": float(h[:k].sum() / n_users),
+            "ndcg": float((h[:k] * ndcg_w[:k]).sum() / n_users),
+            "mrr": float((h[:k] * mrr_w[:k]).sum() / n_users),
+        }
+    return out
+
+
+def rank_metrics(rank: Tensor, ks: Sequence[int] = (5, 10, 20, 30)) -> Dict[int, Dict[str, float]]:
+    """HR/NDCG/MRR@k of a device rank vector: one histogram kernel + a (max(ks)+1)-int D2H copy,
+    instead of the reference's per-user Python loops (tools/metrics.py:50-68)."""
+    kmax = int(max(ks))
+    hist = ops.raw_rank_histogram(rank, kmax)
+    return metrics_from_histogram(hist, rank.numel(), ks)
+
+
+def _as_rank_tensor(r) -> Tensor:
+    if isinstance(r, torch.Tensor):
+        return r.to(torch.int64)
+    return torch.as_tensor(np.asarray(r), dtype=torch.int64)
+
+
+def hit_at_k_batch(r, k: int) -> float:
+    """tools/metrics.py:26-33 (accepts a CUDA rank tensor; lists go through one H2D copy)."""
+    t = _as_rank_tensor(r)
+    return rank_metrics(t if t.is_cuda else t.cuda(), (k,))[k]["hr"]
+
+
+def NDCG_at_k_batch(r, k: int) -> float:
+    """tools/metrics.py:49-54"""
+    t = _as_rank_tensor(r)
+    return rank_metrics(t if t.is_cuda else t.cuda(), (k,))[k]["ndcg"]
+
+
+def mrr_at_k_batch(r, k: int) -> float:
+    """tools/metrics.py:64-68"""
+    t = _as_rank_tensor(r)
+    return rank_metrics(t if t.is_cuda else t.cuda(), (k,))[k]["mrr"]
+
+
+# --------------------------------------------------------------------------------------
+# shard arithmetic
+# --------------------------------------------------------------------------------------
+def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Row range [lo, hi) of the candidate slice owned by `rank`."""
+    per = -(-n_items // world)
+    lo = min(n_items, rank * per)
+    hi = min(n_items, lo + per)
+    return lo, hi
+
+
+# --------------------------------------------------------------------------------------
+# the evaluator
+# --------------------------------------------------------------------------------------
+class CatalogEvaluator:
+    """Ranks users against the catalog slice ``weight[id_lo : id_lo + n_items]``.
+
+    ``weight`` is the fp32 (or bf16) item table ``[V1, d]``; by default the candidates are ids
+    ``1 .. V1-2`` (pad row 0 and the EOS row excluded, as the reference's samplers do:
+    data/data_loader.py:117-118,:209-210).  With a process group the candidate range is
+    row-sharded over the ranks; each rank passes only ITS users to :meth:`rank_topk` and gets
+    back the results for those users.
+    """
+
+    def __init__(self, weight: Tensor, k: int = 10, id_lo: int = 1, n_items: Optional[int] = None,
+                 group: Optional[dist.ProcessGroup] = None, sharded: Optional[bool] = None):
+        if n_items is None:
+            n_items = weight.shape[0] - 2
+        self.k = int(k)
+        self.group = group
+        self.world = dist.get_world_size(group) if (sharded or (sharded is None and group is not None)) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        lo, hi = shard_bounds(n_items, self.world, self.rank)
+        self.id_lo = id_lo + lo                      # catalog id of local row 0
+        self.n_local = hi - lo
+        self.n_items = n_items
+        self.d = weight.shape[1]
+        self.items = self._prepare_items(weight[id_lo + lo: id_lo + hi])
+
+    # -- local compute: CUDA kernels (tests for the host logic subclass and override these) --
+    def _prepare_items(self, rows: Tensor) -> Tensor:
+        rows = rows.contiguous()
+        return rows if rows.dtype == torch.bfloat16 else ops.raw_cast_bf16(rows)
+
+    def _prepare_users(self, users: Tensor) -> Tensor:
+        users = users.contiguous()
+        return users if users.dtype == torch.bfloat16 else ops.raw_cast_bf16(users)
+
+    def _local_target_scores(self, users_bf16: Tensor, target: Tensor) -> Tensor:
+        return ops.raw_catalog_target_scores(users_bf16, self.items, target, self.id_lo)
+
+    def _local_topk_rank(self, users_bf16: Tensor, target: Tensor, tscore: Tensor):
+        return ops.raw_catalog_topk_rank(users_bf16, self.items, target, tscore, self.k, self.id_lo)
+
+    def _merge(self, vals: Tensor, ids: Tensor, counts: Tensor):
+        return ops.raw_topk_merge(vals, ids, counts)
+
+    # -- public ---------------------------------------------------------------------------
+    def rank_topk(self, users: Tensor, target: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """users [U_local, d] (fp32 or bf16), target [U_local] int64 catalog ids ->
+        (topk_val [U_local,k] fp32, topk_id [U_local,k] int64, rank [U_local] int64)."""
+        u = self._prepare_users(users)
+        if self.world == 1:
+            ts = self._local_target_scores(u, target)
+            return self._local_topk_rank(u, target, ts)
+        G, g = self.world, self.rank
+        U_loc = u.shape[0]
+        # (1) all-gather user reps (bf16) and targets: every shard scores every user
+        u_all = torch.empty(G * U_loc, self.d, dtype=u.dtype, device=u.device)
+        t_all = torch.empty(G * U_loc, dtype=torch.int64, device=u.device)
+        dist.all_gather_into_tensor(u_all, u, group=self.group)
+        dist.all_gather_into_tensor(t_all, target.contiguous(), group=self.group)
+        # (2) target score: the owner shard computes it on its tensor cores, the others add 0
+        ts = self._local_target_scores(u_all, t_all)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=self.group)
+        # (3) local sweep over this shard's items
+        val, idx, cnt = self._local_topk_rank(u_all, t_all, ts)
+        # (4) exchange: rank r receives every shard's results for ITS users (all-to-all by user)
+        k = self.k
+        val_x = torch.empty(G, U_loc, k, dtype=val.dtype, device=val.device)
+        idx_x = torch.empty(G, U_loc, k, dtype=idx.dtype, device=idx.device)
+        cnt_x = torch.empty(G, U_loc, dtype=cnt.dtype, device=cnt.device)
+        dist.all_to_all_single(val_x, val.view(G, U_loc, k), group=self.group)
+        dist.all_to_all_single(idx_x, idx.view(G, U_loc, k), group=self.group)
+        dist.all_to_all_single(cnt_x, cnt.view(G, U_loc), group=self.group)
+        # (5) merge the G per-shard lists (desc score, asc id) and sum the rank counts
+        return self._merge(val_x, idx_x, cnt_x)
+
+    def evaluate(self, users: Tensor, target: Tensor, ks: Sequence[int] = (5, 10, 20, 30)):
+        """Ranks + HR/NDCG/MRR@k for this rank's users (global metrics need a sum of the
+        histograms over ranks: see :meth:`evaluate_global`)."""
+        _, _, rank = self.rank_topk(users, target)
+        return rank, rank_metrics(rank, ks)
+
+    def evaluate_global(self, users: Tensor, target: Tensor, ks: Sequence[int] = (5, 10, 20, 30)):
+        _, _, rank = self.rank_topk(users, target)
+        kmax = int(max(ks))
+        hist = ops.raw_rank_histogram(rank, kmax)
+        n = torch.tensor([rank.numel()], dtype=torch.int64, device=rank.device)
+        if self.world > 1:
+            dist.all_reduce(hist, group=self.group)
+            dist.all_reduce(n, group=self.group)
+        return metrics_from_histogram(hist, int(n.item()), ks)

@@ -1,0 +1,64 @@
+// Shared helpers for the recguru_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/recguru_b200.h"
+
+namespace rg {
+
+// ---- error plumbing (thread-local message, global launch counter) -------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define RG_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      rg::set_error(__VA_ARGS__);    \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+// Checks the launch that was just enqueued (no synchronisation).
+#define RG_CHECK_LAUNCH(name)                                                     \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      rg::set_error("%s: CUDA launch error: %s", name, cudaGetErrorString(e__));  \
+      return RECGURU_E_CUDA;                                                      \
+    }                                                                             \
+    rg::count_launch();                                                           \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- device helpers --------------------------------------------------------------
+#ifdef __CUDACC__
+// streaming 128-bit load that does not pollute L1 (read-once data)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+// streaming 128-bit store (written once, read by a later kernel)
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+}  // namespace rg

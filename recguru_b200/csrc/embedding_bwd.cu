@@ -1,0 +1,611 @@
+// Piece 2 (K2): deterministic embedding-table backward.
+//
+// Replaces ATen embedding_dense_backward at every lookup site of the reference plus the
+// dense add_ that sums the per-site results (triggered by loss.backward():
+// /root/reference/GURU/train_auto.py:124, gan_training.py:491-564,:860-861; lookup sites
+// AutoEnc4Rec.py:74,:92,:115-127,:180,:192,:219-221; AutoEnc4Rec_cross.py:98-102,:203-210).
+//
+//   dW[i,:] = sum over gathered occurrences j with id_j == i of  coef_j * X[row_j,:]
+//
+// Pipeline (all on one stream, no atomics on floating point => bit-reproducible):
+//   1. build_keys      : concatenate the sites' ids as uint32 keys (occurrence order)
+//   2. LSD radix sort  : ceil(bits/9) passes of {tile histogram, scan, stable scatter};
+//                        stable => equal ids stay in occurrence order, identical to
+//                        torch.sort(ids, stable=True)
+//   3. zero_fill       : dense-grad contract of the reference's Adam (optional)
+//   4. chunk_reduce    : one warp per kChunk sorted occurrences; runs that lie inside the
+//                        chunk are written straight to dW, runs that cross a chunk edge
+//                        leave a partial row in scratch
+//   5. span_fixup      : one warp per run that crosses chunk edges sums its partials in
+//                        chunk order
+// The order of every floating-point addition depends only on the (sorted) data.
+//
+// HBM roofline: per occurrence 8 B id + 4d B source row read; 4d B per distinct row
+// written; + 4*V1*d B for the zero fill.
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                           // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;     // 4096 keys per CTA
+constexpr int kMaxRadixBits = 9;
+constexpr int kMaxBins = 1 << kMaxRadixBits;
+constexpr int kChunk = 64;                               // sorted occurrences per warp
+constexpr int kReduceWarps = 8;
+
+struct SiteTable {
+  const int64_t* ids[RECGURU_MAX_SITES];
+  const float* X[RECGURU_MAX_SITES];
+  const float* coef[RECGURU_MAX_SITES];
+  const float* scale[RECGURU_MAX_SITES];
+  const float* scale2[RECGURU_MAX_SITES];
+  int64_t offset[RECGURU_MAX_SITES + 1];  // prefix sum of counts
+  int group[RECGURU_MAX_SITES];
+  int n_sites;
+};
+
+__device__ __forceinline__ int find_site(const SiteTable& st, int64_t occ) {
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < RECGURU_MAX_SITES; ++i)
+    if (i < st.n_sites && occ >= st.offset[i]) s = i;
+  return s;
+}
+
+// ---- 1. keys -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+build_keys_kernel(SiteTable st, int64_t total, uint32_t* __restrict__ keys) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += stride) {
+    const int s = find_site(st, i);
+    keys[i] = static_cast<uint32_t>(st.ids[s][i - st.offset[s]]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+narrow_keys_kernel(const int64_t* __restrict__ ids, int64_t total, uint32_t* __restrict__ keys) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += stride)
+    keys[i] = static_cast<uint32_t>(ids[i]);
+}
+
+// ---- 2. radix sort ---------------------------------------------------------------------
+// Tile layout: warp w of a CTA owns keys [tile0 + w*512, +512); item j of lane l sits at
+// offset j*32 + l, so (j, lane) order == memory order and stability is easy to keep.
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total, int shift, int bits,
+                  uint32_t* __restrict__ block_hist /* [bins][gridDim.x] */) {
+  __shared__ uint32_t s_hist[kMaxBins];
+  const int bins = 1 << bits;
+  for (int b = threadIdx.x; b < bins; b += kSortThreads) s_hist[b] = 0;
+  __syncthreads();
+  const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kSortTile;
+  const uint32_t mask = bins - 1;
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const int64_t i = tile0 + j * kSortThreads + threadIdx.x;
+    if (i < total) atomicAdd(&s_hist[(keys[i] >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += kSortThreads)
+    block_hist[static_cast<int64_t>(b) * gridDim.x + blockIdx.x] = s_hist[b];
+}
+
+// Exclusive scan of the digit-major histogram (single CTA; n = bins * n_tiles entries).
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ hist, int64_t n) {
+  __shared__ uint32_t s_warp[32];
+  const int tid = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t lo = tid * per, hi = min(n, lo + per);
+  uint32_t sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += hist[i];
+  // block exclusive scan of `sum`
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = s_warp[tid], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (tid >= o) wi += v;
+    }
+    s_warp[tid] = wi - w;
+  }
+  __syncthreads();
+  uint32_t run = s_warp[tid >> 5] + incl - sum;
+  for (int64_t i = lo; i < hi; ++i) {
+    const uint32_t v = hist[i];
+    hist[i] = run;
+    run += v;
+  }
+}
+
+template <bool kFirstPass, typename OutVal>
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     int64_t total, int shift, int bits,
+                     const uint32_t* __restrict__ block_base /* scanned [bins][grid] */,
+                     uint32_t* __restrict__ keys_out, OutVal* __restrict__ vals_out,
+                     int64_t* __restrict__ keys_out64 /* optional widened copy (last pass) */) {
+  __shared__ uint32_t s_cnt[kSortThreads / 32][kMaxBins];
+  const int bins = 1 << bits;
+  const uint32_t mask = bins - 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = threadIdx.x; b < (kSortThreads / 32) * kMaxBins; b += kSortThreads)
+    (&s_cnt[0][0])[b] = 0;
+  __syncthreads();
+
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kSortTile + warp * (32 * kSortItems);
+  uint32_t key[kSortItems];
+  uint32_t rank[kSortItems];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    const bool valid = i < total;
+    key[j] = valid ? keys_in[i] : 0xffffffffu;
+    const uint32_t dig = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;  // invalid: own group
+    const uint32_t peers = __match_any_sync(0xffffffffu, dig);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) {
+      base = s_cnt[warp][dig];
+      s_cnt[warp][dig] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[j] = base + __popc(peers & lt_mask);
+  }
+  __syncthreads();
+  // per-digit exclusive prefix over the warps of this CTA, seeded with the global base
+  for (int b = threadIdx.x; b < bins; b += kSortThreads) {
+    uint32_t run = block_base[static_cast<int64_t>(b) * gridDim.x + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      const uint32_t c = s_cnt[w][b];
+      s_cnt[w][b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    if (i < total) {
+      const uint32_t dig = (key[j] >> shift) & mask;
+      const uint32_t dst = s_cnt[warp][dig] + rank[j];
+      keys_out[dst] = key[j];
+      vals_out[dst] = static_cast<OutVal>(kFirstPass ? static_cast<uint32_t>(i) : vals_in[i]);
+      if (keys_out64) keys_out64[dst] = static_cast<int64_t>(key[j]);
+    }
+  }
+}
+
+// ---- 3. zero fill -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n_vec) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += stride)
+    p[i] = z;
+}
+
+// ---- 4. chunked segmented reduce -----------------------------------------------------
+// VPL = float4 per lane (ceil(d/4/32)).
+template <int VPL>
+__global__ void __launch_bounds__(kReduceWarps * 32)
+chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
+                    const uint32_t* __restrict__ svals, int64_t total, int vec /* d/4 */,
+                    int64_t padding_idx, int accumulate, float4* __restrict__ dW,
+                    float4* __restrict__ partial /* [n_chunks][2][vec] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t chunk = static_cast<int64_t>(blockIdx.x) * kReduceWarps + warp;
+  const int64_t c0 = chunk * kChunk;
+  if (c0 >= total) return;
+  const int n = static_cast<int>(rg::min64(kChunk, total - c0));
+
+  // lane-parallel decode of this chunk's occurrences (kChunk/32 per lane)
+  constexpr int kPer = kChunk / 32;
+  uint32_t l_key[kPer];
+  int l_site[kPer];
+  int64_t l_row[kPer];
+  float l_coef[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int i = q * 32 + lane;
+    l_key[q] = 0xffffffffu;
+    l_site[q] = 0;
+    l_row[q] = 0;
+    l_coef[q] = 0.f;
+    if (i < n) {
+      l_key[q] = skeys[c0 + i];
+      const int64_t occ = svals[c0 + i];
+      const int s = find_site(st, occ);
+      const int64_t j = occ - st.offset[s];
+      l_site[q] = s;
+      l_row[q] = j / st.group[s];
+      float c = st.coef[s] ? st.coef[s][j] : 1.f;
+      if (st.scale[s]) c *= *st.scale[s];
+      if (st.scale2[s]) c *= *st.scale2[s];
+      l_coef[q] = c;
+    }
+  }
+  const uint32_t first_key = __shfl_sync(0xffffffffu, l_key[0], 0);
+  const uint32_t last_key = __shfl_sync(0xffffffffu, l_key[(n - 1) / 32], (n - 1) & 31);
+  const uint32_t pad = static_cast<uint32_t>(padding_idx);  // -1 -> 0xffffffff never matches
+  const bool has_pad = padding_idx >= 0;
+  if (has_pad && first_key == pad && last_key == pad) return;  // chunk is all padding
+  const bool lead_open = c0 > 0 && skeys[c0 - 1] == first_key;           // run started earlier
+  const bool trail_open = c0 + n < total && skeys[c0 + n] == last_key;   // run continues
+
+  float4 acc[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t cur = first_key;
+  bool cur_is_lead = lead_open;
+
+  constexpr int kBatch = 8;
+  for (int b0 = 0; b0 < n; b0 += kBatch) {
+    float4 x[kBatch][VPL];
+    uint32_t k[kBatch];
+    float cf[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = b0 + u;
+      const int q = (i >> 5) < kPer ? (i >> 5) : kPer - 1;
+      // select the register of slot q (kPer is tiny; keep it branch-free)
+      uint32_t kk = l_key[0];
+      int ss = l_site[0];
+      int64_t rr = l_row[0];
+      float cc = l_coef[0];
+#pragma unroll
+      for (int t = 1; t < kPer; ++t)
+        if (q == t) { kk = l_key[t]; ss = l_site[t]; rr = l_row[t]; cc = l_coef[t]; }
+      k[u] = __shfl_sync(0xffffffffu, kk, i & 31);
+      const int s = __shfl_sync(0xffffffffu, ss, i & 31);
+      const int64_t row = __shfl_sync(0xffffffffu, rr, i & 31);
+      cf[u] = __shfl_sync(0xffffffffu, cc, i & 31);
+      const bool live = i < n && !(has_pad && k[u] == pad);
+      const float4* src = reinterpret_cast<const float4*>(st.X[s]) + row * vec;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = v * 32 + lane;
+        x[u][v] = (live && col < vec) ? ld_stream_f4(src + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = b0 + u;
+      if (i < n) {
+        if (k[u] != cur) {
+          // close the run `cur` (it ends inside this chunk)
+          if (!(has_pad && cur == pad)) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              const int col = v * 32 + lane;
+              if (col < vec) {
+                if (cur_is_lead) {
+                  partial[(chunk * 2 + 0) * vec + col] = acc[v];
+                } else {
+                  float4* dst = dW + static_cast<int64_t>(cur) * vec + col;
+                  float4 o = acc[v];
+                  if (accumulate) {
+                    const float4 old = *dst;
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *dst = o;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          cur = k[u];
+          cur_is_lead = false;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          acc[v].x = fmaf(cf[u], x[u][v].x, acc[v].x);
+          acc[v].y = fmaf(cf[u], x[u][v].y, acc[v].y);
+          acc[v].z = fmaf(cf[u], x[u][v].z, acc[v].z);
+          acc[v].w = fmaf(cf[u], x[u][v].w, acc[v].w);
+        }
+      }
+    }
+  }
+  // close the last run of the chunk
+  if (!(has_pad && cur == pad)) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = v * 32 + lane;
+      if (col < vec) {
+        if (cur_is_lead) {
+          partial[(chunk * 2 + 0) * vec + col] = acc[v];       // continues from the left
+        } else if (trail_open) {
+          partial[(chunk * 2 + 1) * vec + col] = acc[v];       // starts here, continues right
+        } else {
+          float4* dst = dW + static_cast<int64_t>(cur) * vec + col;
+          float4 o = acc[v];
+          if (accumulate) {
+            const float4 old = *dst;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *dst = o;
+        }
+      }
+    }
+  }
+}
+
+// ---- 5. runs that cross chunk edges --------------------------------------------------
+// One warp per chunk edge b (between chunks b-1 and b).  The warp owns the run iff the
+// edge is the FIRST edge that run crosses; it then walks right summing partials.
+template <int VPL>
+__global__ void __launch_bounds__(kReduceWarps * 32)
+span_fixup_kernel(const uint32_t* __restrict__ skeys, int64_t total, int64_t n_chunks, int vec,
+                  int64_t padding_idx, int accumulate, float4* __restrict__ dW,
+                  const float4* __restrict__ partial) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * kReduceWarps + warp + 1;
+  if (b >= n_chunks) return;
+  const uint32_t key = skeys[b * kChunk];
+  if (skeys[b * kChunk - 1] != key) return;                       // no run crosses this edge
+  if (padding_idx >= 0 && key == static_cast<uint32_t>(padding_idx)) return;
+  // run started before chunk b-1?  then an earlier edge owns it
+  if (b >= 2 && skeys[(b - 1) * kChunk] == key && skeys[(b - 1) * kChunk - 1] == key) return;
+
+  float4 acc[VPL];
+  // first piece: chunk b-1.  It is the trailing partial unless the run fills chunk b-1
+  // from its first element *and* crossed edge b-1 (excluded above), so slot 1 always.
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = v * 32 + lane;
+    acc[v] = col < vec ? partial[((b - 1) * 2 + 1) * vec + col] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int64_t c = b;  // invariant: edge c is crossed by this run => chunk c has a leading partial
+  bool done = false;
+  while (!done) {
+    constexpr int kBatch = 8;
+    int cnt = 0;
+    while (cnt < kBatch) {
+      ++cnt;
+      const int64_t e = c + cnt;  // edge index == index of the chunk on its right
+      if (!(e < n_chunks && skeys[e * kChunk] == key && skeys[e * kChunk - 1] == key)) {
+        done = true;
+        break;
+      }
+    }
+    float4 x[kBatch][VPL];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = v * 32 + lane;
+        x[u][v] = (u < cnt && col < vec) ? partial[((c + u) * 2 + 0) * vec + col]
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (u < cnt) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          acc[v].x += x[u][v].x; acc[v].y += x[u][v].y;
+          acc[v].z += x[u][v].z; acc[v].w += x[u][v].w;
+        }
+      }
+    c += cnt;
+  }
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = v * 32 + lane;
+    if (col < vec) {
+      float4* dst = dW + static_cast<int64_t>(key) * vec + col;
+      float4 o = acc[v];
+      if (accumulate) {
+        const float4 old = *dst;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *dst = o;
+    }
+  }
+}
+
+// ---- host orchestration -------------------------------------------------------------
+struct SortPlan {
+  int total_bits, passes, bits_per_pass;
+  int64_t n_tiles;
+  // workspace carve-up (bytes, 256-aligned)
+  int64_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_hist, end;
+};
+
+static SortPlan make_sort_plan(int64_t count, int64_t V1) {
+  SortPlan p;
+  int bits = 1;
+  while ((1ll << bits) < V1) ++bits;
+  p.total_bits = bits;
+  p.passes = (bits + kMaxRadixBits - 1) / kMaxRadixBits;
+  p.bits_per_pass = (bits + p.passes - 1) / p.passes;
+  p.n_tiles = ceil_div(count > 0 ? count : 1, kSortTile);
+  int64_t o = 0;
+  const int64_t kb = align_up(count * 4, 256);
+  p.off_keys_a = o; o += kb;
+  p.off_keys_b = o; o += kb;
+  p.off_vals_a = o; o += kb;
+  p.off_vals_b = o; o += kb;
+  p.off_hist = o; o += align_up(static_cast<int64_t>(kMaxBins) * p.n_tiles * 4, 256);
+  p.end = o;
+  return p;
+}
+
+// Sorts keys (already in ws keys_a).  On return *skeys / *svals point at the sorted arrays.
+// If out_keys64/out_perm64 are given the final pass writes widened copies there instead.
+static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, cudaStream_t st,
+                          uint32_t** skeys, uint32_t** svals, int64_t* out_keys64,
+                          int64_t* out_perm64) {
+  uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws + p.off_keys_a),
+                       reinterpret_cast<uint32_t*>(ws + p.off_keys_b)};
+  uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(ws + p.off_vals_a),
+                       reinterpret_cast<uint32_t*>(ws + p.off_vals_b)};
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + p.off_hist);
+  const unsigned grid = static_cast<unsigned>(p.n_tiles);
+  int cur = 0;
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const int shift = pass * p.bits_per_pass;
+    const int bits = min(p.bits_per_pass, p.total_bits - shift);
+    radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(keys[cur], count, shift, bits, hist);
+    RG_CHECK_LAUNCH("radix_hist");
+    radix_scan_kernel<<<1, 1024, 0, st>>>(hist, (1ll << bits) * p.n_tiles);
+    RG_CHECK_LAUNCH("radix_scan");
+    const bool last = pass == p.passes - 1;
+    if (last && out_perm64) {
+      if (pass == 0)
+        radix_scatter_kernel<true, int64_t><<<grid, kSortThreads, 0, st>>>(
+            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], out_perm64, out_keys64);
+      else
+        radix_scatter_kernel<false, int64_t><<<grid, kSortThreads, 0, st>>>(
+            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], out_perm64, out_keys64);
+    } else {
+      if (pass == 0)
+        radix_scatter_kernel<true, uint32_t><<<grid, kSortThreads, 0, st>>>(
+            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], vals[cur ^ 1], nullptr);
+      else
+        radix_scatter_kernel<false, uint32_t><<<grid, kSortThreads, 0, st>>>(
+            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], vals[cur ^ 1], nullptr);
+    }
+    RG_CHECK_LAUNCH("radix_scatter");
+    cur ^= 1;
+  }
+  *skeys = keys[cur];
+  *svals = vals[cur];
+  return RECGURU_OK;
+}
+
+}  // namespace rg
+
+extern "C" int64_t recguru_sort_ids_workspace_bytes(int64_t count, int64_t V1) {
+  if (count < 0 || V1 <= 0) return RECGURU_E_SHAPE;
+  return rg::make_sort_plan(count, V1).end;
+}
+
+extern "C" int recguru_sort_ids(const int64_t* ids, int64_t count, int64_t V1, int64_t* sorted_ids,
+                                int64_t* perm, void* workspace, int64_t workspace_bytes,
+                                recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(count >= 0 && V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "sort_ids: bad sizes");
+  RG_REQUIRE(count < (1ll << 32), RECGURU_E_UNSUPPORTED, "sort_ids: count must be < 2^32");
+  if (count == 0) return RECGURU_OK;
+  RG_REQUIRE(ids && sorted_ids && perm && workspace, RECGURU_E_SHAPE, "sort_ids: null pointer");
+  const SortPlan p = make_sort_plan(count, V1);
+  RG_REQUIRE(workspace_bytes >= p.end, RECGURU_E_WORKSPACE, "sort_ids: workspace %lld < %lld",
+             (long long)workspace_bytes, (long long)p.end);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  int64_t blocks = rg::min64(ceil_div(count, 256 * 4), kNumSMs * 8);
+  narrow_keys_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      ids, count, reinterpret_cast<uint32_t*>(ws + p.off_keys_a));
+  RG_CHECK_LAUNCH("narrow_keys");
+  uint32_t *sk, *sv;
+  return run_radix_sort(p, ws, count, st, &sk, &sv, sorted_ids, perm);
+}
+
+extern "C" int64_t recguru_embedding_bwd_workspace_bytes(int64_t total_count, int64_t V1,
+                                                         int64_t d) {
+  if (total_count < 0 || V1 <= 0 || d <= 0) return RECGURU_E_SHAPE;
+  const rg::SortPlan p = rg::make_sort_plan(total_count, V1);
+  const int64_t n_chunks = rg::ceil_div(total_count > 0 ? total_count : 1, rg::kChunk);
+  return p.end + rg::align_up(n_chunks * 2 * d * 4, 256);
+}
+
+extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites,
+                                     int64_t d, int64_t V1, int64_t padding_idx, float* dW,
+                                     int zero_fill, void* workspace, int64_t workspace_bytes,
+                                     recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(sites_host && n_sites >= 1 && n_sites <= RECGURU_MAX_SITES, RECGURU_E_SHAPE,
+             "embedding_bwd: n_sites=%d out of range [1,%d]", n_sites, RECGURU_MAX_SITES);
+  RG_REQUIRE(dW && aligned16(dW), RECGURU_E_SHAPE, "embedding_bwd: dW null or unaligned");
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "embedding_bwd: bad V1");
+  RG_REQUIRE(d > 0 && d % 4 == 0 && d <= 512, RECGURU_E_UNSUPPORTED,
+             "embedding_bwd: d=%lld must be a multiple of 4 and <= 512", (long long)d);
+  SiteTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n_sites = n_sites;
+  int64_t total = 0;
+  for (int s = 0; s < n_sites; ++s) {
+    const recguru_lookup_site_t& site = sites_host[s];
+    RG_REQUIRE(site.count >= 0 && site.group >= 1 && site.count % site.group == 0, RECGURU_E_SHAPE,
+               "embedding_bwd: site %d count=%lld group=%lld", s, (long long)site.count,
+               (long long)site.group);
+    RG_REQUIRE(site.count == 0 || (site.ids && site.X && aligned16(site.X)), RECGURU_E_SHAPE,
+               "embedding_bwd: site %d null/unaligned pointer", s);
+    tab.ids[s] = site.ids; tab.X[s] = site.X; tab.coef[s] = site.coef; tab.scale[s] = site.scale; tab.scale2[s] = site.scale2;
+    tab.group[s] = static_cast<int>(site.group);
+    tab.offset[s] = total;
+    total += site.count;
+  }
+  for (int s = n_sites; s <= RECGURU_MAX_SITES; ++s) tab.offset[s] = total;
+  RG_REQUIRE(total < (1ll << 32), RECGURU_E_UNSUPPORTED, "embedding_bwd: total count >= 2^32");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vec = static_cast<int>(d / 4);
+  if (zero_fill) {
+    const int64_t n_vec = V1 * vec;
+    const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 4), kNumSMs * 16);
+    zero_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(dW),
+                                                                    n_vec);
+    RG_CHECK_LAUNCH("zero_fill");
+  }
+  if (total == 0) return RECGURU_OK;
+  const SortPlan p = make_sort_plan(total, V1);
+  const int64_t n_chunks = ceil_div(total, kChunk);
+  const int64_t need = p.end + align_up(n_chunks * 2 * d * 4, 256);
+  RG_REQUIRE(workspace && workspace_bytes >= need, RECGURU_E_WORKSPACE,
+             "embedding_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)need);
+  char* ws = static_cast<char*>(workspace);
+  {
+    const int64_t blocks = rg::min64(ceil_div(total, 256 * 4), kNumSMs * 8);
+    build_keys_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        tab, total, reinterpret_cast<uint32_t*>(ws + p.off_keys_a));
+    RG_CHECK_LAUNCH("build_keys");
+  }
+  uint32_t *sk, *sv;
+  int rc = run_radix_sort(p, ws, total, st, &sk, &sv, nullptr, nullptr);
+  if (rc != RECGURU_OK) return rc;
+  float4* partial = reinterpret_cast<float4*>(ws + p.end);
+  float4* dW4 = reinterpret_cast<float4*>(dW);
+  const int accumulate = zero_fill ? 0 : 1;
+  const unsigned grid = static_cast<unsigned>(ceil_div(n_chunks, kReduceWarps));
+  const int vpl = (vec + 31) / 32;
+#define RG_LAUNCH_REDUCE(V)                                                                   \
+  do {                                                                                        \
+    chunk_reduce_kernel<V><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, total, vec,       \
+                                                               padding_idx, accumulate, dW4,  \
+                                                               partial);                      \
+    RG_CHECK_LAUNCH("chunk_reduce");                                                          \
+    if (n_chunks > 1) {                                                                       \
+      const unsigned g2 = static_cast<unsigned>(ceil_div(n_chunks - 1, kReduceWarps));        \
+      span_fixup_kernel<V><<<g2, kReduceWarps * 32, 0, st>>>(sk, total, n_chunks, vec,        \
+                                                             padding_idx, accumulate, dW4,    \
+                                                             partial);                        \
+      RG_CHECK_LAUNCH("span_fixup");                                                          \
+    }                                                                                         \
+  } while (0)
+  switch (vpl) {
+    case 1: RG_LAUNCH_REDUCE(1); break;
+    case 2: RG_LAUNCH_REDUCE(2); break;
+    case 3: RG_LAUNCH_REDUCE(3); break;
+    case 4: RG_LAUNCH_REDUCE(4); break;
+    default:
+      set_error("embedding_bwd: d=%lld unsupported", (long long)d);
+      return RECGURU_E_UNSUPPORTED;
+  }
+#undef RG_LAUNCH_REDUCE
+  return RECGURU_OK;
+}

@@ -1,0 +1,169 @@
+// Piece 1 (K1): fused item-embedding gather + positional add + pad mask.
+//
+// Replaces  src_emb(ids) -> (x + pe[:, :L]) * mask[..., None]   (before dropout)
+//   /root/reference/GURU/AutoEnc4Rec.py:71-75,:89-93,:176-181,:189-193
+//   /root/reference/GURU/AutoEnc4Rec_cross.py:98-102,:124-128,:156-160
+//   /root/reference/GURU/Transformer/transformer.py:104-106
+//
+// HBM-bound (no reuse except hot rows): per token 8 B id + 4d B row read + 4d B out write
+// + 4 B mask write.  Layout: a CTA owns a contiguous tile of tokens; the tile's ids are
+// loaded once, coalesced, into shared memory (narrowed to int32) together with the 0/1
+// mask; then every thread issues kUnroll independent 128-bit row loads before the first
+// use (memory-level parallelism), adds the PE vector (L2-resident, [L,d]) and streams the
+// result out with 128-bit stores.  Arithmetic is an fp32 add followed by an fp32 multiply
+// by 0/1 (no FMA contraction), i.e. bit-identical to the reference's two ATen kernels.
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kGatherThreads = 256;
+constexpr int kGatherUnroll = 8;
+
+template <int VEC>  // float4 per row (d/4); 0 = runtime
+__global__ void __launch_bounds__(kGatherThreads)
+gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restrict__ ids,
+                      const float4* __restrict__ pe, const float* __restrict__ mask_in,
+                      int64_t pad_index, int64_t n_tokens, int L, int vec_rt,
+                      float4* __restrict__ out, float* __restrict__ mask_out) {
+  extern __shared__ int smem_raw[];
+  const int vec = VEC > 0 ? VEC : vec_rt;
+  const int tok_per_block = (kGatherThreads * kGatherUnroll) / vec;
+  int* s_id = smem_raw;
+  float* s_mask = reinterpret_cast<float*>(smem_raw + tok_per_block);
+
+  const int64_t tok0 = static_cast<int64_t>(blockIdx.x) * tok_per_block;
+  for (int t = threadIdx.x; t < tok_per_block; t += kGatherThreads) {
+    const int64_t tok = tok0 + t;
+    int id = 0;
+    float m = 0.f;
+    if (tok < n_tokens) {
+      const int64_t id64 = ids[tok];
+      id = static_cast<int>(id64);
+      m = mask_in ? mask_in[tok] : (id64 != pad_index ? 1.f : 0.f);
+      if (mask_out) mask_out[tok] = m;
+    }
+    s_id[t] = id;
+    s_mask[t] = m;
+  }
+  __syncthreads();
+
+  float4 row[kGatherUnroll];
+  int tl[kGatherUnroll], vv[kGatherUnroll];
+#pragma unroll
+  for (int u = 0; u < kGatherUnroll; ++u) {
+    const int flat = u * kGatherThreads + threadIdx.x;
+    tl[u] = flat / vec;
+    vv[u] = flat - tl[u] * vec;
+    if (tok0 + tl[u] < n_tokens) {
+      row[u] = __ldg(weight + static_cast<int64_t>(s_id[tl[u]]) * vec + vv[u]);
+    }
+  }
+  if (pe != nullptr) {
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const int64_t tok = tok0 + tl[u];
+      if (tok < n_tokens) {
+        const int l = static_cast<int>(tok % L);
+        const float4 p = __ldg(pe + static_cast<int64_t>(l) * vec + vv[u]);
+        const float m = s_mask[tl[u]];
+        float4 r = row[u];
+        r.x = __fmul_rn(__fadd_rn(r.x, p.x), m);
+        r.y = __fmul_rn(__fadd_rn(r.y, p.y), m);
+        r.z = __fmul_rn(__fadd_rn(r.z, p.z), m);
+        r.w = __fmul_rn(__fadd_rn(r.w, p.w), m);
+        st_stream_f4(out + tok * vec + vv[u], r);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const int64_t tok = tok0 + tl[u];
+      if (tok < n_tokens) st_stream_f4(out + tok * vec + vv[u], row[u]);
+    }
+  }
+}
+
+// PositionalEncoding.forward(x, mask) on an already materialised x.
+__global__ void __launch_bounds__(256)
+pe_mask_kernel(const float4* __restrict__ x, const float4* __restrict__ pe,
+               const float* __restrict__ mask, int64_t n_vec, int vec, int L,
+               float4* __restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += stride) {
+    const int64_t tok = i / vec;
+    const int v = static_cast<int>(i - tok * vec);
+    const int l = static_cast<int>(tok % L);
+    float4 r = ld_stream_f4(x + i);
+    const float4 p = __ldg(pe + static_cast<int64_t>(l) * vec + v);
+    const float m = __ldg(mask + tok);
+    r.x = __fmul_rn(__fadd_rn(r.x, p.x), m);
+    r.y = __fmul_rn(__fadd_rn(r.y, p.y), m);
+    r.z = __fmul_rn(__fadd_rn(r.z, p.z), m);
+    r.w = __fmul_rn(__fadd_rn(r.w, p.w), m);
+    st_stream_f4(out + i, r);
+  }
+}
+
+}  // namespace rg
+
+extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d,
+                                      const int64_t* ids, int64_t n_tokens, int64_t L,
+                                      const float* pe, const float* mask_in, int64_t pad_index,
+                                      float* out, float* mask_out, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(weight && ids && out, RECGURU_E_SHAPE, "gather_pe_mask: null pointer");
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31) && n_tokens >= 0 && L > 0, RECGURU_E_SHAPE,
+             "gather_pe_mask: bad sizes V1=%lld n_tokens=%lld L=%lld", (long long)V1,
+             (long long)n_tokens, (long long)L);
+  RG_REQUIRE(d > 0 && d % 4 == 0 && d <= 4096, RECGURU_E_UNSUPPORTED,
+             "gather_pe_mask: d=%lld must be a multiple of 4 and <= 4096", (long long)d);
+  RG_REQUIRE(aligned16(weight) && aligned16(out) && aligned16(pe), RECGURU_E_SHAPE,
+             "gather_pe_mask: weight/pe/out must be 16-byte aligned");
+  if (n_tokens == 0) return RECGURU_OK;
+  const int vec = static_cast<int>(d / 4);
+  RG_REQUIRE((kGatherThreads * kGatherUnroll) % vec == 0, RECGURU_E_UNSUPPORTED,
+             "gather_pe_mask: d/4=%d must divide %d", vec, kGatherThreads * kGatherUnroll);
+  const int tok_per_block = (kGatherThreads * kGatherUnroll) / vec;
+  const int64_t blocks = ceil_div(n_tokens, tok_per_block);
+  const size_t smem = static_cast<size_t>(tok_per_block) * 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float4* w4 = reinterpret_cast<const float4*>(weight);
+  const float4* pe4 = reinterpret_cast<const float4*>(pe);
+  float4* o4 = reinterpret_cast<float4*>(out);
+#define RG_LAUNCH_GATHER(V)                                                              \
+  gather_pe_mask_kernel<V><<<static_cast<unsigned>(blocks), kGatherThreads, smem, st>>>( \
+      w4, ids, pe4, mask_in, pad_index, n_tokens, static_cast<int>(L), vec, o4, mask_out)
+  switch (vec) {
+    case 8: RG_LAUNCH_GATHER(8); break;
+    case 16: RG_LAUNCH_GATHER(16); break;
+    case 32: RG_LAUNCH_GATHER(32); break;
+    case 64: RG_LAUNCH_GATHER(64); break;
+    default: RG_LAUNCH_GATHER(0); break;
+  }
+#undef RG_LAUNCH_GATHER
+  RG_CHECK_LAUNCH("gather_pe_mask");
+  return RECGURU_OK;
+}
+
+extern "C" int recguru_pe_mask(const float* x, const float* pe, const float* mask,
+                               int64_t n_tokens, int64_t L, int64_t d, float* out,
+                               recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(x && pe && mask && out, RECGURU_E_SHAPE, "pe_mask: null pointer");
+  RG_REQUIRE(d > 0 && d % 4 == 0, RECGURU_E_UNSUPPORTED, "pe_mask: d=%lld must be a multiple of 4",
+             (long long)d);
+  RG_REQUIRE(aligned16(x) && aligned16(pe) && aligned16(out), RECGURU_E_SHAPE,
+             "pe_mask: x/pe/out must be 16-byte aligned");
+  RG_REQUIRE(n_tokens >= 0 && L > 0, RECGURU_E_SHAPE, "pe_mask: bad sizes");
+  if (n_tokens == 0) return RECGURU_OK;
+  const int vec = static_cast<int>(d / 4);
+  const int64_t n_vec = n_tokens * vec;
+  int64_t blocks = ceil_div(n_vec, 256 * 4);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  pe_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pe), mask, n_vec, vec,
+      static_cast<int>(L), reinterpret_cast<float4*>(out));
+  RG_CHECK_LAUNCH("pe_mask");
+  return RECGURU_OK;
+}

@@ -1,0 +1,409 @@
+// Piece 3 (K3): sampled-negative scoring as one fused gather-dot-loss kernel (+ backward).
+//
+// Replaces, per training step,
+//   src_emb(dec_out).view(-1,L,1,d) ; src_emb(n_items).view(-1,L,K,d) ; 2x batched matmul ;
+//   loss module
+//   /root/reference/GURU/AutoEnc4Rec.py:115-131,:219-227
+//   /root/reference/GURU/AutoEnc4Rec_cross.py:203-215 ; tools/utils.py:103-126
+//   /root/reference/GURU/tools/lossfunctions.py:36-49 (SampledCrossEntropyLoss, label 0),
+//                                               :56-72 (BPRLoss), :79-96 (BPRLoss_sas)
+//
+// HBM-bound: per position 4d B (h) + (1+K)(8 + 4d) B (ids + rows) + 4 B mask read,
+// 4(1+K) B written; 2d(1+K) flop.  The [B,L,K,d] gathered-row intermediate of the
+// reference is never materialised.  One warp per position; rows narrower than a warp's
+// 512 B (d < 128) are handled by sub-warp groups so that all 32 lanes keep loading.
+// Loss reduction is a fixed-order two-level sum (warp -> CTA -> one finalising CTA), so
+// the scalar is bit-reproducible run to run.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kScoreWarps = 8;
+constexpr int kPosPerWarp = 4;
+constexpr int kPosPerBlock = kScoreWarps * kPosPerWarp;
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Loss + unnormalised derivatives of one position.  `score` holds candidate `lane`
+// (lane 0 = positive, lanes 1..K = negatives); result identical in all lanes.
+__device__ __forceinline__ float warp_position_loss(int kind, float score, int K, int lane,
+                                                    float* dscore /* this lane's d l/d score */) {
+  const bool is_neg = lane >= 1 && lane <= K;
+  const float p = __shfl_sync(0xffffffffu, score, 0);
+  if (kind == RECGURU_LOSS_SCE) {
+    float m = (lane <= K) ? score : -CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e = (lane <= K) ? expf(score - m) : 0.f;
+    const float sum = warp_sum(e);
+    *dscore = (lane <= K) ? (e / sum - (lane == 0 ? 1.f : 0.f)) : 0.f;
+    return (m + logf(sum)) - p;
+  }
+  const float nbar = warp_sum(is_neg ? score : 0.f) / static_cast<float>(K);
+  if (kind == RECGURU_LOSS_BPR) {
+    const float sg = sigmoidf_ref(p - nbar);
+    *dscore = lane == 0 ? (sg - 1.f) : (is_neg ? (1.f - sg) / static_cast<float>(K) : 0.f);
+    return -logf(sg);
+  }
+  // RECGURU_LOSS_BPR_SAS
+  const float a = sigmoidf_ref(p), b = sigmoidf_ref(nbar);
+  const float ya = a + 1e-24f, yb = (1.f - b) + 1e-24f;
+  const float dp = -(a * (1.f - a)) / ya;
+  const float dn = (b * (1.f - b)) / yb / static_cast<float>(K);
+  *dscore = lane == 0 ? dp : (is_neg ? dn : 0.f);
+  return -(logf(ya) + logf(yb));
+}
+
+template <int VEC>  // float4 per row
+__global__ void __launch_bounds__(kScoreWarps * 32)
+sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ weight,
+                         const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+                         int64_t n_pos, int K, const float* __restrict__ mask, int kind,
+                         float* __restrict__ p_out, float* __restrict__ n_out,
+                         float* __restrict__ dp_unit, float* __restrict__ dn_unit,
+                         float2* __restrict__ block_partial) {
+  constexpr int LANES = VEC < 32 ? VEC : 32;  // lanes cooperating on one row
+  constexpr int G = 32 / LANES;               // rows in flight per warp step
+  constexpr int VPL = VEC / LANES;            // float4 per lane per row
+  constexpr int UN = 8 / G > 0 ? 8 / G : 1;   // unroll: 8 rows in flight per warp
+  __shared__ float2 s_part[kScoreWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LANES, sub = lane % LANES;
+  const int C = K + 1;
+  float loss_acc = 0.f, mask_acc = 0.f;
+
+  for (int q = 0; q < kPosPerWarp; ++q) {
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kPosPerWarp + q;
+    if (i >= n_pos) break;  // warp-uniform
+    int64_t my_id = 0;
+    if (lane == 0) my_id = pos[i];
+    else if (lane <= K) my_id = neg[i * K + (lane - 1)];
+    float4 hv[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) hv[v] = ld_stream_f4(h + i * VEC + v * LANES + sub);
+
+    float score = 0.f;
+    for (int c0 = 0; c0 < C; c0 += G * UN) {
+      float4 w[UN][VPL];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int c = c0 + u * G + g;
+        const int64_t id = __shfl_sync(0xffffffffu, my_id, c < C ? c : 0);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        float acc = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          acc = fmaf(hv[v].x, w[u][v].x, acc);
+          acc = fmaf(hv[v].y, w[u][v].y, acc);
+          acc = fmaf(hv[v].z, w[u][v].z, acc);
+          acc = fmaf(hv[v].w, w[u][v].w, acc);
+        }
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+#pragma unroll
+        for (int gg = 0; gg < G; ++gg) {
+          const float v = __shfl_sync(0xffffffffu, acc, gg * LANES);
+          if (lane == c0 + u * G + gg) score = v;
+        }
+      }
+    }
+    if (p_out && lane == 0) p_out[i] = score;
+    if (n_out && lane >= 1 && lane <= K) n_out[i * K + (lane - 1)] = score;
+    if (kind >= 0) {
+      const float m = mask ? __ldg(mask + i) : 1.f;
+      float ds;
+      const float l = warp_position_loss(kind, score, K, lane, &ds);
+      loss_acc += l * m;
+      mask_acc += m;
+      if (dp_unit && lane == 0) dp_unit[i] = ds * m;
+      if (dn_unit && lane >= 1 && lane <= K) dn_unit[i * K + (lane - 1)] = ds * m;
+    }
+  }
+  if (kind >= 0) {
+    if (lane == 0) s_part[warp] = make_float2(loss_acc, mask_acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < kScoreWarps; ++w) { t.x += s_part[w].x; t.y += s_part[w].y; }
+      block_partial[blockIdx.x] = t;
+    }
+  }
+}
+
+// Loss from already computed logits: one thread per position.
+__global__ void __launch_bounds__(256)
+sampled_loss_kernel(const float* __restrict__ p, const float* __restrict__ n, int64_t n_pos, int K,
+                    const float* __restrict__ mask, int kind, float* __restrict__ dp_unit,
+                    float* __restrict__ dn_unit, float2* __restrict__ block_partial) {
+  __shared__ float2 s_part[256 / 32];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  float l = 0.f, m = 0.f;
+  if (i < n_pos) {
+    m = mask ? mask[i] : 1.f;
+    const float pv = p[i];
+    const float* nr = n + i * K;
+    float dpv = 0.f;
+    if (kind == RECGURU_LOSS_SCE) {
+      float mx = pv;
+      for (int k = 0; k < K; ++k) mx = fmaxf(mx, nr[k]);
+      const float e0 = expf(pv - mx);
+      float sum = e0;
+      for (int k = 0; k < K; ++k) sum += expf(nr[k] - mx);
+      l = (mx + logf(sum)) - pv;
+      dpv = e0 / sum - 1.f;
+      if (dn_unit)
+        for (int k = 0; k < K; ++k) dn_unit[i * K + k] = expf(nr[k] - mx) / sum * m;
+    } else {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s += nr[k];
+      const float nbar = s / static_cast<float>(K);
+      float dnv;
+      if (kind == RECGURU_LOSS_BPR) {
+        const float sg = sigmoidf_ref(pv - nbar);
+        l = -logf(sg);
+        dpv = sg - 1.f;
+        dnv = (1.f - sg) / static_cast<float>(K);
+      } else {
+        const float a = sigmoidf_ref(pv), b = sigmoidf_ref(nbar);
+        const float ya = a + 1e-24f, yb = (1.f - b) + 1e-24f;
+        l = -(logf(ya) + logf(yb));
+        dpv = -(a * (1.f - a)) / ya;
+        dnv = (b * (1.f - b)) / yb / static_cast<float>(K);
+      }
+      if (dn_unit)
+        for (int k = 0; k < K; ++k) dn_unit[i * K + k] = dnv * m;
+    }
+    if (dp_unit) dp_unit[i] = dpv * m;
+  }
+  float lm = l * m;
+  // fixed-order CTA reduction: lanes by shuffle tree, warps sequentially
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lm += __shfl_xor_sync(0xffffffffu, lm, o);
+    m += __shfl_xor_sync(0xffffffffu, m, o);
+  }
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = make_float2(lm, m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float2 t = make_float2(0.f, 0.f);
+    for (int w = 0; w < 256 / 32; ++w) { t.x += s_part[w].x; t.y += s_part[w].y; }
+    block_partial[blockIdx.x] = t;
+  }
+}
+
+// loss_out[0] = sum(l*m)/sum(m);  loss_out[1] = 1/sum(m)  (the factor still missing from
+// dp_unit/dn_unit; consumers multiply it in through their `scale2` argument).
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(const float2* __restrict__ block_partial, int64_t n_blocks,
+                     float* __restrict__ loss_out) {
+  __shared__ float2 s[256];
+  float2 t = make_float2(0.f, 0.f);
+  for (int64_t b = threadIdx.x; b < n_blocks; b += 256) {
+    const float2 v = block_partial[b];
+    t.x += v.x; t.y += v.y;
+  }
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s[threadIdx.x].x += s[threadIdx.x + o].x; s[threadIdx.x].y += s[threadIdx.x + o].y; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    loss_out[0] = s[0].x / s[0].y;
+    loss_out[1] = 1.f / s[0].y;
+  }
+}
+
+// dh[i,:] = s * (dp[i] * W[pos[i],:] + sum_k dn[i,k] * W[neg[i,k],:])
+template <int VEC>
+__global__ void __launch_bounds__(kScoreWarps * 32)
+sampled_score_bwd_dh_kernel(const float* __restrict__ dp, const float* __restrict__ dn,
+                            const float* __restrict__ scale, const float* __restrict__ scale2,
+                            const float4* __restrict__ weight, const int64_t* __restrict__ pos,
+                            const int64_t* __restrict__ neg, int64_t n_pos, int K,
+                            float4* __restrict__ dh) {
+  constexpr int LANES = VEC < 32 ? VEC : 32;
+  constexpr int G = 32 / LANES;
+  constexpr int VPL = VEC / LANES;
+  constexpr int UN = 8 / G > 0 ? 8 / G : 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LANES, sub = lane % LANES;
+  const int C = K + 1;
+  float s = scale ? __ldg(scale) : 1.f;
+  if (scale2) s *= __ldg(scale2);
+  for (int q = 0; q < kPosPerWarp; ++q) {
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kPosPerWarp + q;
+    if (i >= n_pos) break;
+    int64_t my_id = 0;
+    float my_c = 0.f;
+    if (lane == 0) { my_id = pos[i]; my_c = dp[i] * s; }
+    else if (lane <= K) { my_id = neg[i * K + (lane - 1)]; my_c = dn[i * K + (lane - 1)] * s; }
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < C; c0 += G * UN) {
+      float4 w[UN][VPL];
+      float cf[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int c = c0 + u * G + g;
+        const int src = c < C ? c : 0;
+        const int64_t id = __shfl_sync(0xffffffffu, my_id, src);
+        cf[u] = __shfl_sync(0xffffffffu, my_c, src);
+        if (c >= C) cf[u] = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          acc[v].x = fmaf(cf[u], w[u][v].x, acc[v].x);
+          acc[v].y = fmaf(cf[u], w[u][v].y, acc[v].y);
+          acc[v].z = fmaf(cf[u], w[u][v].z, acc[v].z);
+          acc[v].w = fmaf(cf[u], w[u][v].w, acc[v].w);
+        }
+    }
+    // combine the G sub-warp groups (fixed order: xor tree over group index)
+#pragma unroll
+    for (int o = 16; o >= LANES; o >>= 1)
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+        acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+        acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+        acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+      }
+    if (g == 0) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) st_stream_f4(dh + i * VEC + v * LANES + sub, acc[v]);
+    }
+  }
+}
+
+static int check_common(const char* who, int64_t V1, int64_t d, int64_t n_pos, int64_t K) {
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31) && n_pos >= 0, RECGURU_E_SHAPE, "%s: bad sizes", who);
+  RG_REQUIRE(d == 32 || d == 64 || d == 128 || d == 256, RECGURU_E_UNSUPPORTED,
+             "%s: d=%lld not in {32,64,128,256}", who, (long long)d);
+  RG_REQUIRE(K >= 1 && K <= 31, RECGURU_E_UNSUPPORTED, "%s: K=%lld not in [1,31]", who,
+             (long long)K);
+  return RECGURU_OK;
+}
+
+}  // namespace rg
+
+extern "C" int64_t recguru_sampled_workspace_bytes(int64_t n_pos, int64_t K) {
+  (void)K;
+  if (n_pos < 0) return RECGURU_E_SHAPE;
+  // block partials of whichever kernel uses more CTAs (kPosPerBlock = 32 < 256)
+  return rg::align_up((rg::ceil_div(n_pos > 0 ? n_pos : 1, rg::kPosPerBlock) + 1) * 8, 256);
+}
+
+extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weight, int64_t V1,
+                                              int64_t d, const int64_t* pos, const int64_t* neg,
+                                              int64_t n_pos, int64_t K, const float* mask, int kind,
+                                              float* p_out, float* n_out, float* loss_out,
+                                              float* dp_unit, float* dn_unit, void* workspace,
+                                              int64_t workspace_bytes, recguru_stream_t stream) {
+  using namespace rg;
+  int rc = check_common("sampled_score_loss_fwd", V1, d, n_pos, K);
+  if (rc) return rc;
+  RG_REQUIRE(h && weight && pos && neg, RECGURU_E_SHAPE, "sampled_score_loss_fwd: null pointer");
+  RG_REQUIRE(aligned16(h) && aligned16(weight), RECGURU_E_SHAPE,
+             "sampled_score_loss_fwd: h/weight must be 16-byte aligned");
+  RG_REQUIRE(kind <= RECGURU_LOSS_SCE, RECGURU_E_UNSUPPORTED, "sampled_score_loss_fwd: kind=%d", kind);
+  RG_REQUIRE(kind < 0 || loss_out, RECGURU_E_SHAPE, "sampled_score_loss_fwd: loss_out is null");
+  if (n_pos == 0) return RECGURU_OK;
+  const int64_t blocks = ceil_div(n_pos, kPosPerBlock);
+  if (kind >= 0)
+    RG_REQUIRE(workspace && workspace_bytes >= blocks * 8, RECGURU_E_WORKSPACE,
+               "sampled_score_loss_fwd: workspace %lld < %lld", (long long)workspace_bytes,
+               (long long)(blocks * 8));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* part = static_cast<float2*>(workspace);
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  const float4* w4 = reinterpret_cast<const float4*>(weight);
+#define RG_LAUNCH_SCORE(V)                                                                     \
+  sampled_score_fwd_kernel<V><<<static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st>>>(     \
+      h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, \
+      part)
+  switch (d / 4) {
+    case 8: RG_LAUNCH_SCORE(8); break;
+    case 16: RG_LAUNCH_SCORE(16); break;
+    case 32: RG_LAUNCH_SCORE(32); break;
+    default: RG_LAUNCH_SCORE(64); break;
+  }
+#undef RG_LAUNCH_SCORE
+  RG_CHECK_LAUNCH("sampled_score_fwd");
+  if (kind >= 0) {
+    loss_finalize_kernel<<<1, 256, 0, st>>>(part, blocks, loss_out);
+    RG_CHECK_LAUNCH("loss_finalize");
+  }
+  return RECGURU_OK;
+}
+
+extern "C" int recguru_sampled_loss_fwd(const float* p, const float* n, int64_t n_pos, int64_t K,
+                                        const float* mask, int kind, float* loss_out,
+                                        float* dp_unit, float* dn_unit, void* workspace,
+                                        int64_t workspace_bytes, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(p && n && loss_out, RECGURU_E_SHAPE, "sampled_loss_fwd: null pointer");
+  RG_REQUIRE(n_pos > 0, RECGURU_E_SHAPE, "sampled_loss_fwd: n_pos must be > 0");
+  RG_REQUIRE(K >= 1 && K <= 4096, RECGURU_E_UNSUPPORTED, "sampled_loss_fwd: K=%lld", (long long)K);
+  RG_REQUIRE(kind >= 0 && kind <= RECGURU_LOSS_SCE, RECGURU_E_UNSUPPORTED,
+             "sampled_loss_fwd: kind=%d", kind);
+  const int64_t blocks = ceil_div(n_pos, 256);
+  RG_REQUIRE(workspace && workspace_bytes >= blocks * 8, RECGURU_E_WORKSPACE,
+             "sampled_loss_fwd: workspace %lld < %lld", (long long)workspace_bytes,
+             (long long)(blocks * 8));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* part = static_cast<float2*>(workspace);
+  sampled_loss_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      p, n, n_pos, static_cast<int>(K), mask, kind, dp_unit, dn_unit, part);
+  RG_CHECK_LAUNCH("sampled_loss");
+  loss_finalize_kernel<<<1, 256, 0, st>>>(part, blocks, loss_out);
+  RG_CHECK_LAUNCH("loss_finalize");
+  return RECGURU_OK;
+}
+
+extern "C" int recguru_sampled_score_bwd_dh(const float* dp, const float* dn, const float* scale,
+                                            const float* scale2, const float* weight, int64_t V1,
+                                            int64_t d, const int64_t* pos, const int64_t* neg,
+                                            int64_t n_pos, int64_t K, float* dh,
+                                            recguru_stream_t stream) {
+  using namespace rg;
+  int rc = check_common("sampled_score_bwd_dh", V1, d, n_pos, K);
+  if (rc) return rc;
+  RG_REQUIRE(dp && dn && weight && pos && neg && dh, RECGURU_E_SHAPE,
+             "sampled_score_bwd_dh: null pointer");
+  RG_REQUIRE(aligned16(weight) && aligned16(dh), RECGURU_E_SHAPE,
+             "sampled_score_bwd_dh: weight/dh must be 16-byte aligned");
+  if (n_pos == 0) return RECGURU_OK;
+  const int64_t blocks = ceil_div(n_pos, kPosPerBlock);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float4* w4 = reinterpret_cast<const float4*>(weight);
+  float4* dh4 = reinterpret_cast<float4*>(dh);
+#define RG_LAUNCH_DH(V)                                                                        \
+  sampled_score_bwd_dh_kernel<V><<<static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st>>>(  \
+      dp, dn, scale, scale2, w4, pos, neg, n_pos, static_cast<int>(K), dh4)
+  switch (d / 4) {
+    case 8: RG_LAUNCH_DH(8); break;
+    case 16: RG_LAUNCH_DH(16); break;
+    case 32: RG_LAUNCH_DH(32); break;
+    default: RG_LAUNCH_DH(64); break;
+  }
+#undef RG_LAUNCH_DH
+  RG_CHECK_LAUNCH("sampled_score_bwd_dh");
+  return RECGURU_OK;
+}

@@ -1,0 +1,704 @@
+"""torch.library custom ops (namespace ``recguru``) over the C ABI in include/recguru_b200.h.
+
+Host-side mirror of the reference's PyTorch surface for the embedding-and-scoring hot path
+(SURVEY.md section 8b).  Every op is CUDA-only: there is no CPU implementation, no Triton,
+no multi-backend dispatch.  PyTorch is used for device memory, streams and autograd glue.
+
+Raw layer   : ``raw_*`` functions -- validate, allocate outputs/scratch with torch's caching
+              allocator, pass raw device pointers to the shared library.
+Op layer    : ``torch.ops.recguru.*`` with register_fake (shape inference) and
+              register_autograd where the reference op is differentiable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LOSS_KINDS, LookupSite, check
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: Tensor, dtype: torch.dtype, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"recguru: {name} must be a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"recguru: {name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# raw layer
+# --------------------------------------------------------------------------------------
+def raw_gather_pe_mask(weight: Tensor, ids: Tensor, pe: Optional[Tensor], pad_index: int,
+                       mask_in: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                       mask_out: Optional[Tensor] = None, want_mask: bool = True
+                       ) -> Tuple[Tensor, Optional[Tensor]]:
+    """out[..., :] = (weight[ids] + pe[l]) * mask ; mask = (ids != pad_index) unless mask_in.
+
+    Reference: AutoEnc4Rec.py:71-75,:89-93,:176-181 ; Transformer/transformer.py:104-106.
+    ``pe`` may be ``[>=L, d]`` or the reference's ``[1, max_len, d]`` buffer; ``None`` gives a
+    plain gather (S1/S2/E1 sites)."""
+    lib = _lib.load()
+    weight = _need(weight, torch.float32, "weight")
+    ids = _need(ids, torch.int64, "ids")
+    V1, d = weight.shape
+    L = ids.shape[-1] if ids.dim() >= 1 else 1
+    n_tokens = ids.numel()
+    if pe is not None:
+        pe = _need(pe, torch.float32, "pe")
+        if pe.dim() == 3:
+            pe = pe[0]
+        if pe.shape[0] < L or pe.shape[1] != d:
+            raise RuntimeError(f"recguru: pe shape {tuple(pe.shape)} incompatible with L={L}, d={d}")
+    if mask_in is not None:
+        mask_in = _need(mask_in, torch.float32, "mask")
+        if mask_in.numel() != n_tokens:
+            raise RuntimeError("recguru: mask must have one entry per token")
+    if out is None:
+        out = torch.empty(*ids.shape, d, dtype=torch.float32, device=weight.device)
+    if mask_out is None and want_mask and pe is not None:
+        mask_out = torch.empty(ids.shape, dtype=torch.float32, device=weight.device)
+    check(lib.recguru_gather_pe_mask(_ptr(weight), V1, d, _ptr(ids), n_tokens, max(L, 1), _ptr(pe),
+                                     _ptr(mask_in), int(pad_index), _ptr(out), _ptr(mask_out),
+                                     _stream()), "gather_pe_mask")
+    return out, mask_out
+
+
+def raw_pe_mask(x: Tensor, pe: Tensor, mask: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """PositionalEncoding.forward before dropout (Transformer/transformer.py:104-106)."""
+    lib = _lib.load()
+    x = _need(x, torch.float32, "x")
+    pe = _need(pe, torch.float32, "pe")
+    mask = _need(mask, torch.float32, "mask")
+    if pe.dim() == 3:
+        pe = pe[0]
+    L, d = x.shape[-2], x.shape[-1]
+    n_tokens = x.numel() // d
+    if mask.numel() != n_tokens or pe.shape[0] < L or pe.shape[1] != d:
+        raise RuntimeError("recguru: pe_mask shape mismatch")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.recguru_pe_mask(_ptr(x), _ptr(pe), _ptr(mask), n_tokens, L, d, _ptr(out), _stream()),
+          "pe_mask")
+    return out
+
+
+class Site:
+    """One lookup site of the table backward: dW[ids[j]] += coef[j]*scale*scale2 * X[j//group]."""
+    __slots__ = ("ids", "X", "coef", "scale", "scale2", "group")
+
+    def __init__(self, ids: Tensor, X: Tensor, coef: Optional[Tensor] = None,
+                 scale: Optional[Tensor] = None, scale2: Optional[Tensor] = None, group: int = 1):
+        self.ids, self.X, self.coef, self.scale, self.scale2, self.group = ids, X, coef, scale, scale2, group
+
+
+def embedding_bwd_workspace_bytes(total: int, V1: int, d: int) -> int:
+    return int(_lib.load().recguru_embedding_bwd_workspace_bytes(total, V1, d))
+
+
+def raw_embedding_bwd(sites: Sequence[Site], V1: int, d: int, padding_idx: int = -1,
+                      out: Optional[Tensor] = None, zero_fill: bool = True,
+                      workspace: Optional[Tensor] = None) -> Tensor:
+    """Deterministic dense table gradient over all lookup sites in one pass.
+
+    Replaces ATen embedding_dense_backward per site + the dense accumulation
+    (train_auto.py:124).  ``padding_idx=-1`` means none (cross-domain tables,
+    AutoEnc4Rec_cross.py:32,:35)."""
+    lib = _lib.load()
+    if not 1 <= len(sites) <= _lib.MAX_SITES:
+        raise RuntimeError(f"recguru: 1..{_lib.MAX_SITES} sites supported, got {len(sites)}")
+    arr = (LookupSite * len(sites))()
+    keep = []
+    total = 0
+    dev = sites[0].X.device
+    for i, s in enumerate(sites):
+        ids = _need(s.ids, torch.int64, "site.ids")
+        X = _need(s.X, torch.float32, "site.X")
+        coef = None if s.coef is None else _need(s.coef, torch.float32, "site.coef")
+        scale = None if s.scale is None else _need(s.scale, torch.float32, "site.scale")
+        scale2 = None if s.scale2 is None else _need(s.scale2, torch.float32, "site.scale2")
+        n = ids.numel()
+        if n % s.group or X.numel() != (n // s.group) * d:
+            raise RuntimeError(f"recguru: site {i}: ids {n}, group {s.group}, X {tuple(X.shape)}, d {d}")
+        if coef is not None and coef.numel() != n:
+            raise RuntimeError(f"recguru: site {i}: coef must have one entry per id")
+        keep += [ids, X, coef, scale, scale2]
+        arr[i] = LookupSite(_ptr(ids), n, _ptr(X), _ptr(coef), _ptr(scale), _ptr(scale2), s.group)
+        total += n
+    if out is None:
+        out = torch.empty(V1, d, dtype=torch.float32, device=dev)
+    else:
+        out = _need(out, torch.float32, "out")
+        if tuple(out.shape) != (V1, d):
+            raise RuntimeError("recguru: out must be [V1, d]")
+    need = embedding_bwd_workspace_bytes(total, V1, d)
+    if workspace is None or workspace.numel() < need:
+        workspace = _workspace(need, dev)
+    check(lib.recguru_embedding_bwd(arr, len(sites), d, V1, int(padding_idx), _ptr(out),
+                                    1 if zero_fill else 0, _ptr(workspace), workspace.numel(),
+                                    _stream()), "embedding_bwd")
+    return out
+
+
+def raw_sort_ids(ids: Tensor, V1: int) -> Tuple[Tensor, Tensor]:
+    """Stable ascending sort of ids; returns (sorted_ids, perm) == torch.sort(ids, stable=True)."""
+    lib = _lib.load()
+    ids = _need(ids, torch.int64, "ids").reshape(-1)
+    n = ids.numel()
+    sorted_ids = torch.empty_like(ids)
+    perm = torch.empty_like(ids)
+    ws = _workspace(lib.recguru_sort_ids_workspace_bytes(n, V1), ids.device)
+    check(lib.recguru_sort_ids(_ptr(ids), n, V1, _ptr(sorted_ids), _ptr(perm), _ptr(ws), ws.numel(),
+                               _stream()), "sort_ids")
+    return sorted_ids, perm
+
+
+def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
+                           mask: Optional[Tensor], kind: Optional[str], want_grads: bool = True,
+                           bufs: Optional[dict] = None):
+    """p = h.W[pos], n = h.W[neg]; loss per tools/lossfunctions.py:36-49,:56-72,:79-96.
+
+    Returns (p [..,1], n [..,K], loss_aux [2] or None, dp_unit, dn_unit).  loss_aux[0] is the
+    loss, loss_aux[1] = 1/sum(mask)."""
+    lib = _lib.load()
+    h = _need(h, torch.float32, "h")
+    weight = _need(weight, torch.float32, "weight")
+    pos = _need(pos, torch.int64, "pos")
+    neg = _need(neg, torch.int64, "neg")
+    V1, d = weight.shape
+    n_pos = pos.numel()
+    if n_pos == 0 or neg.numel() % n_pos:
+        raise RuntimeError("recguru: neg must hold K ids per position")
+    K = neg.numel() // n_pos
+    if h.numel() != n_pos * d:
+        raise RuntimeError(f"recguru: h has {h.numel()} elements, expected {n_pos}*{d}")
+    if mask is not None:
+        mask = _need(mask, torch.float32, "mask")
+        if mask.numel() != n_pos:
+            raise RuntimeError("recguru: mask must have one entry per position")
+    dev = h.device
+    b = bufs or {}
+    p = b.get("p") if "p" in b else torch.empty(*pos.shape, 1, dtype=torch.float32, device=dev)
+    n = b.get("n") if "n" in b else torch.empty(*pos.shape, K, dtype=torch.float32, device=dev)
+    kind_i = -1 if kind is None else LOSS_KINDS[kind]
+    aux = dp = dn = ws = None
+    if kind is not None:
+        aux = b.get("aux") if "aux" in b else torch.empty(2, dtype=torch.float32, device=dev)
+        if want_grads:
+            dp = b.get("dp") if "dp" in b else torch.empty(n_pos, dtype=torch.float32, device=dev)
+            dn = b.get("dn") if "dn" in b else torch.empty(n_pos, K, dtype=torch.float32, device=dev)
+        ws = b.get("ws") if "ws" in b else _workspace(lib.recguru_sampled_workspace_bytes(n_pos, K), dev)
+    check(lib.recguru_sampled_score_loss_fwd(_ptr(h), _ptr(weight), V1, d, _ptr(pos), _ptr(neg), n_pos,
+                                             K, _ptr(mask), kind_i, _ptr(p), _ptr(n), _ptr(aux),
+                                             _ptr(dp), _ptr(dn), _ptr(ws),
+                                             0 if ws is None else ws.numel(), _stream()),
+          "sampled_score_loss_fwd")
+    return p, n, aux, dp, dn
+
+
+def raw_sampled_loss(p: Tensor, n: Tensor, mask: Optional[Tensor], kind: str):
+    """Loss from logits only.  Returns (loss_aux [2], dp_unit [n_pos], dn_unit [n_pos, K])."""
+    lib = _lib.load()
+    p = _need(p, torch.float32, "p_logit")
+    n = _need(n, torch.float32, "n_logit")
+    n_pos = p.numel()
+    if n_pos == 0 or n.numel() % n_pos:
+        raise RuntimeError("recguru: n_logit must hold K logits per position")
+    K = n.numel() // n_pos
+    if mask is not None:
+        mask = _need(mask, torch.float32, "mask")
+        if mask.numel() != n_pos:
+            raise RuntimeError("recguru: mask must have one entry per position")
+    dev = p.device
+    aux = torch.empty(2, dtype=torch.float32, device=dev)
+    dp = torch.empty(n_pos, dtype=torch.float32, device=dev)
+    dn = torch.empty(n_pos, K, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.recguru_sampled_workspace_bytes(n_pos, K), dev)
+    check(lib.recguru_sampled_loss_fwd(_ptr(p), _ptr(n), n_pos, K, _ptr(mask), LOSS_KINDS[kind],
+                                       _ptr(aux), _ptr(dp), _ptr(dn), _ptr(ws), ws.numel(), _stream()),
+          "sampled_loss_fwd")
+    return aux, dp, dn
+
+
+def raw_sampled_score_bwd_dh(dp: Tensor, dn: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
+                             scale: Optional[Tensor] = None, scale2: Optional[Tensor] = None,
+                             out: Optional[Tensor] = None) -> Tensor:
+    lib = _lib.load()
+    dp = _need(dp, torch.float32, "dp")
+    dn = _need(dn, torch.float32, "dn")
+    weight = _need(weight, torch.float32, "weight")
+    pos = _need(pos, torch.int64, "pos")
+    neg = _need(neg, torch.int64, "neg")
+    V1, d = weight.shape
+    n_pos = pos.numel()
+    K = neg.numel() // n_pos
+    if out is None:
+        out = torch.empty(*pos.shape, d, dtype=torch.float32, device=weight.device)
+    check(lib.recguru_sampled_score_bwd_dh(_ptr(dp), _ptr(dn), _ptr(scale), _ptr(scale2), _ptr(weight),
+                                           V1, d, _ptr(pos), _ptr(neg), n_pos, K, _ptr(out), _stream()),
+          "sampled_score_bwd_dh")
+    return out
+
+
+def raw_cast_bf16(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    lib = _lib.load()
+    x = _need(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib.recguru_cast_bf16(_ptr(x), x.numel(), _ptr(out), _stream()), "cast_bf16")
+    return out
+
+
+def raw_catalog_target_scores(users_bf16: Tensor, items_bf16: Tensor, target: Tensor, id_lo: int,
+                              out: Optional[Tensor] = None) -> Tensor:
+    """Score of (u, target[u]) through the tensor-core path; 0 where the target is not in
+    [id_lo, id_lo + n_items) (so that a sum over shards yields the owner's value)."""
+    lib = _lib.load()
+    users_bf16 = _need(users_bf16, torch.bfloat16, "users")
+    items_bf16 = _need(items_bf16, torch.bfloat16, "items")
+    target = _need(target, torch.int64, "target")
+    U, d = users_bf16.shape
+    if out is None:
+        out = torch.empty(U, dtype=torch.float32, device=users_bf16.device)
+    check(lib.recguru_catalog_target_scores(_ptr(users_bf16), U, _ptr(items_bf16), int(id_lo),
+                                            items_bf16.shape[0], d, _ptr(target), _ptr(out), _stream()),
+          "catalog_target_scores")
+    return out
+
+
+def raw_catalog_topk_rank(users_bf16: Tensor, items_bf16: Tensor, target: Tensor,
+                          target_score: Tensor, k: int, id_lo: int, bufs: Optional[dict] = None):
+    """Fused scoring GEMM + running top-k + rank count over items [id_lo, id_lo+n_items)."""
+    lib = _lib.load()
+    users_bf16 = _need(users_bf16, torch.bfloat16, "users")
+    items_bf16 = _need(items_bf16, torch.bfloat16, "items")
+    target = _need(target, torch.int64, "target")
+    target_score = _need(target_score, torch.float32, "target_score")
+    U, d = users_bf16.shape
+    n_items = items_bf16.shape[0]
+    if items_bf16.shape[1] != d or target.numel() != U or target_score.numel() != U:
+        raise RuntimeError("recguru: catalog_topk_rank shape mismatch")
+    dev = users_bf16.device
+    b = bufs or {}
+    val = b.get("val") if "val" in b else torch.empty(U, k, dtype=torch.float32, device=dev)
+    idx = b.get("idx") if "idx" in b else torch.empty(U, k, dtype=torch.int64, device=dev)
+    cnt = b.get("cnt") if "cnt" in b else torch.empty(U, dtype=torch.int64, device=dev)
+    need = lib.recguru_catalog_workspace_bytes(U, n_items, d, k)
+    if need < 0:
+        raise _lib.RecGuruError(f"catalog_workspace_bytes rejected U={U} n_items={n_items} k={k}")
+    ws = b.get("ws") if "ws" in b and b["ws"].numel() >= need else _workspace(need, dev)
+    check(lib.recguru_catalog_topk_rank(_ptr(users_bf16), U, _ptr(items_bf16), int(id_lo), n_items, d,
+                                        _ptr(target), _ptr(target_score), k, _ptr(val), _ptr(idx),
+                                        _ptr(cnt), _ptr(ws), ws.numel(), _stream()),
+          "catalog_topk_rank")
+    return val, idx, cnt
+
+
+def raw_catalog_scores_dense(users_bf16: Tensor, items_bf16: Tensor) -> Tensor:
+    """Debug/parity: the dense [U, n_items] score matrix from the same tcgen05 data path."""
+    lib = _lib.load()
+    users_bf16 = _need(users_bf16, torch.bfloat16, "users")
+    items_bf16 = _need(items_bf16, torch.bfloat16, "items")
+    U, d = users_bf16.shape
+    n_items = items_bf16.shape[0]
+    out = torch.empty(U, n_items, dtype=torch.float32, device=users_bf16.device)
+    check(lib.recguru_catalog_scores_dense(_ptr(users_bf16), U, _ptr(items_bf16), n_items, d, _ptr(out),
+                                           _stream()), "catalog_scores_dense")
+    return out
+
+
+def raw_topk_merge(vals: Tensor, ids: Tensor, counts: Optional[Tensor]):
+    """vals/ids [G,U,k] (+ counts [G,U]) -> (top-k vals [U,k], ids [U,k], rank [U] or None)."""
+    lib = _lib.load()
+    vals = _need(vals, torch.float32, "vals")
+    ids = _need(ids, torch.int64, "ids")
+    G, U, k = vals.shape
+    dev = vals.device
+    out_v = torch.empty(U, k, dtype=torch.float32, device=dev)
+    out_i = torch.empty(U, k, dtype=torch.int64, device=dev)
+    out_r = None
+    if counts is not None:
+        counts = _need(counts, torch.int64, "counts")
+        out_r = torch.empty(U, dtype=torch.int64, device=dev)
+    check(lib.recguru_topk_merge(_ptr(vals), _ptr(ids), _ptr(counts), G, U, k, _ptr(out_v), _ptr(out_i),
+                                 _ptr(out_r), _stream()), "topk_merge")
+    return out_v, out_i, out_r
+
+
+def raw_rank_histogram(rank: Tensor, kmax: int, hist: Optional[Tensor] = None,
+                       accumulate: bool = False) -> Tensor:
+    """hist[r] = #{rank == r} for r < kmax; hist[kmax] = #{rank >= kmax}  (int64, exact)."""
+    lib = _lib.load()
+    rank = _need(rank, torch.int64, "rank").reshape(-1)
+    if hist is None:
+        hist = torch.empty(kmax + 1, dtype=torch.int64, device=rank.device)
+        accumulate = False
+    check(lib.recguru_rank_histogram(_ptr(rank), rank.numel(), kmax, _ptr(hist), 1 if accumulate else 0,
+                                     _stream()), "rank_histogram")
+    return hist
+
+
+# --------------------------------------------------------------------------------------
+# op layer: torch.library custom ops + autograd
+# --------------------------------------------------------------------------------------
+_lib_def = torch.library.Library("recguru", "DEF")
+_lib_def.define("gather_pe_mask(Tensor weight, Tensor ids, Tensor pe, int pad_index) -> (Tensor, Tensor)")
+_lib_def.define("gather_pe_mask_m(Tensor weight, Tensor ids, Tensor pe, Tensor mask) -> Tensor")
+_lib_def.define("gather_rows(Tensor weight, Tensor ids, int padding_idx) -> Tensor")
+_lib_def.define("pe_mask(Tensor x, Tensor pe, Tensor mask) -> Tensor")
+_lib_def.define("embedding_bwd(Tensor grad, Tensor ids, Tensor? coef, int V1, int padding_idx) -> Tensor")
+_lib_def.define("sort_ids(Tensor ids, int V1) -> (Tensor, Tensor)")
+_lib_def.define("sampled_scores(Tensor h, Tensor weight, Tensor pos, Tensor neg, int padding_idx) -> (Tensor, Tensor)")
+_lib_def.define("sampled_loss(Tensor p, Tensor n, Tensor? mask, str kind) -> (Tensor, Tensor, Tensor)")
+_lib_def.define("sampled_score_loss(Tensor h, Tensor weight, Tensor pos, Tensor neg, Tensor? mask, str kind, int padding_idx)"
+                " -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+_lib_def.define("sampled_score_bwd(Tensor dp, Tensor dn, Tensor? scale, Tensor? scale2, Tensor h, Tensor weight,"
+                " Tensor pos, Tensor neg, int padding_idx) -> (Tensor, Tensor)")
+_lib_def.define("cast_bf16(Tensor x) -> Tensor")
+_lib_def.define("catalog_topk_rank(Tensor users, Tensor items_bf16, Tensor target, int k, int id_lo)"
+                " -> (Tensor, Tensor, Tensor)")
+_lib_def.define("topk_merge(Tensor vals, Tensor ids, Tensor counts) -> (Tensor, Tensor, Tensor)")
+_lib_def.define("rank_histogram(Tensor rank, int kmax) -> Tensor")
+
+
+def _impl(name):
+    def deco(fn):
+        torch.library.impl(_lib_def, name, "CUDA")(fn)
+        return fn
+    return deco
+
+
+@_impl("gather_pe_mask")
+def _gather_pe_mask(weight, ids, pe, pad_index):
+    out, mask = raw_gather_pe_mask(weight, ids, pe, pad_index)
+    return out, mask
+
+
+@_impl("gather_pe_mask_m")
+def _gather_pe_mask_m(weight, ids, pe, mask):
+    out, _ = raw_gather_pe_mask(weight, ids, pe, -1, mask_in=mask, want_mask=False)
+    return out
+
+
+@_impl("gather_rows")
+def _gather_rows(weight, ids, padding_idx):
+    out, _ = raw_gather_pe_mask(weight, ids, None, -1, want_mask=False)
+    return out
+
+
+@_impl("pe_mask")
+def _pe_mask(x, pe, mask):
+    return raw_pe_mask(x, pe, mask)
+
+
+@_impl("embedding_bwd")
+def _embedding_bwd(grad, ids, coef, V1, padding_idx):
+    d = grad.shape[-1]
+    return raw_embedding_bwd([Site(ids, grad, coef)], V1, d, padding_idx)
+
+
+@_impl("sort_ids")
+def _sort_ids(ids, V1):
+    return raw_sort_ids(ids, V1)
+
+
+@_impl("sampled_scores")
+def _sampled_scores(h, weight, pos, neg, padding_idx):
+    p, n, _, _, _ = raw_sampled_score_loss(h, weight, pos, neg, None, None)
+    return p, n
+
+
+@_impl("sampled_loss")
+def _sampled_loss(p, n, mask, kind):
+    aux, dp, dn = raw_sampled_loss(p, n, mask, kind)
+    return aux, dp, dn
+
+
+@_impl("sampled_score_loss")
+def _sampled_score_loss(h, weight, pos, neg, mask, kind, padding_idx):
+    p, n, aux, dp, dn = raw_sampled_score_loss(h, weight, pos, neg, mask, kind)
+    return aux, p, n, dp, dn
+
+
+@_impl("sampled_score_bwd")
+def _sampled_score_bwd(dp, dn, scale, scale2, h, weight, pos, neg, padding_idx):
+    V1, d = weight.shape
+    n_pos = pos.numel()
+    K = neg.numel() // n_pos
+    dh = raw_sampled_score_bwd_dh(dp, dn, weight, pos, neg, scale, scale2)
+    dh = dh.view(h.shape)
+    h2 = h.reshape(n_pos, d)
+    dW = raw_embedding_bwd([Site(pos, h2, dp, scale, scale2, 1), Site(neg, h2, dn, scale, scale2, K)],
+                           V1, d, padding_idx)
+    return dh, dW
+
+
+@_impl("cast_bf16")
+def _cast_bf16(x):
+    return raw_cast_bf16(x)
+
+
+@_impl("catalog_topk_rank")
+def _catalog_topk_rank(users, items_bf16, target, k, id_lo):
+    u = users if users.dtype == torch.bfloat16 else raw_cast_bf16(users)
+    ts = raw_catalog_target_scores(u, items_bf16, target, id_lo)
+    return raw_catalog_topk_rank(u, items_bf16, target, ts, k, id_lo)
+
+
+@_impl("topk_merge")
+def _topk_merge(vals, ids, counts):
+    return raw_topk_merge(vals, ids, counts)
+
+
+@_impl("rank_histogram")
+def _rank_histogram(rank, kmax):
+    return raw_rank_histogram(rank, kmax)
+
+
+# ---- fake (meta) kernels: shape inference -----------------------------------------------
+def _fake(name):
+    def deco(fn):
+        torch.library.register_fake(f"recguru::{name}")(fn)
+        return fn
+    return deco
+
+
+@_fake("gather_pe_mask")
+def _(weight, ids, pe, pad_index):
+    return weight.new_empty(*ids.shape, weight.shape[1]), weight.new_empty(ids.shape)
+
+
+@_fake("gather_pe_mask_m")
+def _(weight, ids, pe, mask):
+    return weight.new_empty(*ids.shape, weight.shape[1])
+
+
+@_fake("gather_rows")
+def _(weight, ids, padding_idx):
+    return weight.new_empty(*ids.shape, weight.shape[1])
+
+
+@_fake("pe_mask")
+def _(x, pe, mask):
+    return torch.empty_like(x)
+
+
+@_fake("embedding_bwd")
+def _(grad, ids, coef, V1, padding_idx):
+    return grad.new_empty(V1, grad.shape[-1])
+
+
+@_fake("sort_ids")
+def _(ids, V1):
+    return ids.new_empty(ids.numel()), ids.new_empty(ids.numel())
+
+
+@_fake("sampled_scores")
+def _(h, weight, pos, neg, padding_idx):
+    K = neg.numel() // max(pos.numel(), 1)
+    return h.new_empty(*pos.shape, 1), h.new_empty(*pos.shape, K)
+
+
+@_fake("sampled_loss")
+def _(p, n, mask, kind):
+    n_pos = p.numel()
+    return p.new_empty(2), p.new_empty(n_pos), p.new_empty(n_pos, n.numel() // max(n_pos, 1))
+
+
+@_fake("sampled_score_loss")
+def _(h, weight, pos, neg, mask, kind, padding_idx):
+    n_pos = pos.numel()
+    K = neg.numel() // max(n_pos, 1)
+    return (h.new_empty(2), h.new_empty(*pos.shape, 1), h.new_empty(*pos.shape, K),
+            h.new_empty(n_pos), h.new_empty(n_pos, K))
+
+
+@_fake("sampled_score_bwd")
+def _(dp, dn, scale, scale2, h, weight, pos, neg, padding_idx):
+    return torch.empty_like(h), torch.empty_like(weight)
+
+
+@_fake("cast_bf16")
+def _(x):
+    return x.new_empty(x.shape, dtype=torch.bfloat16)
+
+
+@_fake("catalog_topk_rank")
+def _(users, items_bf16, target, k, id_lo):
+    U = users.shape[0]
+    return (users.new_empty(U, k, dtype=torch.float32), target.new_empty(U, k), target.new_empty(U))
+
+
+@_fake("topk_merge")
+def _(vals, ids, counts):
+    _, U, k = vals.shape
+    return vals.new_empty(U, k), ids.new_empty(U, k), ids.new_empty(U)
+
+
+@_fake("rank_histogram")
+def _(rank, kmax):
+    return rank.new_empty(kmax + 1)
+
+
+# ---- autograd ------------------------------------------------------------------------------
+def _setup_gather_pe_mask(ctx, inputs, output):
+    weight, ids, pe, pad_index = inputs
+    _, mask = output
+    ctx.save_for_backward(ids, mask)
+    ctx.V1 = weight.shape[0]
+
+
+def _bwd_gather_pe_mask(ctx, g_out, g_mask):
+    ids, mask = ctx.saved_tensors
+    d = g_out.shape[-1]
+    # d out / d W[id] = mask ; pad rows get coef 0 (== the reference: x*mask kills their grad,
+    # and nn.Embedding(padding_idx) would skip them anyway)
+    dW = torch.ops.recguru.embedding_bwd(g_out.reshape(-1, d), ids.reshape(-1), mask.reshape(-1),
+                                         ctx.V1, -1)
+    return dW, None, None, None
+
+
+torch.library.register_autograd("recguru::gather_pe_mask", _bwd_gather_pe_mask,
+                                setup_context=_setup_gather_pe_mask)
+
+
+def _setup_gather_pe_mask_m(ctx, inputs, output):
+    weight, ids, pe, mask = inputs
+    ctx.save_for_backward(ids, mask)
+    ctx.V1 = weight.shape[0]
+
+
+def _bwd_gather_pe_mask_m(ctx, g_out):
+    ids, mask = ctx.saved_tensors
+    d = g_out.shape[-1]
+    dW = torch.ops.recguru.embedding_bwd(g_out.reshape(-1, d), ids.reshape(-1), mask.reshape(-1),
+                                         ctx.V1, -1)
+    return dW, None, None, None
+
+
+torch.library.register_autograd("recguru::gather_pe_mask_m", _bwd_gather_pe_mask_m,
+                                setup_context=_setup_gather_pe_mask_m)
+
+
+def _setup_pe_mask(ctx, inputs, output):
+    _, _, mask = inputs
+    ctx.save_for_backward(mask)
+
+
+def _bwd_pe_mask(ctx, g):
+    (mask,) = ctx.saved_tensors
+    return g * mask.reshape(*g.shape[:-1], 1), None, None
+
+
+torch.library.register_autograd("recguru::pe_mask", _bwd_pe_mask, setup_context=_setup_pe_mask)
+
+
+def _setup_sampled_scores(ctx, inputs, output):
+    h, weight, pos, neg, padding_idx = inputs
+    ctx.save_for_backward(h, weight, pos, neg)
+    ctx.padding_idx = padding_idx
+
+
+def _bwd_sampled_scores(ctx, g_p, g_n):
+    h, weight, pos, neg = ctx.saved_tensors
+    n_pos = pos.numel()
+    K = neg.numel() // n_pos
+    dp = g_p.reshape(n_pos).contiguous()
+    dn = g_n.reshape(n_pos, K).contiguous()
+    dh, dW = torch.ops.recguru.sampled_score_bwd(dp, dn, None, None, h, weight, pos, neg,
+                                                 ctx.padding_idx)
+    return dh, dW, None, None, None
+
+
+torch.library.register_autograd("recguru::sampled_scores", _bwd_sampled_scores,
+                                setup_context=_setup_sampled_scores)
+
+
+def _setup_sampled_loss(ctx, inputs, output):
+    p, n, mask, kind = inputs
+    aux, dp, dn = output
+    ctx.save_for_backward(aux, dp, dn)
+    ctx.shapes = (p.shape, n.shape)
+    ctx.mark_non_differentiable(dp, dn)
+
+
+def _bwd_sampled_loss(ctx, g_aux, g_dp, g_dn):
+    aux, dp, dn = ctx.saved_tensors
+    s = g_aux[0] * aux[1]
+    return (dp * s).view(ctx.shapes[0]), (dn * s).view(ctx.shapes[1]), None, None
+
+
+torch.library.register_autograd("recguru::sampled_loss", _bwd_sampled_loss,
+                                setup_context=_setup_sampled_loss)
+
+
+def _setup_sampled_score_loss(ctx, inputs, output):
+    h, weight, pos, neg, mask, kind, padding_idx = inputs
+    aux, p, n, dp, dn = output
+    ctx.save_for_backward(h, weight, pos, neg, aux, dp, dn)
+    ctx.padding_idx = padding_idx
+    ctx.mark_non_differentiable(dp, dn)
+    ctx.set_materialize_grads(False)  # g_p / g_n stay None unless p / n are used downstream
+
+
+def _bwd_sampled_score_loss(ctx, g_aux, g_p, g_n, g_dp, g_dn):
+    h, weight, pos, neg, aux, dp, dn = ctx.saved_tensors
+    n_pos = pos.numel()
+    K = neg.numel() // n_pos
+    inv_m = aux[1:2]                      # 1/sum(mask), still missing from dp/dn
+    if g_p is None and g_n is None and g_aux is not None:
+        go = g_aux[0:1].contiguous()      # upstream grad of the scalar loss (device scalar)
+        dh, dW = torch.ops.recguru.sampled_score_bwd(dp, dn, go, inv_m, h, weight, pos, neg,
+                                                     ctx.padding_idx)
+    else:
+        # logits were also used downstream: fold their grads in (rare; plain torch arithmetic)
+        dp_t = torch.zeros_like(dp) if g_aux is None else dp * (g_aux[0] * aux[1])
+        dn_t = torch.zeros_like(dn) if g_aux is None else dn * (g_aux[0] * aux[1])
+        if g_p is not None:
+            dp_t = dp_t + g_p.reshape(n_pos)
+        if g_n is not None:
+            dn_t = dn_t + g_n.reshape(n_pos, K)
+        dh, dW = torch.ops.recguru.sampled_score_bwd(dp_t.contiguous(), dn_t.contiguous(), None, None,
+                                                     h, weight, pos, neg, ctx.padding_idx)
+    return dh, dW, None, None, None, None, None
+
+
+torch.library.register_autograd("recguru::sampled_score_loss", _bwd_sampled_score_loss,
+                                setup_context=_setup_sampled_score_loss)
+
+
+def _setup_gather_rows(ctx, inputs, output):
+    weight, ids, padding_idx = inputs
+    ctx.save_for_backward(ids)
+    ctx.V1 = weight.shape[0]
+    ctx.padding_idx = padding_idx
+
+
+def _bwd_gather_rows(ctx, g):
+    (ids,) = ctx.saved_tensors
+    d = g.shape[-1]
+    dW = torch.ops.recguru.embedding_bwd(g.reshape(-1, d).contiguous(), ids.reshape(-1), None, ctx.V1,
+                                         ctx.padding_idx)
+    return dW, None, None
+
+
+torch.library.register_autograd("recguru::gather_rows", _bwd_gather_rows, setup_context=_setup_gather_rows)
