@@ -1,0 +1,545 @@
+#!/usr/bin/env python
+"""bench.py -- RecGURU embedding-and-scoring hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|catalog] [--impl reference]
+
+BASELINE.json's metric has three parts; one JSON line carries all of them:
+  * primary (``value``): train seqs/sec of the hot-path training step on configs[1]
+    (SASRec shape: 100k items, L=200, d=128, B=1024, K=5 BPR negatives) -- gather+PE+mask,
+    sampled scoring + BPRLoss_sas forward, its backward, and the one-pass deterministic table
+    backward.  N>1: replicas only (the reference replicates the table; nothing is partitioned).
+  * ``catalog``: full-catalog eval users/sec -- cfg4 (1M items, N=1 only) and cfg5 (10M items,
+    row-sharded over the N GPUs: all-gather users, all-reduce target score, all-to-all + merge).
+  * ``gather``: GB/s of the fused gather kernel alone (cold: rotating inputs larger than L2).
+``--workload catalog`` makes the cfg5 catalog line the primary one instead.
+
+``--impl reference`` times the reference's own CPU op sequence for the same path (the oracle
+port: identical ATen ops; the reference is pure PyTorch and /root/reference does not travel to
+the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CFG2 = dict(n_items=100_000, L=200, d=128, B=1024, K=5, kind="bpr_sas")
+CFG4 = dict(n_items=1_000_000, d=128, k=10, users_total=1_000_000)
+CFG5 = dict(n_items=10_000_000, d=128, k=10, users_total=1_000_000)
+USERS_PER_STEP = 148 * 4 * 128          # 4 full waves of 128-user tiles on 148 SMs
+
+
+# ----------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class Dist:
+    def __init__(self, n_gpus: int):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        else:
+            torch.cuda.set_device(0)
+            self.dist = None
+        if self.world != n_gpus and self.rank == 0:
+            print(f"# note: --gpus {n_gpus} but WORLD_SIZE={self.world}; using WORLD_SIZE", file=sys.stderr)
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def group(self):
+        return None if self.dist is None else self.dist.group.WORLD
+
+
+def timed_loop(D: Dist, fn, steps: int, warmup: int):
+    """W untimed steps, then exactly K steps between barrier+synchronize, CUDA events on the
+    launching stream, max over ranks.  fn(i) enqueues step i."""
+    for i in range(warmup):
+        fn(i)
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    D.barrier()
+    return D.max_over_ranks(ms)
+
+
+# ----------------------------------------------------------------------------------------------
+# workload 1: training-step hot path (configs[1])
+# ----------------------------------------------------------------------------------------------
+def make_train_inputs(cfg, n_batches: int, device):
+    from recguru_b200 import synth, modules
+    W = synth.item_table(cfg["n_items"], cfg["d"]).to(device)
+    pe = modules.sinusoid_table(max(cfg["L"], 256), cfg["d"])[0].to(device)
+    batches, host = [], []
+    for b in range(n_batches):
+        tb = synth.train_batch(cfg["B"], cfg["L"], cfg["n_items"], cfg["K"], seed=synth.SEED_DATA + 100 * b)
+        h = synth.hidden_states(cfg["B"], cfg["L"], cfg["d"], seed=50 + b)
+        g = synth.hidden_states(cfg["B"], cfg["L"], cfg["d"], seed=90 + b)
+        host.append(tb)
+        batches.append(dict(tb=tb.to(device), h=h.to(device), g=g.to(device)))
+    return W, pe, batches, host
+
+
+def bench_train(D: Dist, args, peaks):
+    from recguru_b200 import _lib
+    from recguru_b200.hotpath import TrainHotPath
+    cfg = CFG2
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_batches = 4      # rotating inputs: 4 x (h + g + out) = 4 x 315 MB >> 126 MB L2
+    W, pe, batches, host = make_train_inputs(cfg, n_batches, dev)
+    hp = TrainHotPath(W, pe, cfg["B"], cfg["L"], cfg["K"], cfg["kind"])
+    K, Wm = args.steps, args.warmup
+
+    # ---- device-resident timing with per-stage events ----
+    n_ev = 5
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(K)]
+
+    def step(i):
+        b = batches[i % n_batches]
+        tb = b["tb"]
+        rec = evs[i - Wm] if i >= Wm else None
+        if rec: rec[0].record()
+        hp.forward_in(tb.dec_in)
+        if rec: rec[1].record()
+        hp.forward_loss(b["h"], tb.dec_out, tb.n_items)
+        if rec: rec[2].record()
+        from recguru_b200 import ops
+        ops.raw_sampled_score_bwd_dh(hp.sbuf["dp"], hp.sbuf["dn"], hp.weight, tb.dec_out, tb.n_items,
+                                     scale=hp.one, scale2=hp.sbuf["aux"][1:2], out=hp.dh)
+        if rec: rec[3].record()
+        n = cfg["B"] * cfg["L"]
+        h2 = b["h"].view(n, cfg["d"])
+        sites = [ops.Site(tb.dec_in, b["g"].view(n, cfg["d"]), coef=hp.mask.view(n)),
+                 ops.Site(tb.dec_out, h2, coef=hp.sbuf["dp"], scale=hp.one, scale2=hp.sbuf["aux"][1:2]),
+                 ops.Site(tb.n_items, h2, coef=hp.sbuf["dn"].view(-1), scale=hp.one,
+                          scale2=hp.sbuf["aux"][1:2], group=cfg["K"])]
+        ops.raw_embedding_bwd(sites, hp.V1, hp.d, 0, out=hp.dW, zero_fill=True, workspace=hp.ws_bwd)
+        if rec: rec[4].record()
+
+    l0 = _lib.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed_loop(D, step, K, Wm)
+    launches = (_lib.launch_count() - l0) * K // (K + Wm)
+    stage_names = ["gather_pe_mask", "sampled_score_loss_fwd", "sampled_score_bwd_dh", "embedding_bwd"]
+    stage_ms = {nme: sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)) / K
+                for j, nme in enumerate(stage_names)}
+    # distinct touched rows (for the algorithmic bytes of the table backward)
+    tb0 = batches[0]["tb"]
+    distinct = int(torch.unique(torch.cat([tb0.dec_in.view(-1), tb0.dec_out.view(-1), tb0.n_items.view(-1)])).numel())
+    abytes = hp.algorithmic_bytes(distinct)
+    stages = {nme: {"ms": round(stage_ms[nme], 4), "algorithmic_mb": round(abytes[nme] / 1e6, 1),
+                    "gbs": round(abytes[nme] / 1e6 / stage_ms[nme], 1),
+                    "frac_of_hbm_peak": round(abytes[nme] / 1e6 / stage_ms[nme] / peaks["hbm"], 3)}
+              for nme in stage_names}
+    dom = max(stage_names, key=lambda s: stage_ms[s])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": stages[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["src"]}
+
+    # ---- end to end through the public API with host buffers ----
+    pin = [dict(dec_in=t.dec_in.pin_memory(), dec_out=t.dec_out.pin_memory(), n_items=t.n_items.pin_memory())
+           for t in host]
+    d_in = {k: torch.empty_like(v, device=dev) for k, v in pin[0].items()}
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        b = batches[i % n_batches]
+        src = pin[i % n_batches]
+        for k in d_in:
+            d_in[k].copy_(src[k], non_blocking=True)
+        loss, _, _ = hp.step(d_in["dec_in"], d_in["dec_out"], d_in["n_items"], b["h"], b["g"])
+        loss_host.copy_(loss.view(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the reference reads loss.item() every step
+
+    ms_e2e = timed_loop(D, e2e_step, K, Wm)
+    h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
+    seqs = cfg["B"] * D.world
+    out = {
+        "value": seqs * K / (ms / 1e3), "ms_per_step": ms / K, "stages": stages, "roofline": roof,
+        "e2e": {"value": seqs * K / (ms_e2e / 1e3), "unit": "seqs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
+                "note": "ids from pinned host memory each step, loss read back each step; h and the "
+                        "gradient w.r.t. the input activations come from the (out-of-scope) transformer "
+                        "and are device resident"},
+        "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
+        "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
+    }
+    return out, (W, pe, batches)
+
+
+def bench_gather(D: Dist, args, peaks, W, pe, batches):
+    """Gather GB/s in isolation: fused gather+PE+mask, rotating ids/out buffers (> L2)."""
+    from recguru_b200 import ops
+    cfg = CFG2
+    dev = W.device
+    outs = [torch.empty(cfg["B"], cfg["L"], cfg["d"], device=dev) for _ in range(4)]
+    masks = [torch.empty(cfg["B"], cfg["L"], device=dev) for _ in range(4)]
+
+    def step(i):
+        j = i % 4
+        ops.raw_gather_pe_mask(W, batches[j]["tb"].dec_in, pe, 0, out=outs[j], mask_out=masks[j])
+
+    ms = timed_loop(D, step, max(args.steps, 20), args.warmup)
+    n = cfg["B"] * cfg["L"]
+    mb = n * (8 + 8 * cfg["d"] + 4) / 1e6
+    per = ms / max(args.steps, 20)
+    # dense ids (no padding) variant: every token reads a real row
+    ids = torch.randint(1, cfg["n_items"] + 1, (4, cfg["B"], cfg["L"]), device=dev)
+
+    def step2(i):
+        j = i % 4
+        ops.raw_gather_pe_mask(W, ids[j], pe, 0, out=outs[j], mask_out=masks[j])
+
+    ms2 = timed_loop(D, step2, max(args.steps, 20), args.warmup) / max(args.steps, 20)
+    return {"gbs": round(mb / per, 1), "frac_of_hbm_peak": round(mb / per / peaks["hbm"], 3),
+            "ms": round(per, 4), "algorithmic_mb": round(mb, 1),
+            "dense_ids": {"gbs": round(mb / ms2, 1), "frac_of_hbm_peak": round(mb / ms2 / peaks["hbm"], 3),
+                          "ms": round(ms2, 4)},
+            "note": "amazon-shaped batch (93% pad tokens hit one row) and a no-padding batch; "
+                    "4 rotating out buffers = 420 MB > L2"}
+
+
+# ----------------------------------------------------------------------------------------------
+# workload 2: full-catalog eval
+# ----------------------------------------------------------------------------------------------
+def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
+    from recguru_b200 import _lib, ops, catalog
+    dev = torch.device("cuda", torch.cuda.current_device())
+    G = D.world if sharded else 1
+    n_items, d, k = cfg["n_items"], cfg["d"], cfg["k"]
+    lo, hi = catalog.shard_bounds(n_items, G, D.rank if sharded else 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1235 + (D.rank if sharded else 0))
+    # item slice generated on the device (cfg5 is 5 GB fp32 on the host otherwise); N(0,1) rows
+    items = torch.empty(hi - lo, d, dtype=torch.bfloat16, device=dev)
+    chunk = 1 << 20
+    for r0 in range(0, hi - lo, chunk):
+        r1 = min(hi - lo, r0 + chunk)
+        items[r0:r1] = ops.raw_cast_bf16(torch.randn(r1 - r0, d, generator=gen, device=dev))
+    ev = catalog.CatalogEvaluator.__new__(catalog.CatalogEvaluator)
+    ev.k, ev.group, ev.world, ev.rank = k, (D.group() if sharded else None), G, (D.rank if sharded else 0)
+    ev.id_lo, ev.n_local, ev.n_items, ev.d, ev.items = 1 + lo, hi - lo, n_items, d, items
+    u_step = USERS_PER_STEP
+    u_loc = u_step // G
+    n_chunks = 4
+    gen.manual_seed(77 + D.rank)
+    users = [torch.randn(u_loc, d, generator=gen, device=dev) for _ in range(n_chunks)]
+    users_bf = [ops.raw_cast_bf16(u) for u in users]
+    targets = [torch.randint(1, n_items + 1, (u_loc,), generator=gen, device=dev) for _ in range(n_chunks)]
+    steps = max(3, min(args.steps, 10 if n_items <= 1_000_000 else 4))
+    warm = max(3, min(args.warmup, 3))
+    res = {}
+
+    def step(i):
+        j = i % n_chunks
+        res["out"] = ev.rank_topk(users_bf[j], targets[j])
+
+    l0 = _lib.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed_loop(D, step, steps, warm)
+    launches = (_lib.launch_count() - l0) * steps // (steps + warm)
+    per = ms / steps
+
+    # sweep kernel alone (dominant kernel) with CUDA events, single device view
+    ub, tg = (users_bf[0], targets[0]) if G == 1 else (None, None)
+    sweep_ms = None
+    if G == 1:
+        ts = ops.raw_catalog_target_scores(ub, items, tg, ev.id_lo)
+        bufs = {}
+
+        def sweep(i):
+            ops.raw_catalog_topk_rank(users_bf[i % n_chunks], items, targets[i % n_chunks], ts, k, ev.id_lo, bufs=bufs)
+        sweep_ms = timed_loop(D, sweep, steps, warm) / steps
+    flops = 2.0 * u_step * (hi - lo) * d
+    t_kernel = sweep_ms if sweep_ms is not None else per
+    tflops = flops / (t_kernel * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "catalog_sweep_kernel", "achieved": round(tflops, 1),
+            "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": round(tflops / peaks["tf_sust"], 3),
+            "frac_of_burst_peak": round(tflops / peaks["tf_burst"], 3), "traffic": None,
+            "peak_source": peaks["src"] + " (sustained bf16 cuBLAS)"}
+
+    # end to end: fp32 user reps + targets from pinned host memory, ranks read back
+    pin_u = [u.cpu().pin_memory() for u in users[:2]]
+    pin_t = [t.cpu().pin_memory() for t in targets[:2]]
+    d_u = torch.empty_like(users[0]); d_t = torch.empty_like(targets[0])
+    rank_host = torch.empty(u_loc, dtype=torch.int64).pin_memory()
+
+    def e2e(i):
+        d_u.copy_(pin_u[i % 2], non_blocking=True); d_t.copy_(pin_t[i % 2], non_blocking=True)
+        _, _, rk = ev.rank_topk(d_u, d_t)               # includes the fp32->bf16 cast kernel
+        rank_host.copy_(rk, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = timed_loop(D, e2e, steps, warm) / steps
+    met = catalog.rank_metrics(res["out"][2], (5, 10))
+    return {
+        "metric": "full-catalog eval users/sec", "value": u_step / (per * 1e-3), "unit": "users/s",
+        "ms_per_step": per, "steps": steps, "warmup": warm,
+        "config": {"workload": name, "n_items": n_items, "d": d, "k": k, "users_per_step": u_step,
+                   "users_total_cfg": cfg["users_total"], "sharding": f"rows/{G}" if sharded else "none",
+                   "l2": "4 rotating user chunks; item table 256 MB-2.5 GB > L2"},
+        "scaling": "strong" if sharded else None,
+        "sweep_kernel_ms": sweep_ms, "roofline": roof,
+        "e2e": {"value": u_step / (ms_e2e * 1e-3), "unit": "users/s",
+                "h2d_bytes_per_step": u_loc * (d * 4 + 8), "d2h_bytes_per_step": u_loc * 8, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": cs.summary(),
+        "hr10_synthetic": met[10]["hr"],
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's ATen op sequence on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_train_step_fn(cfg, B_cpu: int):
+    from oracle import ref_path as O
+    from recguru_b200 import synth, modules
+    W = torch.nn.Parameter(synth.item_table(cfg["n_items"], cfg["d"]))
+    pe = modules.sinusoid_table(max(cfg["L"], 256), cfg["d"])
+    tb = synth.train_batch(B_cpu, cfg["L"], cfg["n_items"], cfg["K"])
+    h = synth.hidden_states(B_cpu, cfg["L"], cfg["d"]).requires_grad_(True)
+    g = synth.hidden_states(B_cpu, cfg["L"], cfg["d"], seed=91)
+    L, K = cfg["L"], cfg["K"]
+
+    def step():
+        W.grad = None; h.grad = None
+        x0, mask = O.gather_pe_mask(W, tb.dec_in, pe, 0, padding_idx=0)            # G1 + M1 + P1
+        p, n = O.sampled_scores(h, W, tb.dec_out, tb.n_items, L, K, padding_idx=0)  # S1-S3
+        loss = O.LOSSES[cfg["kind"]](p, n, mask.view(-1))                           # Lsas
+        (loss + (x0 * g).sum()).backward()                                          # B1 (+ dh)
+        return float(loss.detach())
+    return step
+
+
+def cpu_catalog_fn(cfg, U_cpu: int):
+    from oracle import ref_path as O
+    g = torch.Generator().manual_seed(5)
+    W = torch.randn(cfg["n_items"], cfg["d"], generator=g)
+    u = torch.randn(U_cpu, cfg["d"], generator=g)
+    tgt = torch.randint(0, cfg["n_items"], (U_cpu,), generator=g)
+
+    def step():
+        s = torch.matmul(u, W.transpose(1, 0))                                     # AutoEnc4Rec.py:230
+        rank = torch.argsort(torch.argsort(-s, dim=1), dim=1)[torch.arange(U_cpu), tgt]   # train_auto.py:234-237
+        r = rank.cpu().detach().numpy()
+        return O.hit_at_k_batch(r, 10), O.NDCG_at_k_batch(r, 10)
+    return step
+
+
+def time_cpu(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    if args.workload == "catalog":
+        cfg, U_cpu = CFG5, 8
+        sec = time_cpu(cpu_catalog_fn(cfg, U_cpu), max(1, min(args.steps, 3)), 1)
+        val, unit, metric = U_cpu / sec, "users/s", "full-catalog eval users/sec"
+        sample = f"{U_cpu} users x {cfg['n_items']} items per step (u@W^T + double argsort + metrics)"
+        conf = {"workload": "cfg5 full-catalog eval, 10M items, d=128 (bounded CPU sample)"}
+    else:
+        cfg, B_cpu = CFG2, 512
+        steps = max(1, min(args.steps, 20))
+        sec = time_cpu(cpu_train_step_fn(cfg, B_cpu), steps, max(1, min(args.warmup, 3)))
+        val, unit, metric = B_cpu / sec, "seqs/s", "train seqs/sec"
+        sample = (f"{B_cpu} of {cfg['B']} sequences per step (F.embedding+pe+mask, sampled matmuls, "
+                  f"BPRLoss_sas, autograd backward incl. dense [V1,d] embedding grads)")
+        conf = {"workload": "cfg2 SASRec hot-path training step: 100k items, L=200, d=128, K=5 (bounded CPU sample)"}
+    line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "catalog"])
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only", default="", help="comma list of sections: train,gather,cfg4,cfg5")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (recguru_b200 has no CPU path); "
+                         "use --impl reference for the CPU reference arm")
+    from recguru_b200 import build
+    build.build()
+    D = Dist(args.gpus)
+    peaks = load_peaks()
+    only = set(filter(None, args.only.split(",")))
+
+    def want(s):
+        return not only or s in only
+
+    line = {}
+    train = gather = None
+    if want("train") or want("gather"):
+        train, (W, pe, batches) = bench_train(D, args, peaks)
+        if want("gather"):
+            gather = bench_gather(D, args, peaks, W, pe, batches)
+        del W, pe, batches
+        torch.cuda.empty_cache()
+    cat = {}
+    if D.world == 1 and want("cfg4"):
+        cat["cfg4"] = bench_catalog(D, args, peaks, CFG4, "cfg4 full-catalog eval 1M users x 1M items, d=128, top-10", False)
+        torch.cuda.empty_cache()
+    if want("cfg5"):
+        cat["cfg5"] = bench_catalog(D, args, peaks, CFG5,
+                                    "cfg5 full-catalog eval, 10M items row-sharded, d=128, top-10", D.world > 1)
+        torch.cuda.empty_cache()
+
+    cpu = None
+    if D.rank == 0 and D.world == 1 and not args.skip_cpu:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        if args.workload == "train":
+            B_cpu = 512
+            sec = time_cpu(cpu_train_step_fn(CFG2, B_cpu), 10, 2)
+            cpu = {"value": B_cpu / sec, "unit": "seqs/s", "cores": cores, "kind": "port",
+                   "sample": f"{B_cpu} of {CFG2['B']} sequences per step, 10 steps, reference ATen op sequence (oracle/ref_path.py)"}
+        else:
+            U_cpu = 8
+            sec = time_cpu(cpu_catalog_fn(CFG5, U_cpu), 2, 1)
+            cpu = {"value": U_cpu / sec, "unit": "users/s", "cores": cores, "kind": "port",
+                   "sample": f"{U_cpu} users x 10M items per step, 2 steps (u@W^T + double argsort + metrics)"}
+
+    if D.rank == 0:
+        if args.workload == "train" and train is not None:
+            line = {"metric": "train seqs/sec", "value": train["value"], "unit": "seqs/s", "n_gpus": D.world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": train["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                    "data": "synthetic",
+                    "config": {"workload": "cfg2 SASRec hot-path training step (configs[1]): 100k items, L=200, "
+                                           "d=128, B=1024/GPU, K=5, BPRLoss_sas; replicas only for N>1",
+                               "l2": "4 rotating batches (h+g+out = 315 MB each) > 126 MB L2",
+                               **{k: v for k, v in CFG2.items()}},
+                    "roofline": train["roofline"], "stages": train["stages"], "e2e": train["e2e"],
+                    "gpu_launches": train["gpu_launches"], "clocks": train["clocks"],
+                    "algorithmic_mb_per_step": train["algorithmic_mb_per_step"]}
+            if gather is not None:
+                line["gather"] = gather
+            line["catalog"] = cat
+        else:
+            c = cat.get("cfg5") or cat.get("cfg4")
+            line = {"metric": c["metric"], "value": c["value"], "unit": c["unit"], "n_gpus": D.world,
+                    "steps": c["steps"], "warmup": c["warmup"], "ms_per_step": c["ms_per_step"],
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                    "data": "synthetic", "config": c["config"], "roofline": c["roofline"], "e2e": c["e2e"],
+                    "gpu_launches": c["gpu_launches"], "clocks": c["clocks"], "catalog": cat}
+            if train is not None:
+                line["train"] = {k: train[k] for k in ("value", "ms_per_step", "stages", "e2e")}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if D.dist is not None:
+        D.dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

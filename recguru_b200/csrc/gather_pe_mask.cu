@@ -12,6 +12,8 @@
 // use (memory-level parallelism), adds the PE vector (L2-resident, [L,d]) and streams the
 // result out with 128-bit stores.  Arithmetic is an fp32 add followed by an fp32 multiply
 // by 0/1 (no FMA contraction), i.e. bit-identical to the reference's two ATen kernels.
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace rg {
@@ -54,6 +56,7 @@ gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restri
     const int flat = u * kGatherThreads + threadIdx.x;
     tl[u] = flat / vec;
     vv[u] = flat - tl[u] * vec;
+    if (tl[u] >= tok_per_block) tl[u] = INT_MAX / 2;  // d/4 does not divide the tile: idle slot
     if (tok0 + tl[u] < n_tokens) {
       row[u] = __ldg(weight + static_cast<int64_t>(s_id[tl[u]]) * vec + vv[u]);
     }
@@ -122,8 +125,6 @@ extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d
              "gather_pe_mask: weight/pe/out must be 16-byte aligned");
   if (n_tokens == 0) return RECGURU_OK;
   const int vec = static_cast<int>(d / 4);
-  RG_REQUIRE((kGatherThreads * kGatherUnroll) % vec == 0, RECGURU_E_UNSUPPORTED,
-             "gather_pe_mask: d/4=%d must divide %d", vec, kGatherThreads * kGatherUnroll);
   const int tok_per_block = (kGatherThreads * kGatherUnroll) / vec;
   const int64_t blocks = ceil_div(n_tokens, tok_per_block);
   const size_t smem = static_cast<size_t>(tok_per_block) * 8;

@@ -1,0 +1,104 @@
+"""The training-step hot path as one object: all lookup sites of a step, fused.
+
+A reference training step touches the item table at its two edges
+(SURVEY.md section 3.5): ids -> (W[ids] + pe) * mask -> [transformer, not ours] -> h ->
+(h . W[pos], h . W[neg]) -> loss, and back.  ``TrainHotPath`` runs exactly those edges with
+pre-allocated buffers and no per-step allocation, and produces ONE dense table gradient for all
+lookup sites (input + positive + negative) in a single deterministic sort/segmented-reduce pass,
+instead of one dense [V1, d] gradient per site summed by autograd.
+
+It is driven by whatever sits between the edges (the reference's EncoderM/DecoderM): call
+:meth:`forward_in`, run the transformer on the returned activations, call :meth:`forward_loss`
+on its output, then :meth:`backward` with the gradient that came back to the input activations.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .ops import Site
+
+Tensor = torch.Tensor
+
+
+class TrainHotPath:
+    """SASRec / AutoRec BPR step edges (MyRec.forward, AutoEnc4Rec.py:98-133 + BPRLoss_sas)."""
+
+    def __init__(self, weight: Tensor, pe: Tensor, B: int, L: int, K: int, kind: str = "bpr_sas",
+                 pad_index: int = 0, padding_idx: Optional[int] = 0):
+        assert weight.is_cuda and weight.dtype == torch.float32
+        self.weight = weight
+        self.pe = pe[0] if pe.dim() == 3 else pe
+        self.B, self.L, self.K, self.kind = B, L, K, kind
+        self.pad_index = pad_index
+        self.padding_idx = -1 if padding_idx is None else padding_idx
+        V1, d = weight.shape
+        self.V1, self.d = V1, d
+        dev = weight.device
+        n = B * L
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x0 = torch.empty(B, L, d, **f32)
+        self.mask = torch.empty(B, L, **f32)
+        self.sbuf = {
+            "p": torch.empty(B, L, 1, **f32), "n": torch.empty(B, L, K, **f32),
+            "aux": torch.empty(2, **f32), "dp": torch.empty(n, **f32), "dn": torch.empty(n, K, **f32),
+            "ws": torch.empty(max(256, int(ops._lib.load().recguru_sampled_workspace_bytes(n, K))),
+                              dtype=torch.uint8, device=dev),
+        }
+        self.dh = torch.empty(B, L, d, **f32)
+        self.dW = torch.empty(V1, d, **f32)
+        total = n * (2 + K)
+        self.ws_bwd = torch.empty(ops.embedding_bwd_workspace_bytes(total, V1, d), dtype=torch.uint8, device=dev)
+        self.one = torch.ones(1, **f32)
+
+    # -- edge 1: ids -> activations ------------------------------------------------------
+    def forward_in(self, dec_in: Tensor) -> Tensor:
+        ops.raw_gather_pe_mask(self.weight, dec_in, self.pe, self.pad_index, out=self.x0, mask_out=self.mask)
+        return self.x0
+
+    # -- edge 2: hidden states -> loss ---------------------------------------------------
+    def forward_loss(self, h: Tensor, dec_out: Tensor, n_items: Tensor, mask: Optional[Tensor] = None) -> Tensor:
+        m = self.mask if mask is None else mask
+        ops.raw_sampled_score_loss(h, self.weight, dec_out, n_items, m, self.kind, bufs=self.sbuf)
+        return self.sbuf["aux"][0]
+
+    # -- backward of both edges ------------------------------------------------------------
+    def backward(self, h: Tensor, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, g_x0: Tensor,
+                 grad_loss: Optional[Tensor] = None):
+        """Returns (dh, dW).  ``g_x0`` is d loss / d x0 as it comes back through the transformer."""
+        go = self.one if grad_loss is None else grad_loss
+        inv_m = self.sbuf["aux"][1:2]
+        ops.raw_sampled_score_bwd_dh(self.sbuf["dp"], self.sbuf["dn"], self.weight, dec_out, n_items,
+                                     scale=go, scale2=inv_m, out=self.dh)
+        n = self.B * self.L
+        h2 = h.view(n, self.d)
+        sites = [
+            Site(dec_in, g_x0.view(n, self.d), coef=self.mask.view(n)),                       # input site
+            Site(dec_out, h2, coef=self.sbuf["dp"], scale=go, scale2=inv_m),                   # positives
+            Site(n_items, h2, coef=self.sbuf["dn"].view(-1), scale=go, scale2=inv_m, group=self.K),  # negatives
+        ]
+        ops.raw_embedding_bwd(sites, self.V1, self.d, self.padding_idx, out=self.dW, zero_fill=True,
+                              workspace=self.ws_bwd)
+        return self.dh, self.dW
+
+    def step(self, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, h: Tensor, g_x0: Tensor):
+        """All edges of one step with the transformer replaced by given (h, g_x0)."""
+        self.forward_in(dec_in)
+        loss = self.forward_loss(h, dec_out, n_items)
+        dh, dW = self.backward(h, dec_in, dec_out, n_items, g_x0)
+        return loss, dh, dW
+
+    # algorithmic bytes per step, for roofline accounting
+    def algorithmic_bytes(self, distinct_rows: Optional[int] = None) -> dict:
+        n, d, K, V1 = self.B * self.L, self.d, self.K, self.V1
+        b = {
+            "gather_pe_mask": n * (8 + 4 * d + 4 * d + 4),
+            "sampled_score_loss_fwd": n * (4 * d + (1 + K) * (8 + 4 * d) + 4 + 4 * (1 + K)),
+            "sampled_score_bwd_dh": n * ((1 + K) * (8 + 4 * d + 4) + 4 * d),
+            "embedding_bwd": n * (2 + K) * (8 + 4 * d) + 4 * V1 * d
+            + (4 * d * distinct_rows if distinct_rows is not None else 0),
+        }
+        b["total"] = sum(b.values())
+        return b

@@ -1,0 +1,69 @@
+"""The C-ABI library builds, loads and exports every symbol include/recguru_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "recguru_b200.h").read_text()
+
+
+def declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    decls = re.findall(r"\b(recguru_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", body, flags=re.S)
+    out = {}
+    for name, args in decls:
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        out[name] = n
+    return out
+
+
+def test_header_declares_expected_entry_points():
+    fns = declared_functions()
+    for must in ("recguru_gather_pe_mask", "recguru_embedding_bwd", "recguru_sampled_score_loss_fwd",
+                 "recguru_catalog_topk_rank", "recguru_topk_merge", "recguru_rank_histogram"):
+        assert must in fns
+    assert len(fns) >= 19
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(str(built_lib))
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+
+
+def test_ctypes_table_matches_header(built_lib):
+    from recguru_b200 import _lib
+    fns = declared_functions()
+    assert set(_lib.SIGNATURES) == set(fns)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == fns[name], f"{name}: ctypes has {len(argtypes)} args, header {fns[name]}"
+    lib = _lib.load()
+    assert lib.recguru_abi_version() == _lib.ABI_VERSION
+    assert lib.recguru_last_error() == b""
+    assert _lib.launch_count() == 0
+    assert ctypes.sizeof(_lib.LookupSite) == 56
+
+
+def test_argument_validation_without_gpu(built_lib):
+    """Shape/argument checks return the documented negative codes before any CUDA call."""
+    from recguru_b200 import _lib
+    lib = _lib.load()
+    assert lib.recguru_gather_pe_mask(None, 10, 32, None, 4, 2, None, None, 0, None, None, None) == -1
+    assert b"null" in lib.recguru_last_error()
+    assert lib.recguru_embedding_bwd_workspace_bytes(-1, 10, 32) == -1
+    assert lib.recguru_embedding_bwd_workspace_bytes(1000, 100, 64) > 0
+    assert lib.recguru_catalog_workspace_bytes(100, 100, 128, 64) == -1      # k > 32
+    assert lib.recguru_sort_ids_workspace_bytes(4096, 1 << 20) > 4096 * 16
+    with pytest.raises(_lib.RecGuruError):
+        _lib.check(-2, "demo")
+
+
+def test_sources_are_sm100a_only():
+    from recguru_b200 import build
+    assert "arch=compute_100a,code=sm_100a" in build.NVCC_FLAGS
+    assert "-lineinfo" in build.NVCC_FLAGS
+    assert len(build.sources()) >= 5

@@ -1,0 +1,285 @@
+"""GPU parity: pieces 1-3 (gather+PE+mask, deterministic table backward, sampled scoring)
+against the oracle and the reference-generated golden fixtures.  All calls go through the
+C ABI (recguru_b200.ops raw layer -> ctypes -> librecguru_b200.so)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+from oracle import ref_path as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    from recguru_b200 import ops as _ops
+    return _ops
+
+
+def dev(x):
+    return x.cuda()
+
+
+# ---------------------------------------------------------------- piece 1 -------------------
+@pytest.mark.parametrize("d", [32, 64, 128, 256, 48])
+@pytest.mark.parametrize("B,L", [(1, 1), (3, 7), (64, 50), (17, 200)])
+def test_gather_pe_mask_bit_exact(ops, d, B, L):
+    torch.manual_seed(d * 1000 + B * 10 + L)
+    V1 = 503
+    W = torch.randn(V1, d); W[0] = 0
+    ids = torch.randint(0, V1, (B, L))
+    ids[torch.rand(B, L) < 0.4] = 0
+    pe = O.pe_table(max(L, 8), d)
+    ref, ref_mask = O.gather_pe_mask(W, ids, pe, 0)
+    out, mask = ops.raw_gather_pe_mask(dev(W), dev(ids), dev(pe), 0)
+    assert torch.equal(out.cpu(), ref)                      # values
+    assert torch.equal(out.cpu().view(torch.int32), ref.view(torch.int32))   # bits (incl. -0.0)
+    assert torch.equal(mask.cpu(), ref_mask)
+
+
+def test_gather_golden_all_models(ops):
+    g = load_golden("myrec_sas.npz")
+    out, mask = ops.raw_gather_pe_mask(dev(t(g["weight"])), dev(t(g["dec_in"])), dev(t(g["pe"])), 0)
+    assert torch.equal(out.cpu(), t(g["x0"])) and torch.equal(mask.cpu().view(-1), t(g["mask"]))
+    r = load_golden("myrec_recon.npz")
+    for ids, x in (("enc_in", "x_enc"), ("dec_in", "x_dec")):
+        out, _ = ops.raw_gather_pe_mask(dev(t(r["weight"])), dev(t(r[ids])), dev(t(r["pe"])), 0)
+        assert torch.equal(out.cpu(), t(r[x]))
+    c = load_golden("cross_a.npz")
+    L = int(c["L"])
+    out, _ = ops.raw_gather_pe_mask(dev(t(c["weight"])), dev(t(c["enc_in"])), dev(t(c["pe"])), -1,
+                                    mask_in=dev(t(c["enc_mask"]).view(-1, L)))
+    assert torch.equal(out.cpu(), t(c["x_enc"]))
+
+
+def test_plain_gather_and_pe_mask_ops(ops):
+    torch.manual_seed(1)
+    W = torch.randn(1000, 64)
+    ids = torch.randint(0, 1000, (9, 33))
+    out, _ = ops.raw_gather_pe_mask(dev(W), dev(ids), None, -1, want_mask=False)
+    assert torch.equal(out.cpu(), W[ids])
+    x = torch.randn(9, 33, 64)
+    mask = (torch.rand(9, 33) > 0.3).float()
+    pe = O.pe_table(40, 64)
+    ref = (x + pe[:, :33]) * mask.unsqueeze(2)
+    assert torch.equal(ops.raw_pe_mask(dev(x), dev(pe), dev(mask)).cpu(), ref)
+
+
+def test_gather_empty_and_errors(ops):
+    W = torch.randn(10, 32).cuda()
+    out, _ = ops.raw_gather_pe_mask(W, torch.zeros(0, 5, dtype=torch.int64).cuda(), None, -1, want_mask=False)
+    assert out.shape == (0, 5, 32)
+    with pytest.raises(RuntimeError):
+        ops.raw_gather_pe_mask(W.cpu(), torch.zeros(2, 2, dtype=torch.int64), None, -1)      # CPU tensor
+    with pytest.raises(RuntimeError):
+        ops.raw_gather_pe_mask(W, torch.zeros(2, 2, dtype=torch.int32).cuda(), None, -1)     # wrong dtype
+    from recguru_b200._lib import RecGuruError
+    with pytest.raises(RecGuruError):
+        ops.raw_gather_pe_mask(torch.randn(10, 30).cuda(), torch.zeros(2, 2, dtype=torch.int64).cuda(), None, -1)
+
+
+# ---------------------------------------------------------------- piece 2 -------------------
+@pytest.mark.parametrize("n,V1", [(1, 2), (31, 5), (4096, 70), (4097, 100003), (100000, 511),
+                                  (300001, 1 << 20), (50000, 10_000_002)])
+def test_sort_ids_bit_exact(ops, n, V1):
+    torch.manual_seed(n)
+    ids = torch.randint(0, V1, (n,))
+    if n > 100:
+        ids[torch.rand(n) < 0.3] = int(ids[0])      # heavy duplicates: stability matters
+    s_ref, p_ref = O.stable_sort_ids(ids)
+    s, p = ops.raw_sort_ids(dev(ids), V1)
+    assert torch.equal(s.cpu(), s_ref)
+    assert torch.equal(p.cpu(), p_ref)
+
+
+def _zipf(n, V1, seed):
+    from recguru_b200 import synth
+    return synth.zipf_ids(n, V1 - 2, seed=seed)
+
+
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+@pytest.mark.parametrize("n", [5, 64, 65, 1000, 30000])
+def test_embedding_bwd_single_site(ops, d, n):
+    torch.manual_seed(n + d)
+    V1 = 997
+    ids = _zipf(n, V1, seed=n)
+    ids[torch.rand(n) < 0.3] = 0
+    g = torch.randn(n, d)
+    ref = O.embedding_backward(ids, g, V1, padding_idx=0)
+    out = ops.raw_embedding_bwd([ops.Site(dev(ids), dev(g))], V1, d, padding_idx=0)
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+    assert float(out[0].abs().max()) == 0.0                       # padding row skipped
+    untouched = torch.ones(V1, dtype=torch.bool); untouched[ids] = False
+    assert float(out.cpu()[untouched].abs().max()) == 0.0         # dense zero fill
+    # no padding_idx: row 0 accumulates like any other
+    ref2 = O.embedding_backward(ids, g, V1, padding_idx=None)
+    out2 = ops.raw_embedding_bwd([ops.Site(dev(ids), dev(g))], V1, d, padding_idx=-1)
+    assert torch.allclose(out2.cpu(), ref2, rtol=1e-5, atol=2e-4)
+
+
+def test_embedding_bwd_hot_item_and_determinism(ops):
+    """One id owns 60 % of the occurrences (runs spanning hundreds of chunks); two runs must
+    agree bit for bit (no floating-point atomics)."""
+    torch.manual_seed(5)
+    n, V1, d = 200_000, 5003, 128
+    ids = torch.randint(1, V1, (n,))
+    ids[torch.rand(n) < 0.6] = 77
+    ids[:100] = 1          # run at the very start
+    ids[-300:] = V1 - 1    # run at the very end
+    g = torch.randn(n, d)
+    coef = torch.rand(n)
+    a = ops.raw_embedding_bwd([ops.Site(dev(ids), dev(g), dev(coef))], V1, d, padding_idx=0)
+    b = ops.raw_embedding_bwd([ops.Site(dev(ids), dev(g), dev(coef))], V1, d, padding_idx=0)
+    assert torch.equal(a, b)
+    ref = O.embedding_backward_sites([(ids, g, coef, 1)], V1, d, 0).float()
+    assert torch.allclose(a.cpu(), ref, rtol=2e-5, atol=2e-3)
+    rel = (a.cpu() - ref).norm() / ref.norm()
+    assert rel < 1e-6
+
+
+def test_embedding_bwd_multi_site_golden(ops):
+    """All lookup sites of a reference training step in ONE launch == the reference's W.grad."""
+    g = load_golden("myrec_sas.npz")
+    W = t(g["weight"]); V1, d = W.shape; K = int(g["K"])
+    h = dev(t(g["h"]).reshape(-1, d))
+    sites = [ops.Site(dev(t(g["dec_in"])), dev(t(g["g_in"]).reshape(-1, d))),
+             ops.Site(dev(t(g["dec_out"])), h, dev(t(g["dp"]).reshape(-1))),
+             ops.Site(dev(t(g["n_items"])), h, dev(t(g["dn"]).reshape(-1)), group=K)]
+    dW = ops.raw_embedding_bwd(sites, V1, d, padding_idx=0)
+    assert torch.allclose(dW.cpu(), t(g["dW"]), rtol=1e-5, atol=1e-6)
+
+    c = load_golden("cross_a.npz")                       # no padding_idx
+    W = t(c["weight"]); V1, d = W.shape; K = int(c["K"])
+    h = t(c["h"]).reshape(-1, d)
+    p = t(c["p_logits"]).clone().requires_grad_(True); n = t(c["n_logits"]).clone().requires_grad_(True)
+    O.bpr_loss(p, n, t(c["dec_mask"])).backward()
+    sites = [ops.Site(dev(t(c["enc_in"])), dev(t(c["g_enc"]).reshape(-1, d))),
+             ops.Site(dev(t(c["dec_in"])), dev(t(c["g_dec"]).reshape(-1, d))),
+             ops.Site(dev(t(c["dec_out"])), dev(h), dev(p.grad.reshape(-1))),
+             ops.Site(dev(t(c["n_items"])), dev(h), dev(n.grad.reshape(-1)), group=K)]
+    dW = ops.raw_embedding_bwd(sites, V1, d, padding_idx=-1)
+    assert torch.allclose(dW.cpu(), t(c["dW"]), rtol=1e-5, atol=1e-6)
+
+
+def test_embedding_bwd_accumulate_mode(ops):
+    torch.manual_seed(9)
+    V1, d, n = 300, 64, 5000
+    ids = torch.randint(0, V1, (n,)); g = torch.randn(n, d)
+    base = torch.randn(V1, d)
+    out = dev(base.clone())
+    ops.raw_embedding_bwd([ops.Site(dev(ids), dev(g))], V1, d, padding_idx=-1, out=out, zero_fill=False)
+    ref = base + O.embedding_backward(ids, g, V1, None)
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-4)
+
+
+# ---------------------------------------------------------------- piece 3 -------------------
+@pytest.mark.parametrize("kind", ["bpr", "bpr_sas", "sce"])
+@pytest.mark.parametrize("d,K", [(32, 5), (64, 5), (128, 5), (128, 30), (64, 30), (256, 3), (32, 1), (128, 31)])
+def test_sampled_score_loss_vs_oracle(ops, kind, d, K):
+    torch.manual_seed(d + K)
+    B, L, V1 = 7, 13, 401
+    W = torch.randn(V1, d) * 0.3; W[0] = 0
+    h = torch.randn(B, L, d) * 0.3
+    pos = torch.randint(0, V1, (B, L)); neg = torch.randint(1, V1, (B, L * K))
+    mask = (pos != 0).float().view(-1)
+    p_ref, n_ref = O.sampled_scores(h, W, pos, neg, L, K)
+    pr = p_ref.clone().requires_grad_(True); nr = n_ref.clone().requires_grad_(True)
+    loss_ref = O.LOSSES[kind](pr, nr, mask)
+    loss_ref.backward()
+    p, n, aux, dp, dn = ops.raw_sampled_score_loss(dev(h), dev(W), dev(pos), dev(neg), dev(mask), kind)
+    assert torch.allclose(p.cpu(), p_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(n.cpu(), n_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(aux[0].cpu(), loss_ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(aux[1].cpu(), 1.0 / mask.sum(), rtol=1e-6)
+    assert torch.allclose((dp * aux[1]).cpu(), pr.grad.view(-1), rtol=1e-4, atol=1e-7)
+    assert torch.allclose((dn * aux[1]).cpu(), nr.grad.view(-1, K), rtol=1e-4, atol=1e-7)
+    # loss-only entry point on the oracle's logits
+    aux2, dp2, dn2 = ops.raw_sampled_loss(dev(p_ref), dev(n_ref), dev(mask), kind)
+    assert torch.allclose(aux2[0].cpu(), loss_ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose((dp2 * aux2[1]).cpu(), pr.grad.view(-1), rtol=1e-4, atol=1e-7)
+    assert torch.allclose((dn2 * aux2[1]).cpu(), nr.grad.view(-1, K), rtol=1e-4, atol=1e-7)
+    # unmasked mean
+    _, _, aux3, _, _ = ops.raw_sampled_score_loss(dev(h), dev(W), dev(pos), dev(neg), None, kind)
+    assert torch.allclose(aux3[0].cpu(), O.LOSSES[kind](p_ref, n_ref, None), rtol=1e-5, atol=1e-6)
+
+
+def test_sampled_golden_losses(ops):
+    for name, kind, mkey in (("myrec_sas.npz", "bpr_sas", "mask"), ("cross_a.npz", "bpr", "dec_mask")):
+        g = load_golden(name)
+        p, n, aux, dp, dn = ops.raw_sampled_score_loss(dev(t(g["h"])), dev(t(g["weight"])), dev(t(g["dec_out"])),
+                                                       dev(t(g["n_items"])), dev(t(g[mkey])), kind)
+        assert torch.allclose(p.cpu(), t(g["p_logits"]), rtol=1e-5, atol=1e-5)
+        assert torch.allclose(n.cpu(), t(g["n_logits"]), rtol=1e-5, atol=1e-5)
+        assert torch.allclose(aux[0].cpu(), t(g["loss"]), rtol=1e-5)
+    r = load_golden("myrec_recon.npz")
+    K = int(r["K"])
+    p, n, aux, dp, dn = ops.raw_sampled_score_loss(dev(t(r["h"])), dev(t(r["weight"])), dev(t(r["dec_out"])),
+                                                   dev(t(r["n_items"])), dev(t(r["mask"])), "sce")
+    assert torch.allclose(torch.cat([p, n], 2).cpu(), t(r["logits"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(aux[0].cpu(), t(r["loss"]), rtol=1e-5)
+    dl = t(r["dlogits"]).reshape(-1, K + 1)
+    assert torch.allclose((dp * aux[1]).cpu(), dl[:, 0], rtol=1e-4, atol=1e-7)
+    assert torch.allclose((dn * aux[1]).cpu(), dl[:, 1:], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("d,K", [(32, 5), (64, 30), (128, 5), (256, 2)])
+def test_sampled_score_bwd_dh(ops, d, K):
+    torch.manual_seed(3 * d + K)
+    B, L, V1 = 5, 11, 211
+    W = torch.randn(V1, d); h = torch.randn(B, L, d, requires_grad=True)
+    pos = torch.randint(0, V1, (B, L)); neg = torch.randint(0, V1, (B, L * K))
+    p, n = O.sampled_scores(h, W, pos, neg, L, K)
+    gp = torch.randn_like(p); gn = torch.randn_like(n)
+    (p * gp).sum().add((n * gn).sum()).backward()
+    scale = torch.tensor([0.5]); scale2 = torch.tensor([4.0])
+    dh = ops.raw_sampled_score_bwd_dh(dev(gp.reshape(-1)), dev(gn.reshape(-1, K)), dev(W), dev(pos), dev(neg),
+                                      dev(scale), dev(scale2))
+    assert torch.allclose(dh.cpu(), 2.0 * h.grad, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------- op layer / autograd --------
+def test_modules_autograd_end_to_end_golden(ops):
+    """FusedItemEmbedding + FusedPositionalEncoding + fused loss reproduce the reference's loss
+    and W.grad for a SASRec BPR step, given the transformer's output h and its input gradient."""
+    from recguru_b200 import modules as M
+    g = load_golden("myrec_sas.npz")
+    emb = M.FusedItemEmbedding(*g["weight"].shape, padding_idx=0, _weight=t(g["weight"]).clone()).cuda()
+    pos_emb = M.FusedPositionalEncoding(32, dropout=0.5, max_len=64).cuda().eval()
+    assert torch.equal(pos_emb.pe.cpu(), t(g["pe"]))
+    x0, mask = emb.lookup_pe_mask(dev(t(g["dec_in"])), pos_emb, pad_index=0)
+    assert torch.equal(x0.detach().cpu(), t(g["x0"]))
+    # decomposed drop-in path gives the same bits
+    x0b = pos_emb(emb(dev(t(g["dec_in"]))), mask)
+    assert torch.equal(x0b.detach().cpu(), t(g["x0"]))
+    h = dev(t(g["h"])).requires_grad_(True)
+    loss, p, n = M.sampled_loss_fused(h, emb, dev(t(g["dec_out"])), dev(t(g["n_items"])), dev(t(g["mask"])), "bpr_sas")
+    assert torch.allclose(loss.detach().cpu(), t(g["loss"]), rtol=1e-5)
+    # the transformer sits between x0 and h in the reference; feed its recorded input gradient
+    (loss + (x0 * dev(t(g["g_x0"]))).sum()).backward()
+    assert torch.allclose(h.grad.cpu(), t(g["dh"]), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(emb.weight.grad.cpu(), t(g["dW"]), rtol=1e-5, atol=1e-6)
+    assert float(emb.weight.grad[0].abs().max()) == 0.0
+
+    # decomposed: scores op + loss module, as MyRec.forward + loss_bpr (train_auto.py:57-69)
+    emb.weight.grad = None
+    h2 = dev(t(g["h"])).requires_grad_(True)
+    p2, n2 = M.sampled_logits(h2, emb, dev(t(g["dec_out"])), dev(t(g["n_items"])))
+    assert p2.shape == (6, 12, 1) and n2.shape == (6, 12, 5)
+    l2 = M.FusedBPRLoss_sas()(p2, n2, mask=dev(t(g["mask"])))
+    x0c = pos_emb(emb(dev(t(g["dec_in"]))), mask)
+    (l2 + (x0c * dev(t(g["g_x0"]))).sum()).backward()
+    assert torch.allclose(l2.detach().cpu(), t(g["loss"]), rtol=1e-5)
+    assert torch.allclose(h2.grad.cpu(), t(g["dh"]), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(emb.weight.grad.cpu(), t(g["dW"]), rtol=1e-5, atol=1e-6)
+
+
+def test_sce_module_and_cat(ops):
+    from recguru_b200 import modules as M
+    r = load_golden("myrec_recon.npz")
+    K = int(r["K"])
+    emb = M.FusedItemEmbedding(*r["weight"].shape, padding_idx=0, _weight=t(r["weight"]).clone()).cuda()
+    logits = M.sampled_logits_cat(dev(t(r["h"])), emb, dev(t(r["dec_out"])), dev(t(r["n_items"])))
+    assert torch.allclose(logits.cpu(), t(r["logits"]), rtol=1e-5, atol=1e-5)
+    loss = M.FusedSampledCrossEntropyLoss()(logits, None, K + 1, mask=dev(t(r["mask"])))
+    assert torch.allclose(loss.cpu(), t(r["loss"]), rtol=1e-5)
