@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 #include <limits.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -37,11 +38,14 @@ constexpr int kBlockM = 128;
 constexpr int kBlockN = 128;
 constexpr int kStages = 4;       // smem ring of item tiles
 constexpr int kAccum = 4;        // TMEM accumulator buffers (4 x 128 columns)
-constexpr int kCatThreads = 320; // 10 warps
-constexpr int kEpiThreads = 256;
+static_assert(kStages == kAccum, "stage release piggybacks on the accumulator barrier");
 constexpr int kMaxK = 32;
+constexpr int kFmaSignCols = 16;  // of every 32 columns, sign bits accumulated on the FMA pipe
 
 enum CatalogMode { kModeTopK = 0, kModeDense = 1 };
+
+// debug profile (RECGURU_CATALOG_PROF=1): cycles CTA (0,0) spends in each wait, per role
+__device__ long long g_prof[16];
 
 struct CatalogParams {
   int64_t U;
@@ -56,6 +60,9 @@ struct CatalogParams {
   int64_t* out_id;       // [n_splits, U, k]
   int64_t* out_cnt;      // [n_splits, U]
   float* dense;          // kModeDense: [U, n_items]
+  const __nv_bfloat16* users;  // [U, d] (TS mode reads the user tile directly)
+  uint32_t two;          // the constant 2, opaque to the compiler (keeps IMAD.HI on the FMA pipe)
+  uint32_t debug_flags;  // bit 0: TMEM-load-only epilogue (timing floor experiments; wrong results)
 };
 
 __device__ __forceinline__ float next_below(float t) {
@@ -76,16 +83,26 @@ struct CatSmem {
   // barriers: full[kStages], empty[kStages], acc_full[kAccum], acc_empty[kAccum], a_full
   static constexpr int kNumBars = 2 * kStages + 2 * kAccum + 1;
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
-  static constexpr int kOffCnt = kOffTmemPtr + 8;         // int[128] (set-1 rank counts)
-  static constexpr int kOffList = kOffCnt + 128 * 4;      // float[2*k*128] then int[2*k*128]
-  static constexpr int bytes(int k) { return kOffList + 2 * k * 128 * 8 + 1024; }
+  static constexpr int kOffCnt = kOffTmemPtr + 8;         // int[nsets][128] (per-set rank counts)
+  // then float[nsets*k*128] scores and int[nsets*k*128] ids of the per-thread top-k lists
+  __host__ __device__ static constexpr int off_list(int nsets) { return kOffCnt + nsets * 128 * 4; }
+  __host__ __device__ static constexpr int bytes(int k, int nsets) { return off_list(nsets) + nsets * k * 128 * 8 + 1024; }
 };
 
-template <int D, int MODE>
-__global__ void __launch_bounds__(kCatThreads, 1)
+// CL = cluster size (1 or 2).  With CL == 2 the two CTAs of a cluster sweep the same item tiles
+// for different user tiles: each loads half of every item tile and TMA-multicasts it to both,
+// halving the L2 -> SM operand traffic (the item table is streamed once per CTA otherwise).
+// TS: the user tile (A operand) lives in TMEM for the whole sweep (written once with tcgen05.st),
+// so every MMA reads only the item tile from shared memory -- in SS mode the 128 x 16 A slice is
+// re-read from smem by each instruction and the N=128 MMA is shared-memory-bandwidth bound.
+// TMEM then holds 3 accumulators (384 columns) + A (64 columns).
+template <int D, int MODE, int NSETS, int CL, bool TS>
+__global__ void __launch_bounds__(64 + NSETS * 128, 1)
 catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                      const __grid_constant__ CUtensorMap map_items, CatalogParams p) {
   using L = CatSmem<D>;
+  constexpr int NACC = TS ? 3 : kAccum;     // accumulator ring == smem stage ring depth
+  constexpr uint32_t kTmemA = NACC * kBlockN; // TMEM column of the A operand (TS mode)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -97,8 +114,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
   uint64_t* bar_a = bars + 2 * kStages + 2 * kAccum;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
   int* s_cnt = reinterpret_cast<int*>(smem + L::kOffCnt);
-  float* s_val = reinterpret_cast<float*>(smem + L::kOffList);
-  int* s_id = reinterpret_cast<int*>(smem + L::kOffList + 2 * p.k * 128 * 4);
+  float* s_val = reinterpret_cast<float*>(smem + L::off_list(NSETS));
+  constexpr int kSlots = NSETS * 128;       // list entry i of slot s lives at [i * kSlots + s]
+  int* s_id = reinterpret_cast<int*>(smem + L::off_list(NSETS) + NSETS * p.k * 128 * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * kBlockM;
@@ -110,74 +128,127 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&map_users);
     ptx::tma_prefetch_desc(&map_items);
-    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&bar_full[i], 1); ptx::mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&bar_full[i], 1); ptx::mbar_init(&bar_empty[i], CL); }
     for (int i = 0; i < kAccum; ++i) { ptx::mbar_init(&bar_acc_full[i], 1); ptx::mbar_init(&bar_acc_empty[i], 4); }
-    ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_a, TS ? 4 : 1);
     ptx::mbar_fence_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_ptr, 512);
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();      // peer barriers initialised before any multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+  constexpr uint16_t kClMask = (1u << CL) - 1u;
+  const bool spin = (p.debug_flags & 256u) != 0;   // debug: busy-poll barriers
+  const bool prof = (p.debug_flags & 512u) != 0 && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops; one elected lane issues) ========
+    const bool leader = ptx::elect_one();
+    if (leader && !TS) {
       ptx::mbar_arrive_expect_tx(bar_a, L::kTileBytes);
       for (int kb = 0; kb < L::kKBlocks; ++kb)
         ptx::tma_load_2d(&map_users, bar_a, smem + L::kOffA + kb * (kBlockM * 128), kb * 64,
                          static_cast<int32_t>(m0));
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        ptx::mbar_wait(&bar_empty[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&bar_full[s], L::kTileBytes);
-        uint8_t* dst = smem + L::kOffB + s * L::kTileBytes;
-        const int32_t n0 = (tile_begin + j) * kBlockN;
-        for (int kb = 0; kb < L::kKBlocks; ++kb)
-          ptx::tma_load_2d(&map_items, &bar_full[s], dst + kb * (kBlockN * 128), kb * 64, n0);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      if (p.debug_flags & 32u) break;                 // debug: no smem-ring handshake at all
+      const int s = j % NACC;
+      const uint32_t ph = (j / NACC) & 1;
+      const long long tp0 = prof ? clock64() : 0;
+      // CL == 1: the stage of tile j-4 is free exactly when that tile's MMAs have retired, which
+      // is what acc_full[j % 4] signals to the epilogue -- one tcgen05.commit per tile serves both
+      // (kStages == kAccum).  CL == 2 needs the peer's MMAs too and keeps a separate barrier.
+      ptx::mbar_wait_warp(CL == 1 ? &bar_acc_full[s] : &bar_empty[s], ph ^ 1, spin);
+      if (prof && lane == 0) g_prof[0] += clock64() - tp0;
+      if (leader) {
+        if ((p.debug_flags & 4u) && j >= NACC) {   // debug: no operand traffic (timing floor)
+          ptx::mbar_arrive(&bar_full[s]);
+        } else {
+          ptx::mbar_arrive_expect_tx(&bar_full[s], L::kTileBytes);
+          uint8_t* dst = smem + L::kOffB + s * L::kTileBytes;
+          const int32_t n0 = (tile_begin + j) * kBlockN;
+          if (CL == 1) {
+            for (int kb = 0; kb < L::kKBlocks; ++kb)
+              ptx::tma_load_2d(&map_items, &bar_full[s], dst + kb * (kBlockN * 128), kb * 64, n0);
+          } else {
+            // this CTA fetches rows [rank*64, rank*64+64) of the tile for the whole cluster
+            constexpr int kHalf = kBlockN / CL;
+            for (int kb = 0; kb < L::kKBlocks; ++kb)
+              ptx::tma_load_2d_mcast(&map_items, &bar_full[s],
+                                     dst + kb * (kBlockN * 128) + cta_rank * (kHalf * 128), kb * 64,
+                                     n0 + static_cast<int32_t>(cta_rank) * kHalf, kClMask);
+          }
+        }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, kBlockN);
-      const uint32_t a_addr = ptx::smem_u32(smem + L::kOffA);
-      ptx::mbar_wait(bar_a, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        const int a = j % kAccum;
-        const uint32_t aph = (j / kAccum) & 1;
-        ptx::mbar_wait(&bar_acc_empty[a], aph ^ 1);
-        ptx::mbar_wait(&bar_full[s], ph);
-        ptx::tc_fence_after();
+    // ===================== MMA issuer (whole warp loops; one elected lane issues) ==========
+    const bool leader = ptx::elect_one();
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, kBlockN);
+    const uint32_t a_addr = ptx::smem_u32(smem + L::kOffA);
+    const int reps = (p.debug_flags & 16u) ? 0 : ((p.debug_flags & 8u) ? 2 : 1);  // debug knobs
+    ptx::mbar_wait_warp(bar_a, 0);
+    ptx::tc_fence_after();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % NACC;
+      const uint32_t ph = (j / NACC) & 1;
+      const int a = j % NACC;
+      const uint32_t aph = (j / NACC) & 1;
+      const long long tm0 = prof ? clock64() : 0;
+      if (!(p.debug_flags & 64u)) ptx::mbar_wait_warp(&bar_acc_empty[a], aph ^ 1, spin);
+      const long long tm1 = prof ? clock64() : 0;
+      if (!(p.debug_flags & 32u)) ptx::mbar_wait_warp(&bar_full[s], ph, spin);
+      const long long tm2 = prof ? clock64() : 0;
+      ptx::tc_fence_after();
+      if (leader) {
         const uint32_t b_addr = ptx::smem_u32(smem + L::kOffB + s * L::kTileBytes);
+        for (int rep = 0; rep < reps; ++rep) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t koff = (k / 4) * (kBlockM * 128) + (k % 4) * 32;  // bytes
-          ptx::umma_bf16(tmem_base + a * kBlockN, ptx::umma_smem_desc_sw128(a_addr + koff),
-                         ptx::umma_smem_desc_sw128(b_addr + koff), idesc, k > 0 ? 1u : 0u);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t koff = (k / 4) * (kBlockM * 128) + (k % 4) * 32;  // bytes
+            if (p.debug_flags & 1024u)   // debug: N=256 instruction rate (operands/accumulators overlap; timing only)
+              ptx::umma_bf16(tmem_base + (a & 1) * 256, ptx::umma_smem_desc_sw128(a_addr + koff),
+                             ptx::umma_smem_desc_sw128(ptx::smem_u32(smem + L::kOffB) + (k % 4) * 32),
+                             ptx::umma_idesc_bf16(kBlockM, 256), (k > 0 || rep > 0) ? 1u : 0u);
+            else if (TS)
+              ptx::umma_bf16_ts(tmem_base + a * kBlockN, tmem_base + kTmemA + k * 8,
+                                ptx::umma_smem_desc_sw128(b_addr + koff), idesc, (k > 0 || rep > 0) ? 1u : 0u);
+            else
+              ptx::umma_bf16(tmem_base + a * kBlockN, ptx::umma_smem_desc_sw128(a_addr + koff),
+                             ptx::umma_smem_desc_sw128(b_addr + koff), idesc, (k > 0 || rep > 0) ? 1u : 0u);
+          }
         }
-        ptx::umma_commit(&bar_empty[s]);     // smem stage free once these MMAs retire
-        ptx::umma_commit(&bar_acc_full[a]);  // accumulator ready for the epilogue
+        if (!(p.debug_flags & 32u)) {       // smem stage free (in every CTA of the cluster) once these MMAs retire
+          if (CL > 1) ptx::umma_commit_mcast(&bar_empty[s], kClMask);
+        }
+        if (p.debug_flags & 128u) ptx::mbar_arrive(&bar_acc_full[a]);     // debug: plain arrive instead of commit
+        else ptx::umma_commit(&bar_acc_full[a]);  // accumulator ready for the epilogue (and stage free)
+      }
+      __syncwarp();
+      if (prof && lane == 0) {
+        g_prof[1] += tm1 - tm0; g_prof[2] += tm2 - tm1; g_prof[3] += clock64() - tm2; g_prof[4] += 1;
       }
     }
   } else {
     // ===================== epilogue =====================
-    const int e = (warp - 2) >> 2;            // set: 0 even tiles, 1 odd tiles
+    const int e = (warp - 2) >> 2;            // epilogue set: handles tiles j == e (mod NSETS)
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int64_t u = m0 + row;
     const bool u_ok = u < p.U;
     const int K = p.k;
-    const int slot = e * 128 + row;           // list slot; entry i at [i * 256 + slot]
+    const uint32_t two = p.two;
+    const int slot = e * 128 + row;           // list slot; entry i at [i * kSlots + slot]
 
     float t = 0.f;
     int64_t tgt_local = -1;                   // target's row index inside the slice
     if (MODE == kModeTopK && u_ok) {
       t = p.tscore[u];
+      if (t == 0.f) t = 0.f;                // -0 -> +0 (the sign-bit count relies on it)
       tgt_local = p.target[u] - p.id_lo;
     }
     const float t_below = next_below(t);
@@ -189,126 +260,227 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     int cnt = 0;
     float thr = -CUDART_INF_F;
     if (MODE == kModeTopK) {
-      for (int i = 0; i < K; ++i) { s_val[i * 256 + slot] = -CUDART_INF_F; s_id[i * 256 + slot] = -1; }
+      for (int i = 0; i < K; ++i) { s_val[i * kSlots + slot] = -CUDART_INF_F; s_id[i * kSlots + slot] = -1; }
     }
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    if (TS && e == 0) {
+      // this thread's user row (128 bf16 = 64 packed words) -> TMEM lane `row`, columns kTmemA..
+      uint32_t av[64];
+      const uint4* src = reinterpret_cast<const uint4*>(p.users + (u_ok ? u : 0) * D);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const uint4 x = u_ok ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+        av[4 * q] = x.x; av[4 * q + 1] = x.y; av[4 * q + 2] = x.z; av[4 * q + 3] = x.w;
+      }
+      ptx::tmem_st_32x64(tmem_base + lane_base + kTmemA, av);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_a);
+    }
+    uint32_t cf[4] = {0u, 0u, 0u, 0u};        // sign-bit counters fed by the FMA pipe (IMAD.HI)
+    uint32_t ca[4] = {0u, 0u, 0u, 0u};        // sign-bit counters fed by the ALU pipe (LEA.HI)
+    uint32_t cf2[4] = {0u, 0u, 0u, 0u}, ca2[4] = {0u, 0u, 0u, 0u};
 
-    for (int j = e; j < n_tiles; j += 2) {
-      const int a = j % kAccum;
-      const uint32_t aph = (j / kAccum) & 1;
+    // sorted insert into this thread's list (desc score; equal scores keep arrival = id order)
+    auto insert = [&](float v, int id) {
+      int pos = K - 1;
+      while (pos > 0 && s_val[(pos - 1) * kSlots + slot] < v) {
+        s_val[pos * kSlots + slot] = s_val[(pos - 1) * kSlots + slot];
+        s_id[pos * kSlots + slot] = s_id[(pos - 1) * kSlots + slot];
+        --pos;
+      }
+      s_val[pos * kSlots + slot] = v;
+      s_id[pos * kSlots + slot] = id;
+      thr = s_val[(K - 1) * kSlots + slot];
+    };
+    for (int j = e; j < n_tiles; j += NSETS) {
+      const int a = j % NACC;
+      const uint32_t aph = (j / NACC) & 1;
       const int tile = tile_begin + j;
       const int n0 = tile * kBlockN;                                   // slice-local item index
       const int valid = static_cast<int>(rg::min64(kBlockN, p.n_items - n0));
-      ptx::mbar_wait(&bar_acc_full[a], aph);
+      if (p.debug_flags & 64u) break;                 // debug: no accumulator handshake at all
+      const long long te0 = prof ? clock64() : 0;
+      ptx::mbar_wait_warp(&bar_acc_full[a], aph, spin);
+      const long long te1 = prof ? clock64() : 0;
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + a * kBlockN;
-      const bool exact = (tile == tgt_tile) || (valid < kBlockN);
-      const float tcmp = tile < tgt_tile ? t_below : t;
+      bool released = false;
 
+      if (MODE == kModeDense) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-        uint32_t vr[32];
-        ptx::tmem_ld_32x32(taddr + c0, vr);
-        ptx::tmem_ld_wait();
-        if (MODE == kModeDense) {
+        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+          uint32_t vr[32];
+          ptx::tmem_ld_32x32(taddr + c0, vr);
+          ptx::tmem_ld_wait();
           if (u_ok) {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
               if (c0 + c < valid) p.dense[u * p.n_items + n0 + c0 + c] = __uint_as_float(vr[c]);
           }
-          continue;
         }
-        if (!exact) {
-          float mx = __uint_as_float(vr[0]);
-          int add = 0;
+      } else if (__any_sync(0xffffffffu, tile == tgt_tile) || valid < kBlockN) {
+        // exact tile (warp-uniform): some lane's target lives here and/or the tile runs past
+        // the end of the slice.  Per-column rules, 8 columns at a time.
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBlockN; c0 += 8) {
+          uint32_t w[8];
+          ptx::tmem_ld_32x8(taddr + c0, w);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float v = __uint_as_float(vr[c]);
-            add += (v > tcmp) ? 1 : 0;
-            mx = fmaxf(mx, v);
-          }
-          cnt += add;
-          if (mx > thr) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float v = __uint_as_float(vr[c]);
-              if (v > thr) {
-                int pos = K - 1;
-                while (pos > 0 && s_val[(pos - 1) * 256 + slot] < v) {
-                  s_val[pos * 256 + slot] = s_val[(pos - 1) * 256 + slot];
-                  s_id[pos * 256 + slot] = s_id[(pos - 1) * 256 + slot];
-                  --pos;
-                }
-                s_val[pos * 256 + slot] = v;
-                s_id[pos * 256 + slot] = n0 + c0 + c;
-                thr = s_val[(K - 1) * 256 + slot];
-              }
-            }
-          }
-        } else {
-          // exact path: tile holds the target and/or runs past the end of the slice
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
+          for (int c = 0; c < 8; ++c) {
             const int col = c0 + c;
-            const float v = __uint_as_float(vr[c]);
+            const float v = __uint_as_float(w[c]);
             if (col < valid) {
               if (tile == tgt_tile) {
                 if (col < tgt_col) cnt += (v >= t) ? 1 : 0;
                 else if (col > tgt_col) cnt += (v > t) ? 1 : 0;
               } else {
-                cnt += (v > tcmp) ? 1 : 0;
+                cnt += (v > (tile < tgt_tile ? t_below : t)) ? 1 : 0;
               }
-              if (v > thr) {
-                int pos = K - 1;
-                while (pos > 0 && s_val[(pos - 1) * 256 + slot] < v) {
-                  s_val[pos * 256 + slot] = s_val[(pos - 1) * 256 + slot];
-                  s_id[pos * 256 + slot] = s_id[(pos - 1) * 256 + slot];
-                  --pos;
-                }
-                s_val[pos * 256 + slot] = v;
-                s_id[pos * 256 + slot] = n0 + col;
-                thr = s_val[(K - 1) * 256 + slot];
+              if (v > thr) insert(v, n0 + col);
+            }
+          }
+        }
+      } else {
+        // fast tile: d = tcmp - v has its sign bit set iff v > tcmp (exact: IEEE subtraction is
+        // zero only for equal operands, tcmp is never -0).  FADD2 forms two differences per
+        // instruction on the FMA pipe; the sign bits are accumulated half on the FMA pipe
+        // (IMAD.HI by a run-time 2) and half on the ALU pipe (LEA.HI), the 8-column group maxima
+        // with FMNMX3 on the ALU pipe.  TMEM loads are double buffered against the compute.
+        const float tcmp = tile < tgt_tile ? t_below : t;
+        uint64_t tt;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(tt) : "f"(tcmp));
+        // NSETS=2: the whole accumulator row in one TMEM load (128 registers, a single wait per
+        // tile; the other set's load overlaps this warp's compute).  NSETS=4: two 64-column loads
+        // (the register file only allows ~100 registers per thread with 18 warps).
+        constexpr int CH = NSETS == 2 ? kBlockN : 64;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBlockN; c0 += CH) {
+          uint32_t vr[CH];
+          ptx::tmem_ld_cols<CH>(taddr + c0, vr);
+          ptx::tmem_ld_wait();
+          if (p.debug_flags & 1u) {
+            ca[0] += vr[0] ^ vr[CH - 1];   // debug: TMEM-load-only floor (results meaningless)
+            continue;
+          }
+          // (a) 8-column group maxima first: they decide whether the top-k lists must be touched
+          float gm[CH / 8];
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) {
+            const float* f = reinterpret_cast<const float*>(&vr[g * 8]);
+            gm[g] = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
+          }
+          float mx = gm[0];
+#pragma unroll
+          for (int g = 1; g < CH / 8; ++g) mx = fmaxf(mx, gm[g]);
+          if (__any_sync(0xffffffffu, mx > thr)) {
+            // rare: some lane's threshold was beaten.  Per-lane bitmask of the 8-column groups
+            // that did it; the warp walks the union and re-reads just those groups from TMEM
+            // (the accumulator is still ours; warp-uniform loop => convergent .sync.aligned load)
+            uint32_t gmask = 0;
+#pragma unroll
+            for (int g = 0; g < CH / 8; ++g) gmask |= (gm[g] > thr ? 1u : 0u) << g;
+            uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
+            while (wmask) {
+              const int g = __ffs(wmask) - 1;
+              wmask &= wmask - 1;
+              uint32_t w8[8];
+              ptx::tmem_ld_32x8(taddr + c0 + g * 8, w8);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float v = __uint_as_float(w8[c]);
+                if (v > thr) insert(v, n0 + c0 + g * 8 + c);
+              }
+            }
+          }
+          // (b) the scores now live in registers only: hand the accumulator back to the MMA warp
+          // before the (long) rank count
+          if (c0 + CH == kBlockN) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+            released = true;
+          }
+          // (c) rank count: four differences (two FADD2) ahead of their sign accumulation so the
+          // FMA-pipe latency overlaps
+#pragma unroll
+          for (int c = 0; c < CH; c += 8) {
+            uint64_t dd[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint64_t vv;
+              asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "r"(vr[c + 2 * q]), "r"(vr[c + 2 * q + 1]));
+              asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dd[q]) : "l"(tt), "l"(vv));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t d0, d1;
+              asm("mov.b64 {%0, %1}, %2;" : "=r"(d0), "=r"(d1) : "l"(dd[q]));
+              if (((c + 2 * q) & 31) < kFmaSignCols) {
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf[q]) : "r"(d0), "r"(two));
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf2[q]) : "r"(d1), "r"(two));
+              } else {
+                ca[q] += d0 >> 31;
+                ca2[q] += d1 >> 31;
               }
             }
           }
         }
       }
-      // this warp is done reading accumulator `a`
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+      // this warp is done reading accumulator `a` (the fast path released it already)
+      if (!released) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+      }
+      if (prof && lane == 0 && (warp == 2 || warp == 6)) {
+        const int o = warp == 2 ? 5 : 8;
+        g_prof[o] += te1 - te0; g_prof[o + 1] += clock64() - te1; g_prof[o + 2] += 1;
+      }
     }
+    cnt += static_cast<int>(cf[0] + cf[1] + cf[2] + cf[3] + ca[0] + ca[1] + ca[2] + ca[3] + cf2[0] + cf2[1] +
+                            cf2[2] + cf2[3] + ca2[0] + ca2[1] + ca2[2] + ca2[3]);
 
     if (MODE == kModeTopK) {
-      if (e == 1) s_cnt[row] = cnt;
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      s_cnt[e * 128 + row] = cnt;
+      asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128) : "memory");
       if (e == 0 && u_ok) {
-        // merge the two sets' lists: (score desc, id asc)
-        const int slot1 = 128 + row;
-        int i0 = 0, i1 = 0;
+        // merge the NSETS lists of this row: (score desc, id asc)
+        int head[NSETS];
+#pragma unroll
+        for (int q = 0; q < NSETS; ++q) head[q] = 0;
         const int64_t out = (static_cast<int64_t>(blockIdx.y) * p.U + u) * K;
         for (int i = 0; i < K; ++i) {
-          const float v0 = i0 < K ? s_val[i0 * 256 + slot] : -CUDART_INF_F;
-          const float v1 = i1 < K ? s_val[i1 * 256 + slot1] : -CUDART_INF_F;
-          const int d0 = i0 < K ? s_id[i0 * 256 + slot] : -1;
-          const int d1 = i1 < K ? s_id[i1 * 256 + slot1] : -1;
-          bool take0;
-          if (d1 < 0) take0 = true;
-          else if (d0 < 0) take0 = false;
-          else take0 = (v0 > v1) || (v0 == v1 && d0 < d1);
-          const float v = take0 ? v0 : v1;
-          const int d = take0 ? d0 : d1;
-          if (take0) ++i0; else ++i1;
-          p.out_val[out + i] = d >= 0 ? v : -CUDART_INF_F;
-          p.out_id[out + i] = d >= 0 ? p.id_lo + d : -1;
+          float bv = -CUDART_INF_F;
+          int bd = -1, bq = -1;
+#pragma unroll
+          for (int q = 0; q < NSETS; ++q) {
+            if (head[q] < K) {
+              const float v = s_val[head[q] * kSlots + q * 128 + row];
+              const int d = s_id[head[q] * kSlots + q * 128 + row];
+              if (d >= 0 && (bq < 0 || v > bv || (v == bv && d < bd))) { bv = v; bd = d; bq = q; }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < NSETS; ++q)
+            if (q == bq) ++head[q];
+          p.out_val[out + i] = bd >= 0 ? bv : -CUDART_INF_F;
+          p.out_id[out + i] = bd >= 0 ? p.id_lo + bd : -1;
         }
-        p.out_cnt[static_cast<int64_t>(blockIdx.y) * p.U + u] = cnt + s_cnt[row];
+        int total = 0;
+#pragma unroll
+        for (int q = 0; q < NSETS; ++q) total += s_cnt[q * 128 + row];
+        p.out_cnt[static_cast<int64_t>(blockIdx.y) * p.U + u] = total;
       }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();      // no CTA leaves while its peer may still signal it
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -421,13 +593,14 @@ static EncodeTiledFn get_encoder() {
   return fn;
 }
 
-// [rows, d] bf16 row-major -> box {64 columns, 128 rows}, 128-byte swizzle, OOB rows = 0
-static int make_rowmajor_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d) {
+// [rows, d] bf16 row-major -> box {64 columns, box_rows rows}, 128-byte swizzle, OOB rows = 0
+static int make_rowmajor_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d,
+                             int box_rows = 128) {
   EncodeTiledFn enc = get_encoder();
   RG_REQUIRE(enc != nullptr, RECGURU_E_CUDA, "catalog: cuTensorMapEncodeTiled unavailable");
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d) * 2};
-  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
                          gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -449,23 +622,74 @@ static int pick_splits(int64_t U, int64_t n_items) {
   return static_cast<int>(s);
 }
 
-template <int D, int MODE>
-static int launch_sweep(const CUtensorMap& mu, const CUtensorMap& mi, const CatalogParams& p,
-                        cudaStream_t st) {
-  const int smem = CatSmem<D>::bytes(MODE == kModeTopK ? p.k : 0);
-  static bool attr_set[kMaxK + 1] = {};
-  const int key = MODE == kModeTopK ? p.k : 0;
-  if (!attr_set[key]) {
-    cudaError_t e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int D, int MODE, int NSETS, int CL, bool TS>
+static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const CatalogParams& p,
+                          cudaStream_t st) {
+  const int smem = CatSmem<D>::bytes(MODE == kModeTopK ? p.k : 0, NSETS);
+  RG_REQUIRE(smem <= 227 * 1024, RECGURU_E_UNSUPPORTED, "catalog: k=%d needs %d B of shared memory", p.k, smem);
+  auto kern = catalog_sweep_kernel<D, MODE, NSETS, CL, TS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog: cudaFuncSetAttribute: %s",
                cudaGetErrorString(e));
-    attr_set[key] = true;
+    attr_set = true;
   }
-  const dim3 grid(static_cast<unsigned>(ceil_div(p.U, kBlockM)), static_cast<unsigned>(p.n_splits));
-  catalog_sweep_kernel<D, MODE><<<grid, kCatThreads, smem, st>>>(mu, mi, p);
+  if (p.debug_flags & 512u) {
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+  }
+  cudaLaunchConfig_t cfg = {};
+  const int64_t m_tiles = ceil_div(p.U, kBlockM);
+  cfg.gridDim = dim3(static_cast<unsigned>(ceil_div(m_tiles, CL) * CL), static_cast<unsigned>(p.n_splits));
+  cfg.blockDim = dim3(64 + NSETS * 128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mu, mi, p);
+  RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog_sweep: launch failed: %s", cudaGetErrorString(e));
   RG_CHECK_LAUNCH("catalog_sweep");
+  if (p.debug_flags & 512u) {
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+    fprintf(stderr, "[prof cta0] producer wait_empty %lld | mma wait_acc_empty %lld wait_full %lld issue %lld tiles %lld | "
+            "epi set0 wait_full %lld work %lld tiles %lld | epi set1 wait_full %lld work %lld tiles %lld\n",
+            h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10]);
+  }
   return RECGURU_OK;
+}
+
+// Epilogue sets: 2 (8 warps, one 128-register TMEM load per tile) by default; 4 is kept for
+// experiments.  Cluster of 2 with TMA multicast whenever there are at least two user tiles.
+template <int D, int MODE>
+static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams p, cudaStream_t st) {
+  p.two = 2u;
+  p.debug_flags = static_cast<uint32_t>(env_int("RECGURU_CATALOG_DEBUG", 0));
+  int nsets = env_int("RECGURU_CATALOG_SETS", 2);
+  if (nsets != 2 && nsets != 4) nsets = 2;
+  if (CatSmem<D>::bytes(MODE == kModeTopK ? p.k : 0, 4) > 227 * 1024) nsets = 2;
+  int cl = env_int("RECGURU_CATALOG_CLUSTER", 1);
+  if (cl != 1 && cl != 2) cl = 1;
+  if (p.U <= kBlockM) cl = 1;
+  CUtensorMap mi;
+  int rc = make_rowmajor_map(&mi, items, p.n_items, D, kBlockN / cl);
+  if (rc) return rc;
+  const bool ts = D == 128 && env_int("RECGURU_CATALOG_TS", 0) != 0;
+  if (ts) {   // experimental knob: measured no faster than SS; 2 epilogue sets only
+    if constexpr (D == 128) return launch_sweep_n<D, MODE, 2, 1, true>(mu, mi, p, st);
+  }
+  if (nsets == 4) return cl == 2 ? launch_sweep_n<D, MODE, 4, 2, false>(mu, mi, p, st) : launch_sweep_n<D, MODE, 4, 1, false>(mu, mi, p, st);
+  return cl == 2 ? launch_sweep_n<D, MODE, 2, 2, false>(mu, mi, p, st) : launch_sweep_n<D, MODE, 2, 1, false>(mu, mi, p, st);
 }
 
 static int check_catalog(const char* who, const void* users, int64_t U, const void* items,
@@ -532,15 +756,14 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
              "catalog_topk_rank: null pointer");
   RG_REQUIRE(k >= 1 && k <= kMaxK, RECGURU_E_UNSUPPORTED, "catalog_topk_rank: k=%lld not in [1,%d]",
              (long long)k, kMaxK);
-  CUtensorMap mu, mi;
+  CUtensorMap mu;
   rc = make_rowmajor_map(&mu, users_bf16, U, d);
-  if (rc) return rc;
-  rc = make_rowmajor_map(&mi, items_bf16, n_items, d);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CatalogParams p;
   p.U = U; p.n_items = n_items; p.id_lo = id_lo; p.target = target; p.tscore = target_score;
-  p.k = static_cast<int>(k); p.dense = nullptr;
+  p.k = static_cast<int>(k); p.dense = nullptr; p.two = 2u;
+  p.users = static_cast<const __nv_bfloat16*>(users_bf16);
   p.n_splits = pick_splits(U, n_items);
   const int64_t n_tiles = ceil_div(n_items, kBlockN);
   p.tiles_per_split = static_cast<int>(ceil_div(n_tiles, p.n_splits));
@@ -557,7 +780,7 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
     p.out_id = reinterpret_cast<int64_t*>(ws + sv);
     p.out_cnt = reinterpret_cast<int64_t*>(ws + sv + si);
   }
-  rc = d == 64 ? launch_sweep<64, kModeTopK>(mu, mi, p, st) : launch_sweep<128, kModeTopK>(mu, mi, p, st);
+  rc = d == 64 ? launch_sweep<64, kModeTopK>(items_bf16, mu, p, st) : launch_sweep<128, kModeTopK>(items_bf16, mu, p, st);
   if (rc) return rc;
   if (p.n_splits > 1)
     return recguru_topk_merge(p.out_val, p.out_id, p.out_cnt, p.n_splits, U, k, topk_val, topk_id,
@@ -572,16 +795,15 @@ extern "C" int recguru_catalog_scores_dense(const void* users_bf16, int64_t U,
   int rc = check_catalog("catalog_scores_dense", users_bf16, U, items_bf16, n_items, d);
   if (rc) return rc;
   RG_REQUIRE(scores, RECGURU_E_SHAPE, "catalog_scores_dense: null pointer");
-  CUtensorMap mu, mi;
+  CUtensorMap mu;
   rc = make_rowmajor_map(&mu, users_bf16, U, d);
-  if (rc) return rc;
-  rc = make_rowmajor_map(&mi, items_bf16, n_items, d);
   if (rc) return rc;
   CatalogParams p;
   memset(&p, 0, sizeof(p));
-  p.U = U; p.n_items = n_items; p.k = 1; p.dense = scores;
+  p.U = U; p.n_items = n_items; p.k = 1; p.dense = scores; p.two = 2u;
+  p.users = static_cast<const __nv_bfloat16*>(users_bf16);
   p.n_splits = pick_splits(U, n_items);
   p.tiles_per_split = static_cast<int>(ceil_div(ceil_div(n_items, kBlockN), p.n_splits));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return d == 64 ? launch_sweep<64, kModeDense>(mu, mi, p, st) : launch_sweep<128, kModeDense>(mu, mi, p, st);
+  return d == 64 ? launch_sweep<64, kModeDense>(items_bf16, mu, p, st) : launch_sweep<128, kModeDense>(items_bf16, mu, p, st);
 }

@@ -94,54 +94,77 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total, int shift, i
     block_hist[static_cast<int64_t>(b) * gridDim.x + blockIdx.x] = s_hist[b];
 }
 
-// Exclusive scan of the digit-major histogram (single CTA; n = bins * n_tiles entries).
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ hist, int64_t n) {
-  __shared__ uint32_t s_warp[32];
-  const int tid = threadIdx.x;
-  const int64_t per = (n + 1023) / 1024;
-  const int64_t lo = tid * per, hi = min(n, lo + per);
-  uint32_t sum = 0;
-  for (int64_t i = lo; i < hi; ++i) sum += hist[i];
-  // block exclusive scan of `sum`
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((tid & 31) >= o) incl += v;
-  }
-  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+// Exclusive scan of one digit's row of the digit-major histogram (CTA b <-> digit b); the row
+// total goes to totals[b].  The scatter kernel adds the digit base (scan over totals) itself.
+__global__ void __launch_bounds__(256)
+radix_scan_rows_kernel(uint32_t* __restrict__ hist, int n_tiles, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* row = hist + static_cast<int64_t>(blockIdx.x) * n_tiles;
+  if (tid == 0) s_carry = 0;
   __syncthreads();
-  if (tid < 32) {
-    uint32_t w = s_warp[tid], wi = w;
+  for (int t0 = 0; t0 < n_tiles; t0 += 256) {
+    const int i = t0 + tid;
+    const uint32_t v = i < n_tiles ? row[i] : 0u;
+    uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-      if (tid >= o) wi += v;
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
     }
-    s_warp[tid] = wi - w;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+      if (w < warp) wbase += s_warp[w];
+    const uint32_t carry = s_carry;
+    if (i < n_tiles) row[i] = carry + wbase + incl - v;
+    __syncthreads();
+    if (tid == 255) s_carry = carry + wbase + incl;
+    __syncthreads();
   }
-  __syncthreads();
-  uint32_t run = s_warp[tid >> 5] + incl - sum;
-  for (int64_t i = lo; i < hi; ++i) {
-    const uint32_t v = hist[i];
-    hist[i] = run;
-    run += v;
-  }
+  if (tid == 0) totals[blockIdx.x] = s_carry;
 }
 
 template <bool kFirstPass, typename OutVal>
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      int64_t total, int shift, int bits,
-                     const uint32_t* __restrict__ block_base /* scanned [bins][grid] */,
+                     const uint32_t* __restrict__ block_base /* row-scanned [bins][grid] */,
+                     const uint32_t* __restrict__ totals /* [bins] */,
                      uint32_t* __restrict__ keys_out, OutVal* __restrict__ vals_out,
                      int64_t* __restrict__ keys_out64 /* optional widened copy (last pass) */) {
   __shared__ uint32_t s_cnt[kSortThreads / 32][kMaxBins];
+  __shared__ uint32_t s_base[kMaxBins];      // exclusive scan of the digit totals
+  __shared__ uint32_t s_wsum[kSortThreads / 32];
   const int bins = 1 << bits;
   const uint32_t mask = bins - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = threadIdx.x; b < (kSortThreads / 32) * kMaxBins; b += kSortThreads)
     (&s_cnt[0][0])[b] = 0;
+  {
+    // 256 threads x 2 consecutive digits = 512 = kMaxBins
+    const int b0 = threadIdx.x * 2;
+    const uint32_t t0 = b0 < bins ? totals[b0] : 0u;
+    const uint32_t t1 = b0 + 1 < bins ? totals[b0 + 1] : 0u;
+    uint32_t incl = t0 + t1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w)
+      if (w < warp) wbase += s_wsum[w];
+    const uint32_t excl = wbase + incl - (t0 + t1);
+    s_base[b0] = excl;
+    s_base[b0 + 1] = excl + t0;
+  }
   __syncthreads();
 
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kSortTile + warp * (32 * kSortItems);
@@ -167,7 +190,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __syncthreads();
   // per-digit exclusive prefix over the warps of this CTA, seeded with the global base
   for (int b = threadIdx.x; b < bins; b += kSortThreads) {
-    uint32_t run = block_base[static_cast<int64_t>(b) * gridDim.x + blockIdx.x];
+    uint32_t run = s_base[b] + block_base[static_cast<int64_t>(b) * gridDim.x + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < kSortThreads / 32; ++w) {
       const uint32_t c = s_cnt[w][b];
@@ -201,7 +224,7 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, 
 // ---- 4. chunked segmented reduce -----------------------------------------------------
 // VPL = float4 per lane (ceil(d/4/32)).
 template <int VPL>
-__global__ void __launch_bounds__(kReduceWarps * 32)
+__global__ void __launch_bounds__(kReduceWarps * 32, VPL == 1 ? 3 : 1)
 chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
                     const uint32_t* __restrict__ svals, int64_t total, int vec /* d/4 */,
                     int64_t padding_idx, int accumulate, float4* __restrict__ dW,
@@ -216,7 +239,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
   constexpr int kPer = kChunk / 32;
   uint32_t l_key[kPer];
   int l_site[kPer];
-  int64_t l_row[kPer];
+  int l_row[kPer];
   float l_coef[kPer];
 #pragma unroll
   for (int q = 0; q < kPer; ++q) {
@@ -231,7 +254,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
       const int s = find_site(st, occ);
       const int64_t j = occ - st.offset[s];
       l_site[q] = s;
-      l_row[q] = j / st.group[s];
+      l_row[q] = static_cast<int>(j / st.group[s]);
       float c = st.coef[s] ? st.coef[s][j] : 1.f;
       if (st.scale[s]) c *= *st.scale[s];
       if (st.scale2[s]) c *= *st.scale2[s];
@@ -264,7 +287,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
       // select the register of slot q (kPer is tiny; keep it branch-free)
       uint32_t kk = l_key[0];
       int ss = l_site[0];
-      int64_t rr = l_row[0];
+      int rr = l_row[0];
       float cc = l_coef[0];
 #pragma unroll
       for (int t = 1; t < kPer; ++t)
@@ -423,7 +446,7 @@ struct SortPlan {
   int total_bits, passes, bits_per_pass;
   int64_t n_tiles;
   // workspace carve-up (bytes, 256-aligned)
-  int64_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_hist, end;
+  int64_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_hist, off_totals, end;
 };
 
 static SortPlan make_sort_plan(int64_t count, int64_t V1) {
@@ -441,6 +464,7 @@ static SortPlan make_sort_plan(int64_t count, int64_t V1) {
   p.off_vals_a = o; o += kb;
   p.off_vals_b = o; o += kb;
   p.off_hist = o; o += align_up(static_cast<int64_t>(kMaxBins) * p.n_tiles * 4, 256);
+  p.off_totals = o; o += align_up(kMaxBins * 4, 256);
   p.end = o;
   return p;
 }
@@ -455,6 +479,7 @@ static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, cudaStream
   uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(ws + p.off_vals_a),
                        reinterpret_cast<uint32_t*>(ws + p.off_vals_b)};
   uint32_t* hist = reinterpret_cast<uint32_t*>(ws + p.off_hist);
+  uint32_t* totals = reinterpret_cast<uint32_t*>(ws + p.off_totals);
   const unsigned grid = static_cast<unsigned>(p.n_tiles);
   int cur = 0;
   for (int pass = 0; pass < p.passes; ++pass) {
@@ -462,23 +487,23 @@ static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, cudaStream
     const int bits = min(p.bits_per_pass, p.total_bits - shift);
     radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(keys[cur], count, shift, bits, hist);
     RG_CHECK_LAUNCH("radix_hist");
-    radix_scan_kernel<<<1, 1024, 0, st>>>(hist, (1ll << bits) * p.n_tiles);
-    RG_CHECK_LAUNCH("radix_scan");
+    radix_scan_rows_kernel<<<1u << bits, 256, 0, st>>>(hist, static_cast<int>(p.n_tiles), totals);
+    RG_CHECK_LAUNCH("radix_scan_rows");
     const bool last = pass == p.passes - 1;
     if (last && out_perm64) {
       if (pass == 0)
         radix_scatter_kernel<true, int64_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], out_perm64, out_keys64);
+            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
       else
         radix_scatter_kernel<false, int64_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], out_perm64, out_keys64);
+            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
     } else {
       if (pass == 0)
         radix_scatter_kernel<true, uint32_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], vals[cur ^ 1], nullptr);
+            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
       else
         radix_scatter_kernel<false, uint32_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, keys[cur ^ 1], vals[cur ^ 1], nullptr);
+            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
     }
     RG_CHECK_LAUNCH("radix_scatter");
     cur ^= 1;

@@ -115,7 +115,8 @@ extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d
                                       const float* pe, const float* mask_in, int64_t pad_index,
                                       float* out, float* mask_out, recguru_stream_t stream) {
   using namespace rg;
-  RG_REQUIRE(weight && ids && out, RECGURU_E_SHAPE, "gather_pe_mask: null pointer");
+  RG_REQUIRE(weight && (n_tokens == 0 || (ids && out)), RECGURU_E_SHAPE,
+             "gather_pe_mask: null pointer");
   RG_REQUIRE(V1 > 0 && V1 < (1ll << 31) && n_tokens >= 0 && L > 0, RECGURU_E_SHAPE,
              "gather_pe_mask: bad sizes V1=%lld n_tokens=%lld L=%lld", (long long)V1,
              (long long)n_tokens, (long long)L);

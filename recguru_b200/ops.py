@@ -564,6 +564,7 @@ def _setup_gather_pe_mask(ctx, inputs, output):
     weight, ids, pe, pad_index = inputs
     _, mask = output
     ctx.save_for_backward(ids, mask)
+    ctx.mark_non_differentiable(mask)   # a 0/1 function of the ids: keep it out of the graph
     ctx.V1 = weight.shape[0]
 
 

@@ -108,14 +108,19 @@ def test_embedding_bwd_single_site(ops, d, n):
     g = torch.randn(n, d)
     ref = O.embedding_backward(ids, g, V1, padding_idx=0)
     out = ops.raw_embedding_bwd([ops.Site(dev(ids), dev(g))], V1, d, padding_idx=0)
-    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+    # fp32 summation-order tolerance: a few ulps of the row's sum of magnitudes (the Zipf head
+    # item owns thousands of occurrences); plus an aggregate relative-norm bound
+    mag = O.embedding_backward(ids, g.abs(), V1, padding_idx=0)
+    assert bool(((out.cpu() - ref).abs() <= 2e-6 * mag + 1e-6).all())
+    assert float((out.cpu() - ref).norm() / ref.norm()) < 1e-6
     assert float(out[0].abs().max()) == 0.0                       # padding row skipped
     untouched = torch.ones(V1, dtype=torch.bool); untouched[ids] = False
     assert float(out.cpu()[untouched].abs().max()) == 0.0         # dense zero fill
     # no padding_idx: row 0 accumulates like any other
     ref2 = O.embedding_backward(ids, g, V1, padding_idx=None)
     out2 = ops.raw_embedding_bwd([ops.Site(dev(ids), dev(g))], V1, d, padding_idx=-1)
-    assert torch.allclose(out2.cpu(), ref2, rtol=1e-5, atol=2e-4)
+    mag2 = O.embedding_backward(ids, g.abs(), V1, padding_idx=None)
+    assert bool(((out2.cpu() - ref2).abs() <= 2e-6 * mag2 + 1e-6).all())
 
 
 def test_embedding_bwd_hot_item_and_determinism(ops):
