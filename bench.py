@@ -216,8 +216,13 @@ def bench_train(D: Dist, args, peaks):
                 for j, nme in enumerate(stage_names)}
     # distinct touched rows (for the algorithmic bytes of the table backward)
     tb0 = batches[0]["tb"]
-    distinct = int(torch.unique(torch.cat([tb0.dec_in.view(-1), tb0.dec_out.view(-1), tb0.n_items.view(-1)])).numel())
-    abytes = hp.algorithmic_bytes(distinct)
+    m0 = tb0.mask.view(-1) != 0                                   # positions that carry gradient
+    live_ids = torch.cat([tb0.dec_in.view(-1)[m0 & (tb0.dec_in.view(-1) != 0)],
+                          tb0.dec_out.view(-1)[m0 & (tb0.dec_out.view(-1) != 0)],
+                          tb0.n_items.view(-1, cfg["K"])[m0].reshape(-1)])
+    live, distinct = int(live_ids.numel()), int(torch.unique(live_ids).numel())
+    abytes = hp.algorithmic_bytes(distinct, live, int(m0.sum()))
+    abytes_dense = hp.algorithmic_bytes(distinct, None, None)
     stages = {nme: {"ms": round(stage_ms[nme], 4), "algorithmic_mb": round(abytes[nme] / 1e6, 1),
                     "gbs": round(abytes[nme] / 1e6 / stage_ms[nme], 1),
                     "frac_of_hbm_peak": round(abytes[nme] / 1e6 / stage_ms[nme] / peaks["hbm"], 3)}
@@ -253,6 +258,11 @@ def bench_train(D: Dist, args, peaks):
                         "and are device resident"},
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
+        "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,
+                           "distinct_rows": distinct,
+                           "algorithmic_mb_if_all_live": round(abytes_dense["embedding_bwd"] / 1e6, 1),
+                           "note": "dead indices (pad id or zero coefficient under the pad mask) are compacted "
+                                   "away before the sort; roofline numerator counts only their 12 B id+coef"},
     }
     return out, (W, pe, batches)
 
@@ -521,7 +531,8 @@ def main():
                                **{k: v for k, v in CFG2.items()}},
                     "roofline": train["roofline"], "stages": train["stages"], "e2e": train["e2e"],
                     "gpu_launches": train["gpu_launches"], "clocks": train["clocks"],
-                    "algorithmic_mb_per_step": train["algorithmic_mb_per_step"]}
+                    "algorithmic_mb_per_step": train["algorithmic_mb_per_step"],
+                    "table_backward": train["table_backward"]}
             if gather is not None:
                 line["gather"] = gather
             line["catalog"] = cat

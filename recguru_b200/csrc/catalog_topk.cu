@@ -14,9 +14,10 @@
 //
 // CTA = 128 users (one M tile) sweeping a slice of the catalog in 128-item N tiles.
 //   warp 0      TMA producer: user tile once, then item tiles through a kStages smem ring
-//   warp 1      MMA issuer (one elected lane) + TMEM allocation (4 x 128 fp32 columns = 512)
-//   warps 2-5   epilogue set 0: even tiles      each set = 4 warps = the 4 TMEM lane quarters;
-//   warps 6-9   epilogue set 1: odd tiles       thread <-> user row, registers <-> item columns
+//   warps 1-2   MMA issuers (one elected lane each, alternate tiles); warp 1 owns the TMEM
+//               allocation (4 x 128 fp32 columns = 512)
+//   warps 3-6   epilogue set 0: even tiles      each set = 4 warps = the 4 TMEM lane quarters;
+//   warps 7-10  epilogue set 1: odd tiles       thread <-> user row, registers <-> item columns
 // Each epilogue thread keeps for its user: a rank counter (register), the current K-th best
 // score (register) and a sorted top-K list in shared memory.  Fast path per 32 columns:
 // 32 compares against the target score and one max-reduction against the K-th best; the list
@@ -97,7 +98,7 @@ struct CatSmem {
 // re-read from smem by each instruction and the N=128 MMA is shared-memory-bandwidth bound.
 // TMEM then holds 3 accumulators (384 columns) + A (64 columns).
 template <int D, int MODE, int NSETS, int CL, bool TS>
-__global__ void __launch_bounds__(64 + NSETS * 128, 1)
+__global__ void __launch_bounds__(96 + NSETS * 128, 1)
 catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                      const __grid_constant__ CUtensorMap map_items, CatalogParams p) {
   using L = CatSmem<D>;
@@ -185,15 +186,17 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp loops; one elected lane issues) ==========
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers (whole warp loops; one elected lane issues) =========
+    // Two issuer warps take alternate tiles: the per-tile wait / issue / commit chain of a single
+    // thread (~1700 cycles) would otherwise pace the whole kernel.
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, kBlockN);
     const uint32_t a_addr = ptx::smem_u32(smem + L::kOffA);
     const int reps = (p.debug_flags & 16u) ? 0 : ((p.debug_flags & 8u) ? 2 : 1);  // debug knobs
     ptx::mbar_wait_warp(bar_a, 0);
     ptx::tc_fence_after();
-    for (int j = 0; j < n_tiles; ++j) {
+    for (int j = warp - 1; j < n_tiles; j += 2) {
       const int s = j % NACC;
       const uint32_t ph = (j / NACC) & 1;
       const int a = j % NACC;
@@ -229,13 +232,13 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         else ptx::umma_commit(&bar_acc_full[a]);  // accumulator ready for the epilogue (and stage free)
       }
       __syncwarp();
-      if (prof && lane == 0) {
+      if (prof && lane == 0 && warp == 1) {
         g_prof[1] += tm1 - tm0; g_prof[2] += tm2 - tm1; g_prof[3] += clock64() - tm2; g_prof[4] += 1;
       }
     }
   } else {
     // ===================== epilogue =====================
-    const int e = (warp - 2) >> 2;            // epilogue set: handles tiles j == e (mod NSETS)
+    const int e = (warp - 3) >> 2;            // epilogue set: handles tiles j == e (mod NSETS)
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int64_t u = m0 + row;
@@ -436,8 +439,8 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
       }
-      if (prof && lane == 0 && (warp == 2 || warp == 6)) {
-        const int o = warp == 2 ? 5 : 8;
+      if (prof && lane == 0 && (warp == 3 || warp == 7)) {
+        const int o = warp == 3 ? 5 : 8;
         g_prof[o] += te1 - te0; g_prof[o + 1] += clock64() - te1; g_prof[o + 2] += 1;
       }
     }
@@ -647,7 +650,7 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
   cudaLaunchConfig_t cfg = {};
   const int64_t m_tiles = ceil_div(p.U, kBlockM);
   cfg.gridDim = dim3(static_cast<unsigned>(ceil_div(m_tiles, CL) * CL), static_cast<unsigned>(p.n_splits));
-  cfg.blockDim = dim3(64 + NSETS * 128);
+  cfg.blockDim = dim3(96 + NSETS * 128);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -27,8 +27,10 @@
 namespace rg {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;                           // keys per thread
-constexpr int kSortTile = kSortThreads * kSortItems;     // 4096 keys per CTA
+constexpr int kSortItems = 8;                            // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;     // 2048 keys per CTA
+constexpr int kCompactItems = 4;                         // occurrences per thread (compaction)
+constexpr int kCompactTile = kSortThreads * kCompactItems;
 constexpr int kMaxRadixBits = 9;
 constexpr int kMaxBins = 1 << kMaxRadixBits;
 constexpr int kChunk = 64;                               // sorted occurrences per warp
@@ -45,22 +47,136 @@ struct SiteTable {
   int n_sites;
 };
 
-__device__ __forceinline__ int find_site(const SiteTable& st, int64_t occ) {
-  int s = 0;
+// Site lookup with compile-time indices only: dynamic indexing into the by-value parameter
+// struct would make the compiler copy it to local memory in every thread.
+struct SiteRef {
+  const int64_t* ids;
+  const float* X;
+  const float* coef;
+  const float* scale;
+  const float* scale2;
+  int64_t offset;
+  int group;
+  int index;
+};
+__device__ __forceinline__ SiteRef find_site(const SiteTable& st, int64_t occ) {
+  SiteRef r = {st.ids[0], st.X[0], st.coef[0], st.scale[0], st.scale2[0], 0, st.group[0], 0};
+#pragma unroll
+  for (int i = 1; i < RECGURU_MAX_SITES; ++i) {
+    if (i < st.n_sites && occ >= st.offset[i]) {
+      r.ids = st.ids[i]; r.X = st.X[i]; r.coef = st.coef[i]; r.scale = st.scale[i];
+      r.scale2 = st.scale2[i]; r.offset = st.offset[i]; r.group = st.group[i]; r.index = i;
+    }
+  }
+  return r;
+}
+__device__ __forceinline__ const float* site_X(const SiteTable& st, int s) {
+  const float* x = st.X[0];
 #pragma unroll
   for (int i = 1; i < RECGURU_MAX_SITES; ++i)
-    if (i < st.n_sites && occ >= st.offset[i]) s = i;
-  return s;
+    if (s == i) x = st.X[i];
+  return x;
 }
 
-// ---- 1. keys -------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-build_keys_kernel(SiteTable st, int64_t total, uint32_t* __restrict__ keys) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += stride) {
-    const int s = find_site(st, i);
-    keys[i] = static_cast<uint32_t>(st.ids[s][i - st.offset[s]]);
+// Dead occurrences -- id == padding_idx, or an exactly-zero coefficient (masked positions: the
+// reference multiplies their rows by 0 too) -- are dropped by a stable stream compaction before
+// the sort: on padded batches > 90 % of the gathered indices carry no gradient at all.
+__device__ __forceinline__ bool occurrence_live(const SiteTable& st, int64_t i, int64_t padding_idx,
+                                                uint32_t* key) {
+  const SiteRef r = find_site(st, i);
+  const int64_t j = i - r.offset;
+  const int64_t id = r.ids[j];
+  *key = static_cast<uint32_t>(id);
+  return !(id == padding_idx || (r.coef != nullptr && r.coef[j] == 0.f));
+}
+
+// pass 1: live occurrences per tile (same warp-striped tile layout as the sort)
+__global__ void __launch_bounds__(kSortThreads)
+compact_count_kernel(SiteTable st, int64_t total, int64_t padding_idx, uint32_t* __restrict__ tile_count) {
+  __shared__ uint32_t s_w[kSortThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    uint32_t key;
+    c += (i < total && occurrence_live(st, i, padding_idx, &key)) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) s_w[warp] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) t += s_w[w];
+    tile_count[blockIdx.x] = t;
+  }
+}
+
+// pass 2: exclusive scan of the tile counts (one CTA) + the live total
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(uint32_t* __restrict__ tile_count, int n_tiles, uint32_t* __restrict__ n_live) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+    const int i = t0 + tid;
+    const uint32_t v = i < n_tiles ? tile_count[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    const uint32_t carry = s_carry;
+    if (i < n_tiles) tile_count[i] = carry + wbase + incl - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + wbase + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *n_live = s_carry;
+}
+
+// pass 3: stable scatter of the live (key, occurrence index) pairs
+__global__ void __launch_bounds__(kSortThreads)
+compact_scatter_kernel(SiteTable st, int64_t total, int64_t padding_idx,
+                       const uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ keys,
+                       uint32_t* __restrict__ vals) {
+  __shared__ uint32_t s_w[kSortThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t key[kCompactItems];
+  uint32_t rank[kCompactItems];   // 0xffffffff = dead
+  uint32_t run = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    const bool live = i < total && occurrence_live(st, i, padding_idx, &key[j]);
+    const uint32_t b = __ballot_sync(0xffffffffu, live);
+    rank[j] = live ? run + __popc(b & lt_mask) : 0xffffffffu;
+    run += __popc(b);
+  }
+  if (lane == 0) s_w[warp] = run;
+  __syncthreads();
+  uint32_t base = tile_offset[blockIdx.x];
+#pragma unroll
+  for (int w = 0; w < kSortThreads / 32; ++w)
+    if (w < warp) base += s_w[w];
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    if (rank[j] != 0xffffffffu) {
+      keys[base + rank[j]] = key[j];
+      vals[base + rank[j]] = static_cast<uint32_t>(warp0 + j * 32 + lane);
+    }
   }
 }
 
@@ -76,9 +192,11 @@ narrow_keys_kernel(const int64_t* __restrict__ ids, int64_t total, uint32_t* __r
 // Tile layout: warp w of a CTA owns keys [tile0 + w*512, +512); item j of lane l sits at
 // offset j*32 + l, so (j, lane) order == memory order and stability is easy to keep.
 __global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total, int shift, int bits,
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total_host,
+                  const uint32_t* __restrict__ n_live, int shift, int bits,
                   uint32_t* __restrict__ block_hist /* [bins][gridDim.x] */) {
   __shared__ uint32_t s_hist[kMaxBins];
+  const int64_t total = n_live ? static_cast<int64_t>(*n_live) : total_host;
   const int bins = 1 << bits;
   for (int b = threadIdx.x; b < bins; b += kSortThreads) s_hist[b] = 0;
   __syncthreads();
@@ -131,7 +249,7 @@ radix_scan_rows_kernel(uint32_t* __restrict__ hist, int n_tiles, uint32_t* __res
 template <bool kFirstPass, typename OutVal>
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     int64_t total, int shift, int bits,
+                     int64_t total_host, const uint32_t* __restrict__ n_live, int shift, int bits,
                      const uint32_t* __restrict__ block_base /* row-scanned [bins][grid] */,
                      const uint32_t* __restrict__ totals /* [bins] */,
                      uint32_t* __restrict__ keys_out, OutVal* __restrict__ vals_out,
@@ -139,6 +257,8 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __shared__ uint32_t s_cnt[kSortThreads / 32][kMaxBins];
   __shared__ uint32_t s_base[kMaxBins];      // exclusive scan of the digit totals
   __shared__ uint32_t s_wsum[kSortThreads / 32];
+  const int64_t total = n_live ? static_cast<int64_t>(*n_live) : total_host;
+  if (static_cast<int64_t>(blockIdx.x) * kSortTile >= total) return;   // tile beyond the live range
   const int bins = 1 << bits;
   const uint32_t mask = bins - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,12 +344,14 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, 
 // ---- 4. chunked segmented reduce -----------------------------------------------------
 // VPL = float4 per lane (ceil(d/4/32)).
 template <int VPL>
-__global__ void __launch_bounds__(kReduceWarps * 32, VPL == 1 ? 3 : 1)
+__global__ void __launch_bounds__(kReduceWarps * 32, VPL == 1 ? 2 : 1)
 chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
-                    const uint32_t* __restrict__ svals, int64_t total, int vec /* d/4 */,
+                    const uint32_t* __restrict__ svals, const uint32_t* __restrict__ n_live,
+                    int vec /* d/4 */,
                     int64_t padding_idx, int accumulate, float4* __restrict__ dW,
                     float4* __restrict__ partial /* [n_chunks][2][vec] */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total = *n_live;
   const int64_t chunk = static_cast<int64_t>(blockIdx.x) * kReduceWarps + warp;
   const int64_t c0 = chunk * kChunk;
   if (c0 >= total) return;
@@ -251,13 +373,13 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
     if (i < n) {
       l_key[q] = skeys[c0 + i];
       const int64_t occ = svals[c0 + i];
-      const int s = find_site(st, occ);
-      const int64_t j = occ - st.offset[s];
-      l_site[q] = s;
-      l_row[q] = static_cast<int>(j / st.group[s]);
-      float c = st.coef[s] ? st.coef[s][j] : 1.f;
-      if (st.scale[s]) c *= *st.scale[s];
-      if (st.scale2[s]) c *= *st.scale2[s];
+      const SiteRef r = find_site(st, occ);
+      const int64_t j = occ - r.offset;
+      l_site[q] = r.index;
+      l_row[q] = static_cast<int>(j / r.group);
+      float c = r.coef ? r.coef[j] : 1.f;
+      if (r.scale) c *= *r.scale;
+      if (r.scale2) c *= *r.scale2;
       l_coef[q] = c;
     }
   }
@@ -265,7 +387,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
   const uint32_t last_key = __shfl_sync(0xffffffffu, l_key[(n - 1) / 32], (n - 1) & 31);
   const uint32_t pad = static_cast<uint32_t>(padding_idx);  // -1 -> 0xffffffff never matches
   const bool has_pad = padding_idx >= 0;
-  if (has_pad && first_key == pad && last_key == pad) return;  // chunk is all padding
+  if (has_pad && first_key == pad) return;  // sentinel keys sort last: the whole chunk is dead
   const bool lead_open = c0 > 0 && skeys[c0 - 1] == first_key;           // run started earlier
   const bool trail_open = c0 + n < total && skeys[c0 + n] == last_key;   // run continues
 
@@ -297,7 +419,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
       const int64_t row = __shfl_sync(0xffffffffu, rr, i & 31);
       cf[u] = __shfl_sync(0xffffffffu, cc, i & 31);
       const bool live = i < n && !(has_pad && k[u] == pad);
-      const float4* src = reinterpret_cast<const float4*>(st.X[s]) + row * vec;
+      const float4* src = reinterpret_cast<const float4*>(site_X(st, s)) + row * vec;
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int col = v * 32 + lane;
@@ -373,10 +495,12 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
 // edge is the FIRST edge that run crosses; it then walks right summing partials.
 template <int VPL>
 __global__ void __launch_bounds__(kReduceWarps * 32)
-span_fixup_kernel(const uint32_t* __restrict__ skeys, int64_t total, int64_t n_chunks, int vec,
+span_fixup_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ n_live, int vec,
                   int64_t padding_idx, int accumulate, float4* __restrict__ dW,
                   const float4* __restrict__ partial) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total = *n_live;
+  const int64_t n_chunks = (total + kChunk - 1) / kChunk;
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kReduceWarps + warp + 1;
   if (b >= n_chunks) return;
   const uint32_t key = skeys[b * kChunk];
@@ -446,7 +570,7 @@ struct SortPlan {
   int total_bits, passes, bits_per_pass;
   int64_t n_tiles;
   // workspace carve-up (bytes, 256-aligned)
-  int64_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_hist, off_totals, end;
+  int64_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_hist, off_totals, off_tilecnt, off_nlive, end;
 };
 
 static SortPlan make_sort_plan(int64_t count, int64_t V1) {
@@ -465,15 +589,19 @@ static SortPlan make_sort_plan(int64_t count, int64_t V1) {
   p.off_vals_b = o; o += kb;
   p.off_hist = o; o += align_up(static_cast<int64_t>(kMaxBins) * p.n_tiles * 4, 256);
   p.off_totals = o; o += align_up(kMaxBins * 4, 256);
+  p.off_tilecnt = o; o += align_up(ceil_div(count > 0 ? count : 1, kCompactTile) * 4, 256);
+  p.off_nlive = o; o += 256;
   p.end = o;
   return p;
 }
 
 // Sorts keys (already in ws keys_a).  On return *skeys / *svals point at the sorted arrays.
 // If out_keys64/out_perm64 are given the final pass writes widened copies there instead.
-static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, cudaStream_t st,
-                          uint32_t** skeys, uint32_t** svals, int64_t* out_keys64,
-                          int64_t* out_perm64) {
+// n_live (device) overrides `count` when given; first_pass_vals: pass 0 takes vals from keys' twin
+// array (compacted input) instead of generating the identity.
+static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, const uint32_t* n_live,
+                          bool identity_vals, cudaStream_t st, uint32_t** skeys, uint32_t** svals,
+                          int64_t* out_keys64, int64_t* out_perm64) {
   uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws + p.off_keys_a),
                        reinterpret_cast<uint32_t*>(ws + p.off_keys_b)};
   uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(ws + p.off_vals_a),
@@ -485,25 +613,25 @@ static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, cudaStream
   for (int pass = 0; pass < p.passes; ++pass) {
     const int shift = pass * p.bits_per_pass;
     const int bits = min(p.bits_per_pass, p.total_bits - shift);
-    radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(keys[cur], count, shift, bits, hist);
+    radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(keys[cur], count, n_live, shift, bits, hist);
     RG_CHECK_LAUNCH("radix_hist");
     radix_scan_rows_kernel<<<1u << bits, 256, 0, st>>>(hist, static_cast<int>(p.n_tiles), totals);
     RG_CHECK_LAUNCH("radix_scan_rows");
     const bool last = pass == p.passes - 1;
     if (last && out_perm64) {
-      if (pass == 0)
+      if (pass == 0 && identity_vals)
         radix_scatter_kernel<true, int64_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
+            keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
       else
         radix_scatter_kernel<false, int64_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
+            keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
     } else {
-      if (pass == 0)
+      if (pass == 0 && identity_vals)
         radix_scatter_kernel<true, uint32_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
+            keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
       else
         radix_scatter_kernel<false, uint32_t><<<grid, kSortThreads, 0, st>>>(
-            keys[cur], vals[cur], count, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
+            keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
     }
     RG_CHECK_LAUNCH("radix_scatter");
     cur ^= 1;
@@ -538,7 +666,7 @@ extern "C" int recguru_sort_ids(const int64_t* ids, int64_t count, int64_t V1, i
       ids, count, reinterpret_cast<uint32_t*>(ws + p.off_keys_a));
   RG_CHECK_LAUNCH("narrow_keys");
   uint32_t *sk, *sv;
-  return run_radix_sort(p, ws, count, st, &sk, &sv, sorted_ids, perm);
+  return run_radix_sort(p, ws, count, nullptr, true, st, &sk, &sv, sorted_ids, perm);
 }
 
 extern "C" int64_t recguru_embedding_bwd_workspace_bytes(int64_t total_count, int64_t V1,
@@ -594,14 +722,21 @@ extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, in
   RG_REQUIRE(workspace && workspace_bytes >= need, RECGURU_E_WORKSPACE,
              "embedding_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)need);
   char* ws = static_cast<char*>(workspace);
+  uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(ws + p.off_tilecnt);
+  uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
   {
-    const int64_t blocks = rg::min64(ceil_div(total, 256 * 4), kNumSMs * 8);
-    build_keys_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        tab, total, reinterpret_cast<uint32_t*>(ws + p.off_keys_a));
-    RG_CHECK_LAUNCH("build_keys");
+    const unsigned tiles = static_cast<unsigned>(ceil_div(total, kCompactTile));
+    compact_count_kernel<<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+    RG_CHECK_LAUNCH("compact_count");
+    compact_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, static_cast<int>(tiles), n_live);
+    RG_CHECK_LAUNCH("compact_scan");
+    compact_scatter_kernel<<<tiles, kSortThreads, 0, st>>>(
+        tab, total, padding_idx, tile_cnt, reinterpret_cast<uint32_t*>(ws + p.off_keys_a),
+        reinterpret_cast<uint32_t*>(ws + p.off_vals_a));
+    RG_CHECK_LAUNCH("compact_scatter");
   }
   uint32_t *sk, *sv;
-  int rc = run_radix_sort(p, ws, total, st, &sk, &sv, nullptr, nullptr);
+  int rc = run_radix_sort(p, ws, total, n_live, false, st, &sk, &sv, nullptr, nullptr);
   if (rc != RECGURU_OK) return rc;
   float4* partial = reinterpret_cast<float4*>(ws + p.end);
   float4* dW4 = reinterpret_cast<float4*>(dW);
@@ -610,14 +745,14 @@ extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, in
   const int vpl = (vec + 31) / 32;
 #define RG_LAUNCH_REDUCE(V)                                                                   \
   do {                                                                                        \
-    chunk_reduce_kernel<V><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, total, vec,       \
-                                                               padding_idx, accumulate, dW4,  \
+    chunk_reduce_kernel<V><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, n_live, vec,      \
+                                                               -1, accumulate, dW4,           \
                                                                partial);                      \
     RG_CHECK_LAUNCH("chunk_reduce");                                                          \
     if (n_chunks > 1) {                                                                       \
       const unsigned g2 = static_cast<unsigned>(ceil_div(n_chunks - 1, kReduceWarps));        \
-      span_fixup_kernel<V><<<g2, kReduceWarps * 32, 0, st>>>(sk, total, n_chunks, vec,        \
-                                                             padding_idx, accumulate, dW4,    \
+      span_fixup_kernel<V><<<g2, kReduceWarps * 32, 0, st>>>(sk, n_live, vec,                 \
+                                                             -1, accumulate, dW4,             \
                                                              partial);                        \
       RG_CHECK_LAUNCH("span_fixup");                                                          \
     }                                                                                         \

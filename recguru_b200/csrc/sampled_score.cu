@@ -26,36 +26,68 @@ constexpr int kPosPerBlock = kScoreWarps * kPosPerWarp;
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.f / (1.f + expf(-x)); }
 
-// Loss + unnormalised derivatives of one position.  `score` holds candidate `lane`
-// (lane 0 = positive, lanes 1..K = negatives); result identical in all lanes.
-__device__ __forceinline__ float warp_position_loss(int kind, float score, int K, int lane,
-                                                    float* dscore /* this lane's d l/d score */) {
-  const bool is_neg = lane >= 1 && lane <= K;
-  const float p = __shfl_sync(0xffffffffu, score, 0);
-  if (kind == RECGURU_LOSS_SCE) {
-    float m = (lane <= K) ? score : -CUDART_INF_F;
+// Multi-value butterfly: every lane of a LANES-wide group holds partial sums for UN rows; after
+// log2(UN) halving exchanges + log2(LANES/UN) plain steps, lane (sub) holds the full sum of row
+// (sub / (LANES/UN)).  UN + log2(LANES/UN) - 1 shuffles instead of UN * log2(LANES).
+template <int LANES, int UN>
+__device__ __forceinline__ float group_multi_reduce(float (&v)[UN], int sub) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float e = (lane <= K) ? expf(score - m) : 0.f;
-    const float sum = warp_sum(e);
-    *dscore = (lane <= K) ? (e / sum - (lane == 0 ? 1.f : 0.f)) : 0.f;
-    return (m + logf(sum)) - p;
+  for (int n = UN, off = LANES / 2; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (sub & off) != 0;
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) {
+      const float send = upper ? v[k] : v[k + n / 2];
+      const float keep = upper ? v[k + n / 2] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
   }
-  const float nbar = warp_sum(is_neg ? score : 0.f) / static_cast<float>(K);
-  if (kind == RECGURU_LOSS_BPR) {
-    const float sg = sigmoidf_ref(p - nbar);
-    *dscore = lane == 0 ? (sg - 1.f) : (is_neg ? (1.f - sg) / static_cast<float>(K) : 0.f);
-    return -logf(sg);
-  }
-  // RECGURU_LOSS_BPR_SAS
-  const float a = sigmoidf_ref(p), b = sigmoidf_ref(nbar);
-  const float ya = a + 1e-24f, yb = (1.f - b) + 1e-24f;
-  const float dp = -(a * (1.f - a)) / ya;
-  const float dn = (b * (1.f - b)) / yb / static_cast<float>(K);
-  *dscore = lane == 0 ? dp : (is_neg ? dn : 0.f);
-  return -(logf(ya) + logf(yb));
+  float r = v[0];
+#pragma unroll
+  for (int off = LANES / UN / 2; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
 }
 
+// Loss + unnormalised derivatives of one position from its 1+K scores (row[0] = positive).
+// Overwrites row[] with d l / d score.
+__device__ __forceinline__ float position_loss(int kind, float* row, int K) {
+  const float p = row[0];
+  if (kind == RECGURU_LOSS_SCE) {
+    float m = p;
+    for (int k = 1; k <= K; ++k) m = fmaxf(m, row[k]);
+    float sum = 0.f;
+    for (int k = 0; k <= K; ++k) sum += expf(row[k] - m);
+    for (int k = 0; k <= K; ++k) row[k] = expf(row[k] - m) / sum - (k == 0 ? 1.f : 0.f);
+    return (m + logf(sum)) - p;
+  }
+  float nsum = 0.f;
+  for (int k = 1; k <= K; ++k) nsum += row[k];
+  const float nbar = nsum / static_cast<float>(K);
+  float l, dp, dn;
+  if (kind == RECGURU_LOSS_BPR) {
+    const float sg = sigmoidf_ref(p - nbar);
+    l = -logf(sg);
+    dp = sg - 1.f;
+    dn = (1.f - sg) / static_cast<float>(K);
+  } else {  // RECGURU_LOSS_BPR_SAS
+    const float a = sigmoidf_ref(p), b = sigmoidf_ref(nbar);
+    const float ya = a + 1e-24f, yb = (1.f - b) + 1e-24f;
+    l = -(logf(ya) + logf(yb));
+    dp = -(a * (1.f - a)) / ya;
+    dn = (b * (1.f - b)) / yb / static_cast<float>(K);
+  }
+  row[0] = dp;
+  for (int k = 1; k <= K; ++k) row[k] = dn;
+  return l;
+}
+
+constexpr int kFwdPosPerWarp = 32;
+constexpr int kFwdPosPerBlock = kScoreWarps * kFwdPosPerWarp;   // 256
+constexpr int kRowPad = 33;                                     // 1+K <= 32 scores, +1 against bank conflicts
+
+// One warp owns 32 consecutive positions.  Phase 1 (per position, whole warp): gather the 1+K
+// table rows, dot them with h (8 rows in flight, butterfly reduction), park the scores in shared
+// memory.  Phase 2 (lane = position): loss and derivatives with lane-parallel transcendental
+// math, all outputs written coalesced.
 template <int VEC>  // float4 per row
 __global__ void __launch_bounds__(kScoreWarps * 32)
 sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ weight,
@@ -65,27 +97,26 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
                          float* __restrict__ dp_unit, float* __restrict__ dn_unit,
                          float2* __restrict__ block_partial) {
   constexpr int LANES = VEC < 32 ? VEC : 32;  // lanes cooperating on one row
-  constexpr int G = 32 / LANES;               // rows in flight per warp step
+  constexpr int G = 32 / LANES;               // row groups per warp step
   constexpr int VPL = VEC / LANES;            // float4 per lane per row
-  constexpr int UN = 8 / G > 0 ? 8 / G : 1;   // unroll: 8 rows in flight per warp
+  constexpr int UN = 8 / G;                   // rows per group per step: 8 rows in flight per warp
+  __shared__ float s_sc[kScoreWarps][kFwdPosPerWarp][kRowPad];
   __shared__ float2 s_part[kScoreWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / LANES, sub = lane % LANES;
   const int C = K + 1;
-  float loss_acc = 0.f, mask_acc = 0.f;
+  const int64_t base = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kFwdPosPerWarp;
+  const int n_here = static_cast<int>(rg::min64(kFwdPosPerWarp, n_pos - base));  // may be <= 0
 
-  for (int q = 0; q < kPosPerWarp; ++q) {
-    const int64_t i = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kPosPerWarp + q;
-    if (i >= n_pos) break;  // warp-uniform
+  for (int q = 0; q < n_here; ++q) {
+    const int64_t i = base + q;
     int64_t my_id = 0;
     if (lane == 0) my_id = pos[i];
     else if (lane <= K) my_id = neg[i * K + (lane - 1)];
     float4 hv[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) hv[v] = ld_stream_f4(h + i * VEC + v * LANES + sub);
-
-    float score = 0.f;
-    for (int c0 = 0; c0 < C; c0 += G * UN) {
+    for (int c0 = 0; c0 < C; c0 += 8) {
       float4 w[UN][VPL];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -93,42 +124,66 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
         const int64_t id = __shfl_sync(0xffffffffu, my_id, c < C ? c : 0);
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      float acc[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        float acc = 0.f;
+        float a = 0.f;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-          acc = fmaf(hv[v].x, w[u][v].x, acc);
-          acc = fmaf(hv[v].y, w[u][v].y, acc);
-          acc = fmaf(hv[v].z, w[u][v].z, acc);
-          acc = fmaf(hv[v].w, w[u][v].w, acc);
+          a = fmaf(hv[v].x, w[u][v].x, a);
+          a = fmaf(hv[v].y, w[u][v].y, a);
+          a = fmaf(hv[v].z, w[u][v].z, a);
+          a = fmaf(hv[v].w, w[u][v].w, a);
         }
-#pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-#pragma unroll
-        for (int gg = 0; gg < G; ++gg) {
-          const float v = __shfl_sync(0xffffffffu, acc, gg * LANES);
-          if (lane == c0 + u * G + gg) score = v;
-        }
+        acc[u] = a;
       }
-    }
-    if (p_out && lane == 0) p_out[i] = score;
-    if (n_out && lane >= 1 && lane <= K) n_out[i * K + (lane - 1)] = score;
-    if (kind >= 0) {
-      const float m = mask ? __ldg(mask + i) : 1.f;
-      float ds;
-      const float l = warp_position_loss(kind, score, K, lane, &ds);
-      loss_acc += l * m;
-      mask_acc += m;
-      if (dp_unit && lane == 0) dp_unit[i] = ds * m;
-      if (dn_unit && lane >= 1 && lane <= K) dn_unit[i * K + (lane - 1)] = ds * m;
+      const float r = group_multi_reduce<LANES, UN>(acc, sub);
+      constexpr int kRep = LANES / UN;          // lanes holding the same row's sum
+      const int c = c0 + (sub / kRep) * G + g;  // row (candidate) this lane ended up with
+      if (sub % kRep == 0 && c < C) s_sc[warp][q][c] = r;
     }
   }
+  __syncwarp();
+
+  // ---- phase 2: lane <-> position ------------------------------------------------------
+  const int64_t i = base + lane;
+  const bool ok = lane < n_here;
+  float* row = s_sc[warp][lane];
+  if (p_out && ok) p_out[i] = row[0];
+  if (n_out) {
+    const int tot = max(n_here, 0) * K;
+    for (int idx = lane; idx < tot; idx += 32) {
+      const int q = idx / K, k = idx - q * K;
+      n_out[base * K + idx] = s_sc[warp][q][1 + k];
+    }
+  }
+  float lm = 0.f, m = 0.f;
   if (kind >= 0) {
-    if (lane == 0) s_part[warp] = make_float2(loss_acc, mask_acc);
+    __syncwarp();
+    if (ok) {
+      m = mask ? __ldg(mask + i) : 1.f;
+      lm = position_loss(kind, row, K) * m;
+      if (dp_unit) dp_unit[i] = row[0] * m;
+#pragma unroll 1
+      for (int k = 1; k <= K; ++k) row[k] *= m;
+    }
+    __syncwarp();
+    if (dn_unit) {
+      const int tot = max(n_here, 0) * K;
+      for (int idx = lane; idx < tot; idx += 32) {
+        const int q = idx / K, k = idx - q * K;
+        dn_unit[base * K + idx] = s_sc[warp][q][1 + k];
+      }
+    }
+    // fixed-order reduction: lanes by shuffle tree, warps sequentially
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lm += __shfl_xor_sync(0xffffffffu, lm, o);
+      m += __shfl_xor_sync(0xffffffffu, m, o);
+    }
+    if (lane == 0) s_part[warp] = make_float2(lm, m);
     __syncthreads();
     if (threadIdx.x == 0) {
       float2 t = make_float2(0.f, 0.f);
@@ -250,7 +305,9 @@ sampled_score_bwd_dh_kernel(const float* __restrict__ dp, const float* __restric
     float4 acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c0 = 0; c0 < C; c0 += G * UN) {
+    // masked positions have all-zero coefficients: their dh row is zero, no table row is read
+    const bool any_nz = __any_sync(0xffffffffu, my_c != 0.f);
+    for (int c0 = 0; any_nz && c0 < C; c0 += G * UN) {
       float4 w[UN][VPL];
       float cf[UN];
 #pragma unroll
@@ -325,7 +382,7 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
   RG_REQUIRE(kind <= RECGURU_LOSS_SCE, RECGURU_E_UNSUPPORTED, "sampled_score_loss_fwd: kind=%d", kind);
   RG_REQUIRE(kind < 0 || loss_out, RECGURU_E_SHAPE, "sampled_score_loss_fwd: loss_out is null");
   if (n_pos == 0) return RECGURU_OK;
-  const int64_t blocks = ceil_div(n_pos, kPosPerBlock);
+  const int64_t blocks = ceil_div(n_pos, kFwdPosPerBlock);
   if (kind >= 0)
     RG_REQUIRE(workspace && workspace_bytes >= blocks * 8, RECGURU_E_WORKSPACE,
                "sampled_score_loss_fwd: workspace %lld < %lld", (long long)workspace_bytes,

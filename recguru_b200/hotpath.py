@@ -91,13 +91,22 @@ class TrainHotPath:
         return loss, dh, dW
 
     # algorithmic bytes per step, for roofline accounting
-    def algorithmic_bytes(self, distinct_rows: Optional[int] = None) -> dict:
+    def algorithmic_bytes(self, distinct_rows: Optional[int] = None, live: Optional[int] = None,
+                          live_pos: Optional[int] = None) -> dict:
+        """Per-stage algorithmic bytes (cache hits never discounted).  For the table backward,
+        ``live`` = gathered indices that carry a gradient (id != padding_idx and coefficient != 0);
+        dead ones cost their id + coefficient only (they are compacted away before the sort), which
+        is the honest numerator on padded batches.  ``live=None`` counts every index as live."""
         n, d, K, V1 = self.B * self.L, self.d, self.K, self.V1
+        total = n * (2 + K)
+        live = total if live is None else live
         b = {
             "gather_pe_mask": n * (8 + 4 * d + 4 * d + 4),
             "sampled_score_loss_fwd": n * (4 * d + (1 + K) * (8 + 4 * d) + 4 + 4 * (1 + K)),
-            "sampled_score_bwd_dh": n * ((1 + K) * (8 + 4 * d + 4) + 4 * d),
-            "embedding_bwd": n * (2 + K) * (8 + 4 * d) + 4 * V1 * d
+            # positions whose coefficients are all zero (masked) need no table rows for dh
+            "sampled_score_bwd_dh": n * ((1 + K) * (8 + 4) + 4 * d)
+            + (n if live_pos is None else live_pos) * (1 + K) * 4 * d,
+            "embedding_bwd": total * (8 + 4) + live * 4 * d + 4 * V1 * d
             + (4 * d * distinct_rows if distinct_rows is not None else 0),
         }
         b["total"] = sum(b.values())
