@@ -111,6 +111,10 @@ class Dist:
         if self.world > 1:
             import torch.distributed as dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # NCCL prints its version banner on stdout at INFO/VERSION level; the bench line must be
+            # the only thing there
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+                os.environ["NCCL_DEBUG"] = "WARN"
             torch.cuda.set_device(self.local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
