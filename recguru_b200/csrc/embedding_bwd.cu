@@ -59,10 +59,11 @@ struct SiteRef {
   int group;
   int index;
 };
+template <int NS>  // compile-time bound on the number of sites (the select chain is per element)
 __device__ __forceinline__ SiteRef find_site(const SiteTable& st, int64_t occ) {
   SiteRef r = {st.ids[0], st.X[0], st.coef[0], st.scale[0], st.scale2[0], 0, st.group[0], 0};
 #pragma unroll
-  for (int i = 1; i < RECGURU_MAX_SITES; ++i) {
+  for (int i = 1; i < NS; ++i) {
     if (i < st.n_sites && occ >= st.offset[i]) {
       r.ids = st.ids[i]; r.X = st.X[i]; r.coef = st.coef[i]; r.scale = st.scale[i];
       r.scale2 = st.scale2[i]; r.offset = st.offset[i]; r.group = st.group[i]; r.index = i;
@@ -81,9 +82,10 @@ __device__ __forceinline__ const float* site_X(const SiteTable& st, int s) {
 // Dead occurrences -- id == padding_idx, or an exactly-zero coefficient (masked positions: the
 // reference multiplies their rows by 0 too) -- are dropped by a stable stream compaction before
 // the sort: on padded batches > 90 % of the gathered indices carry no gradient at all.
+template <int NS>
 __device__ __forceinline__ bool occurrence_live(const SiteTable& st, int64_t i, int64_t padding_idx,
                                                 uint32_t* key) {
-  const SiteRef r = find_site(st, i);
+  const SiteRef r = find_site<NS>(st, i);
   const int64_t j = i - r.offset;
   const int64_t id = r.ids[j];
   *key = static_cast<uint32_t>(id);
@@ -91,6 +93,7 @@ __device__ __forceinline__ bool occurrence_live(const SiteTable& st, int64_t i, 
 }
 
 // pass 1: live occurrences per tile (same warp-striped tile layout as the sort)
+template <int NS>
 __global__ void __launch_bounds__(kSortThreads)
 compact_count_kernel(SiteTable st, int64_t total, int64_t padding_idx, uint32_t* __restrict__ tile_count) {
   __shared__ uint32_t s_w[kSortThreads / 32];
@@ -101,7 +104,7 @@ compact_count_kernel(SiteTable st, int64_t total, int64_t padding_idx, uint32_t*
   for (int j = 0; j < kCompactItems; ++j) {
     const int64_t i = warp0 + j * 32 + lane;
     uint32_t key;
-    c += (i < total && occurrence_live(st, i, padding_idx, &key)) ? 1u : 0u;
+    c += (i < total && occurrence_live<NS>(st, i, padding_idx, &key)) ? 1u : 0u;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -146,6 +149,7 @@ compact_scan_kernel(uint32_t* __restrict__ tile_count, int n_tiles, uint32_t* __
 }
 
 // pass 3: stable scatter of the live (key, occurrence index) pairs
+template <int NS>
 __global__ void __launch_bounds__(kSortThreads)
 compact_scatter_kernel(SiteTable st, int64_t total, int64_t padding_idx,
                        const uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ keys,
@@ -160,7 +164,7 @@ compact_scatter_kernel(SiteTable st, int64_t total, int64_t padding_idx,
 #pragma unroll
   for (int j = 0; j < kCompactItems; ++j) {
     const int64_t i = warp0 + j * 32 + lane;
-    const bool live = i < total && occurrence_live(st, i, padding_idx, &key[j]);
+    const bool live = i < total && occurrence_live<NS>(st, i, padding_idx, &key[j]);
     const uint32_t b = __ballot_sync(0xffffffffu, live);
     rank[j] = live ? run + __popc(b & lt_mask) : 0xffffffffu;
     run += __popc(b);
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, 
 
 // ---- 4. chunked segmented reduce -----------------------------------------------------
 // VPL = float4 per lane (ceil(d/4/32)).
-template <int VPL>
+template <int VPL, int NS>
 __global__ void __launch_bounds__(kReduceWarps * 32, VPL == 1 ? 2 : 1)
 chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
                     const uint32_t* __restrict__ svals, const uint32_t* __restrict__ n_live,
@@ -373,7 +377,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
     if (i < n) {
       l_key[q] = skeys[c0 + i];
       const int64_t occ = svals[c0 + i];
-      const SiteRef r = find_site(st, occ);
+      const SiteRef r = find_site<NS>(st, occ);
       const int64_t j = occ - r.offset;
       l_site[q] = r.index;
       l_row[q] = static_cast<int>(j / r.group);
@@ -520,16 +524,15 @@ span_fixup_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict
   int64_t c = b;  // invariant: edge c is crossed by this run => chunk c has a leading partial
   bool done = false;
   while (!done) {
-    constexpr int kBatch = 8;
-    int cnt = 0;
-    while (cnt < kBatch) {
-      ++cnt;
-      const int64_t e = c + cnt;  // edge index == index of the chunk on its right
-      if (!(e < n_chunks && skeys[e * kChunk] == key && skeys[e * kChunk - 1] == key)) {
-        done = true;
-        break;
-      }
-    }
+    constexpr int kBatch = VPL == 1 ? 16 : 8;
+    // how many of the next kBatch chunks still belong to this run?  One lane per edge, so the
+    // key probes are a single round trip instead of a dependent chain.
+    const int64_t e = c + 1 + lane;  // edge index == index of the chunk on its right
+    const bool crossed = lane < kBatch && e < n_chunks && skeys[e * kChunk] == key && skeys[e * kChunk - 1] == key;
+    const uint32_t open_mask = __ballot_sync(0xffffffffu, !crossed);   // first lane whose edge is not crossed
+    const int first_closed = __ffs(open_mask) - 1;                     // in [0, kBatch]
+    int cnt = first_closed + 1;                                        // chunks c .. c+first_closed
+    if (cnt > kBatch) cnt = kBatch; else done = true;
     float4 x[kBatch][VPL];
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
@@ -726,13 +729,17 @@ extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, in
   uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
   {
     const unsigned tiles = static_cast<unsigned>(ceil_div(total, kCompactTile));
-    compact_count_kernel<<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+    uint32_t* ka = reinterpret_cast<uint32_t*>(ws + p.off_keys_a);
+    uint32_t* va = reinterpret_cast<uint32_t*>(ws + p.off_vals_a);
+    if (n_sites <= 1) compact_count_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+    else if (n_sites <= 3) compact_count_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+    else compact_count_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
     RG_CHECK_LAUNCH("compact_count");
     compact_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, static_cast<int>(tiles), n_live);
     RG_CHECK_LAUNCH("compact_scan");
-    compact_scatter_kernel<<<tiles, kSortThreads, 0, st>>>(
-        tab, total, padding_idx, tile_cnt, reinterpret_cast<uint32_t*>(ws + p.off_keys_a),
-        reinterpret_cast<uint32_t*>(ws + p.off_vals_a));
+    if (n_sites <= 1) compact_scatter_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
+    else if (n_sites <= 3) compact_scatter_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
+    else compact_scatter_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
     RG_CHECK_LAUNCH("compact_scatter");
   }
   uint32_t *sk, *sv;
@@ -745,9 +752,15 @@ extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, in
   const int vpl = (vec + 31) / 32;
 #define RG_LAUNCH_REDUCE(V)                                                                   \
   do {                                                                                        \
-    chunk_reduce_kernel<V><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, n_live, vec,      \
-                                                               -1, accumulate, dW4,           \
-                                                               partial);                      \
+    if (n_sites <= 1)                                                                         \
+      chunk_reduce_kernel<V, 1><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, n_live, vec, -1, \
+                                                                    accumulate, dW4, partial);    \
+    else if (n_sites <= 3)                                                                    \
+      chunk_reduce_kernel<V, 3><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, n_live, vec, -1, \
+                                                                    accumulate, dW4, partial);    \
+    else                                                                                      \
+      chunk_reduce_kernel<V, RECGURU_MAX_SITES><<<grid, kReduceWarps * 32, 0, st>>>(          \
+          tab, sk, sv, n_live, vec, -1, accumulate, dW4, partial);                            \
     RG_CHECK_LAUNCH("chunk_reduce");                                                          \
     if (n_chunks > 1) {                                                                       \
       const unsigned g2 = static_cast<unsigned>(ceil_div(n_chunks - 1, kReduceWarps));        \
