@@ -236,19 +236,42 @@ def bench_train(D: Dist, args, peaks):
             "frac": stages[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["src"]}
 
     # ---- end to end through the public API with host buffers ----
+    # A prefetching loader: the ids of step i+1 are copied (pinned host -> device, side stream)
+    # while step i computes; the loss of every step is read back and waited for, as the
+    # reference's loop does with loss.item().  All copies happen inside the timed region.
     pin = [dict(dec_in=t.dec_in.pin_memory(), dec_out=t.dec_out.pin_memory(), n_items=t.n_items.pin_memory())
            for t in host]
-    d_in = {k: torch.empty_like(v, device=dev) for k, v in pin[0].items()}
+    d_in = [{k: torch.empty_like(v, device=dev) for k, v in pin[0].items()} for _ in range(2)]
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"primed": -1}
+
+    def enqueue_copy(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # buffer free (its previous step finished)
+            for k in d_in[slot]:
+                d_in[slot][k].copy_(pin[i % n_batches][k], non_blocking=True)
+            copied[slot].record(copy_stream)
+
+    for ev in consumed:
+        ev.record()
 
     def e2e_step(i):
+        if state["primed"] < i:                              # first step of a loop: nothing prefetched yet
+            enqueue_copy(i)
+        slot = i % 2
         b = batches[i % n_batches]
-        src = pin[i % n_batches]
-        for k in d_in:
-            d_in[k].copy_(src[k], non_blocking=True)
-        loss, _, _ = hp.step(d_in["dec_in"], d_in["dec_out"], d_in["n_items"], b["h"], b["g"])
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copied[slot])
+        enqueue_copy(i + 1)                                  # overlaps this step's kernels
+        state["primed"] = i + 1
+        loss, _, _ = hp.step(d_in[slot]["dec_in"], d_in[slot]["dec_out"], d_in[slot]["n_items"], b["h"], b["g"])
+        consumed[slot].record(cur)
         loss_host.copy_(loss.view(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the reference reads loss.item() every step
+        cur.synchronize()                                    # the reference reads loss.item() every step
 
     ms_e2e = timed_loop(D, e2e_step, K, Wm)
     h2d = sum(v.numel() * v.element_size() for v in pin[0].values())

@@ -80,11 +80,12 @@ __device__ __forceinline__ float position_loss(int kind, float* row, int K) {
   return l;
 }
 
-constexpr int kFwdPosPerWarp = 32;
+constexpr int kFwdPosPerWarp = 16;
 constexpr int kFwdPosPerBlock = kScoreWarps * kFwdPosPerWarp;   // 256
 constexpr int kRowPad = 33;                                     // 1+K <= 32 scores, +1 against bank conflicts
 
-// One warp owns 32 consecutive positions.  Phase 1 (per position, whole warp): gather the 1+K
+// One warp owns 16 consecutive positions (measured best of 8/16/32: more warps shorten the serial
+// chain of dependent row gathers, fewer lanes are idle in phase 2 than with 8).  Phase 1 (per position, whole warp): gather the 1+K
 // table rows, dot them with h (8 rows in flight, butterfly reduction), park the scores in shared
 // memory.  Phase 2 (lane = position): loss and derivatives with lane-parallel transcendental
 // math, all outputs written coalesced.
