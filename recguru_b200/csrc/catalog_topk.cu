@@ -130,7 +130,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     ptx::tma_prefetch_desc(&map_users);
     ptx::tma_prefetch_desc(&map_items);
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&bar_full[i], 1); ptx::mbar_init(&bar_empty[i], CL); }
-    for (int i = 0; i < kAccum; ++i) { ptx::mbar_init(&bar_acc_full[i], 1); ptx::mbar_init(&bar_acc_empty[i], 4); }
+    for (int i = 0; i < kAccum; ++i) { ptx::mbar_init(&bar_acc_full[i], 1); ptx::mbar_init(&bar_acc_empty[i], (p.debug_flags & 16384u) ? 1 : 4); }
     ptx::mbar_init(bar_a, TS ? 4 : 1);
     ptx::mbar_fence_init();
   }
@@ -298,6 +298,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       thr = s_val[(K - 1) * kSlots + slot];
     };
     for (int j = e; j < n_tiles; j += NSETS) {
+      if ((p.debug_flags & 16384u) && quarter != 0) break;   // debug: one warp per set in the handshake
       const int a = j % NACC;
       const uint32_t aph = (j / NACC) & 1;
       const int tile = tile_begin + j;
@@ -361,6 +362,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         constexpr int CH = NSETS == 2 ? kBlockN : 64;
 #pragma unroll 1
         for (int c0 = 0; c0 < kBlockN; c0 += CH) {
+          if (p.debug_flags & 2u) break;               // debug: no TMEM reads, no compute (timing floor)
           uint32_t vr[CH];
           ptx::tmem_ld_cols<CH>(taddr + c0, vr);
           ptx::tmem_ld_wait();
