@@ -36,10 +36,9 @@
 namespace rg {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockN = 128;
+constexpr int kBlockN = 128;   // target kernel tile; the sweep's item tile is the template parameter BN
 constexpr int kStages = 4;       // smem ring of item tiles
 constexpr int kAccum = 4;        // TMEM accumulator buffers (4 x 128 columns)
-static_assert(kStages == kAccum, "stage release piggybacks on the accumulator barrier");
 constexpr int kMaxK = 32;
 constexpr int kFmaSignCols = 16;  // of every 32 columns, sign bits accumulated on the FMA pipe
 
@@ -74,15 +73,18 @@ __device__ __forceinline__ float next_below(float t) {
 }
 
 // Shared-memory carve-up (dynamic, base aligned to 1024 for the 128-byte swizzle).
-template <int D>
+// Ring depth: 4 stages / accumulators of 128 items, or 2 of 256 (TMEM has 512 columns).
+template <int D, int BN>
 struct CatSmem {
   static constexpr int kKBlocks = D / 64;                 // 64-wide (128 B) K blocks
-  static constexpr int kTileBytes = kBlockN * D * 2;      // one operand tile
+  static constexpr int kRing = 512 / BN;                  // smem stages == TMEM accumulators
+  static constexpr int kATileBytes = kBlockM * D * 2;     // user tile
+  static constexpr int kTileBytes = BN * D * 2;           // one item tile
   static constexpr int kOffA = 0;
-  static constexpr int kOffB = kTileBytes;
-  static constexpr int kOffBar = kOffB + kStages * kTileBytes;
-  // barriers: full[kStages], empty[kStages], acc_full[kAccum], acc_empty[kAccum], a_full
-  static constexpr int kNumBars = 2 * kStages + 2 * kAccum + 1;
+  static constexpr int kOffB = kATileBytes;
+  static constexpr int kOffBar = kOffB + kRing * kTileBytes;
+  // barriers: full[4], empty[4], acc_full[4], acc_empty[4], a_full (sized for the deepest ring)
+  static constexpr int kNumBars = 2 * 4 + 2 * 4 + 1;
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr int kOffCnt = kOffTmemPtr + 8;         // int[nsets][128] (per-set rank counts)
   // then float[nsets*k*128] scores and int[nsets*k*128] ids of the per-thread top-k lists
@@ -97,22 +99,24 @@ struct CatSmem {
 // so every MMA reads only the item tile from shared memory -- in SS mode the 128 x 16 A slice is
 // re-read from smem by each instruction and the N=128 MMA is shared-memory-bandwidth bound.
 // TMEM then holds 3 accumulators (384 columns) + A (64 columns).
-template <int D, int MODE, int NSETS, int CL, bool TS>
+template <int D, int MODE, int NSETS, int CL, bool TS, int BN>
 __global__ void __launch_bounds__(96 + NSETS * 128, 1)
 catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                      const __grid_constant__ CUtensorMap map_items, CatalogParams p) {
-  using L = CatSmem<D>;
-  constexpr int NACC = TS ? 3 : kAccum;     // accumulator ring == smem stage ring depth
-  constexpr uint32_t kTmemA = NACC * kBlockN; // TMEM column of the A operand (TS mode)
+  using L = CatSmem<D, BN>;
+  static_assert(!TS || BN == 128, "TS mode is only wired for 128-item tiles");
+  constexpr int NACC = TS ? 3 : L::kRing;   // accumulator ring == smem stage ring depth
+  constexpr uint32_t kTmemA = NACC * BN;    // TMEM column of the A operand (TS mode)
+  constexpr int kBarStride = 4;             // barrier arrays are laid out for the deepest ring
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* bar_full = bars;
-  uint64_t* bar_empty = bars + kStages;
-  uint64_t* bar_acc_full = bars + 2 * kStages;
-  uint64_t* bar_acc_empty = bars + 2 * kStages + kAccum;
-  uint64_t* bar_a = bars + 2 * kStages + 2 * kAccum;
+  uint64_t* bar_empty = bars + kBarStride;
+  uint64_t* bar_acc_full = bars + 2 * kBarStride;
+  uint64_t* bar_acc_empty = bars + 3 * kBarStride;
+  uint64_t* bar_a = bars + 4 * kBarStride;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
   int* s_cnt = reinterpret_cast<int*>(smem + L::kOffCnt);
   float* s_val = reinterpret_cast<float*>(smem + L::off_list(NSETS));
@@ -121,7 +125,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * kBlockM;
-  const int total_tiles = static_cast<int>((p.n_items + kBlockN - 1) / kBlockN);
+  const int total_tiles = static_cast<int>((p.n_items + BN - 1) / BN);
   const int tile_begin = blockIdx.y * p.tiles_per_split;
   const int tile_end = min(total_tiles, tile_begin + p.tiles_per_split);
   const int n_tiles = max(0, tile_end - tile_begin);
@@ -129,8 +133,8 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&map_users);
     ptx::tma_prefetch_desc(&map_items);
-    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&bar_full[i], 1); ptx::mbar_init(&bar_empty[i], CL); }
-    for (int i = 0; i < kAccum; ++i) { ptx::mbar_init(&bar_acc_full[i], 1); ptx::mbar_init(&bar_acc_empty[i], (p.debug_flags & 16384u) ? 1 : 4); }
+    for (int i = 0; i < NACC; ++i) { ptx::mbar_init(&bar_full[i], 1); ptx::mbar_init(&bar_empty[i], CL); }
+    for (int i = 0; i < NACC; ++i) { ptx::mbar_init(&bar_acc_full[i], 1); ptx::mbar_init(&bar_acc_empty[i], (p.debug_flags & 16384u) ? 1 : 4); }
     ptx::mbar_init(bar_a, TS ? 4 : 1);
     ptx::mbar_fence_init();
   }
@@ -149,7 +153,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     // ===================== TMA producer (whole warp loops; one elected lane issues) ========
     const bool leader = ptx::elect_one();
     if (leader && !TS) {
-      ptx::mbar_arrive_expect_tx(bar_a, L::kTileBytes);
+      ptx::mbar_arrive_expect_tx(bar_a, L::kATileBytes);
       for (int kb = 0; kb < L::kKBlocks; ++kb)
         ptx::tma_load_2d(&map_users, bar_a, smem + L::kOffA + kb * (kBlockM * 128), kb * 64,
                          static_cast<int32_t>(m0));
@@ -161,7 +165,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       const long long tp0 = prof ? clock64() : 0;
       // CL == 1: the stage of tile j-4 is free exactly when that tile's MMAs have retired, which
       // is what acc_full[j % 4] signals to the epilogue -- one tcgen05.commit per tile serves both
-      // (kStages == kAccum).  CL == 2 needs the peer's MMAs too and keeps a separate barrier.
+      // (same ring depth).  CL == 2 needs the peer's MMAs too and keeps a separate barrier.
       ptx::mbar_wait_warp(CL == 1 ? &bar_acc_full[s] : &bar_empty[s], ph ^ 1, spin);
       if (prof && lane == 0) g_prof[0] += clock64() - tp0;
       if (leader) {
@@ -170,16 +174,16 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         } else {
           ptx::mbar_arrive_expect_tx(&bar_full[s], L::kTileBytes);
           uint8_t* dst = smem + L::kOffB + s * L::kTileBytes;
-          const int32_t n0 = (tile_begin + j) * kBlockN;
+          const int32_t n0 = (tile_begin + j) * BN;
           if (CL == 1) {
             for (int kb = 0; kb < L::kKBlocks; ++kb)
-              ptx::tma_load_2d(&map_items, &bar_full[s], dst + kb * (kBlockN * 128), kb * 64, n0);
+              ptx::tma_load_2d(&map_items, &bar_full[s], dst + kb * (BN * 128), kb * 64, n0);
           } else {
             // this CTA fetches rows [rank*64, rank*64+64) of the tile for the whole cluster
-            constexpr int kHalf = kBlockN / CL;
+            constexpr int kHalf = BN / CL;
             for (int kb = 0; kb < L::kKBlocks; ++kb)
               ptx::tma_load_2d_mcast(&map_items, &bar_full[s],
-                                     dst + kb * (kBlockN * 128) + cta_rank * (kHalf * 128), kb * 64,
+                                     dst + kb * (BN * 128) + cta_rank * (kHalf * 128), kb * 64,
                                      n0 + static_cast<int32_t>(cta_rank) * kHalf, kClMask);
           }
         }
@@ -191,7 +195,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     // Two issuer warps take alternate tiles: the per-tile wait / issue / commit chain of a single
     // thread (~1700 cycles) would otherwise pace the whole kernel.
     const bool leader = ptx::elect_one();
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, kBlockN);
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, BN);
     const uint32_t a_addr = ptx::smem_u32(smem + L::kOffA);
     const int reps = (p.debug_flags & 16u) ? 0 : ((p.debug_flags & 8u) ? 2 : 1);  // debug knobs
     ptx::mbar_wait_warp(bar_a, 0);
@@ -212,17 +216,18 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         for (int rep = 0; rep < reps; ++rep) {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
-            const uint32_t koff = (k / 4) * (kBlockM * 128) + (k % 4) * 32;  // bytes
+            const uint32_t koff = (k / 4) * (kBlockM * 128) + (k % 4) * 32;   // bytes into the user tile
+            const uint32_t koff_b = (k / 4) * (BN * 128) + (k % 4) * 32;      // bytes into the item tile
             if (p.debug_flags & 1024u)   // debug: N=256 instruction rate (operands/accumulators overlap; timing only)
               ptx::umma_bf16(tmem_base + (a & 1) * 256, ptx::umma_smem_desc_sw128(a_addr + koff),
                              ptx::umma_smem_desc_sw128(ptx::smem_u32(smem + L::kOffB) + (k % 4) * 32),
                              ptx::umma_idesc_bf16(kBlockM, 256), (k > 0 || rep > 0) ? 1u : 0u);
             else if (TS)
-              ptx::umma_bf16_ts(tmem_base + a * kBlockN, tmem_base + kTmemA + k * 8,
-                                ptx::umma_smem_desc_sw128(b_addr + koff), idesc, (k > 0 || rep > 0) ? 1u : 0u);
+              ptx::umma_bf16_ts(tmem_base + a * BN, tmem_base + kTmemA + k * 8,
+                                ptx::umma_smem_desc_sw128(b_addr + koff_b), idesc, (k > 0 || rep > 0) ? 1u : 0u);
             else
-              ptx::umma_bf16(tmem_base + a * kBlockN, ptx::umma_smem_desc_sw128(a_addr + koff),
-                             ptx::umma_smem_desc_sw128(b_addr + koff), idesc, (k > 0 || rep > 0) ? 1u : 0u);
+              ptx::umma_bf16(tmem_base + a * BN, ptx::umma_smem_desc_sw128(a_addr + koff),
+                             ptx::umma_smem_desc_sw128(b_addr + koff_b), idesc, (k > 0 || rep > 0) ? 1u : 0u);
           }
         }
         if (!(p.debug_flags & 32u)) {       // smem stage free (in every CTA of the cluster) once these MMAs retire
@@ -258,7 +263,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     int tgt_tile, tgt_col = -1;               // tile relative to this device's slice
     if (tgt_local < 0) tgt_tile = -1;
     else if (tgt_local >= p.n_items) tgt_tile = INT_MAX;
-    else { tgt_tile = static_cast<int>(tgt_local / kBlockN); tgt_col = static_cast<int>(tgt_local % kBlockN); }
+    else { tgt_tile = static_cast<int>(tgt_local / BN); tgt_col = static_cast<int>(tgt_local % BN); }
 
     int cnt = 0;
     float thr = -CUDART_INF_F;
@@ -302,19 +307,19 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       const int a = j % NACC;
       const uint32_t aph = (j / NACC) & 1;
       const int tile = tile_begin + j;
-      const int n0 = tile * kBlockN;                                   // slice-local item index
-      const int valid = static_cast<int>(rg::min64(kBlockN, p.n_items - n0));
+      const int n0 = tile * BN;                                   // slice-local item index
+      const int valid = static_cast<int>(rg::min64(BN, p.n_items - n0));
       if (p.debug_flags & 64u) break;                 // debug: no accumulator handshake at all
       const long long te0 = prof ? clock64() : 0;
       ptx::mbar_wait_warp(&bar_acc_full[a], aph, spin);
       const long long te1 = prof ? clock64() : 0;
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + lane_base + a * kBlockN;
+      const uint32_t taddr = tmem_base + lane_base + a * BN;
       bool released = false;
 
       if (MODE == kModeDense) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t vr[32];
           ptx::tmem_ld_32x32(taddr + c0, vr);
           ptx::tmem_ld_wait();
@@ -324,11 +329,11 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
               if (c0 + c < valid) p.dense[u * p.n_items + n0 + c0 + c] = __uint_as_float(vr[c]);
           }
         }
-      } else if (__any_sync(0xffffffffu, tile == tgt_tile) || valid < kBlockN) {
+      } else if (__any_sync(0xffffffffu, tile == tgt_tile) || valid < BN) {
         // exact tile (warp-uniform): some lane's target lives here and/or the tile runs past
         // the end of the slice.  Per-column rules, 8 columns at a time.
 #pragma unroll 1
-        for (int c0 = 0; c0 < kBlockN; c0 += 8) {
+        for (int c0 = 0; c0 < BN; c0 += 8) {
           uint32_t w[8];
           ptx::tmem_ld_32x8(taddr + c0, w);
           ptx::tmem_ld_wait();
@@ -359,9 +364,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         // NSETS=2: the whole accumulator row in one TMEM load (128 registers, a single wait per
         // tile; the other set's load overlaps this warp's compute).  NSETS=4: two 64-column loads
         // (the register file only allows ~100 registers per thread with 18 warps).
-        constexpr int CH = NSETS == 2 ? kBlockN : 64;
+        constexpr int CH = NSETS == 2 ? 128 : 64;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kBlockN; c0 += CH) {
+        for (int c0 = 0; c0 < BN; c0 += CH) {
           if (p.debug_flags & 2u) break;               // debug: no TMEM reads, no compute (timing floor)
           uint32_t vr[CH];
           ptx::tmem_ld_cols<CH>(taddr + c0, vr);
@@ -403,7 +408,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           }
           // (b) the scores now live in registers only: hand the accumulator back to the MMA warp
           // before the (long) rank count
-          if (c0 + CH == kBlockN) {
+          if (c0 + CH == BN) {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
@@ -616,9 +621,9 @@ static int make_rowmajor_map(CUtensorMap* map, const void* base, int64_t rows, i
   return RECGURU_OK;
 }
 
-static int pick_splits(int64_t U, int64_t n_items) {
+static int pick_splits(int64_t U, int64_t n_items, int bn) {
   const int64_t m_tiles = ceil_div(U, kBlockM);
-  const int64_t n_tiles = ceil_div(n_items, kBlockN);
+  const int64_t n_tiles = ceil_div(n_items, bn);
   if (m_tiles >= 2 * kNumSMs) return 1;
   int64_t s = ceil_div(2 * kNumSMs, m_tiles);
   const int64_t max_s = n_tiles / 8 > 0 ? n_tiles / 8 : 1;  // >= 8 tiles per split
@@ -631,13 +636,21 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// Items per accumulator hand-off in the top-k sweep: 128 (4 accumulators x 128 TMEM columns, 4 smem
+// stages of 32 KB).  256 (2 x 256 columns) halves the hand-offs per flop but leaves room for only
+// two 64 KB smem stages, which exposes the TMA latency: measured 46 ms vs 34 ms on cfg4
+// (profiles/catalog_exp23.log); kept as a knob.
+static int catalog_bn() {
+  const int bn = env_int("RECGURU_CATALOG_BN", 128);
+  return bn == 256 ? 256 : 128;
+}
 
-template <int D, int MODE, int NSETS, int CL, bool TS>
+template <int D, int MODE, int NSETS, int CL, bool TS, int BN>
 static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const CatalogParams& p,
                           cudaStream_t st) {
-  const int smem = CatSmem<D>::bytes(MODE == kModeTopK ? p.k : 0, NSETS);
+  const int smem = CatSmem<D, BN>::bytes(MODE == kModeTopK ? p.k : 0, NSETS);
   RG_REQUIRE(smem <= 227 * 1024, RECGURU_E_UNSUPPORTED, "catalog: k=%d needs %d B of shared memory", p.k, smem);
-  auto kern = catalog_sweep_kernel<D, MODE, NSETS, CL, TS>;
+  auto kern = catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -677,31 +690,38 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
 // Epilogue sets: 2 (8 warps, one 128-register TMEM load per tile) by default; 4 is kept for
 // experiments.  Cluster of 2 with TMA multicast whenever there are at least two user tiles.
 template <int D, int MODE>
-static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams p, cudaStream_t st) {
+static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams p, int bn, cudaStream_t st) {
   p.two = 2u;
   p.debug_flags = static_cast<uint32_t>(env_int("RECGURU_CATALOG_DEBUG", 0));
+  p.tiles_per_split = static_cast<int>(ceil_div(ceil_div(p.n_items, bn), p.n_splits));
   int nsets = env_int("RECGURU_CATALOG_SETS", 2);
   if (nsets != 2 && nsets != 4) nsets = 2;
-  if (CatSmem<D>::bytes(MODE == kModeTopK ? p.k : 0, 4) > 227 * 1024) nsets = 2;
   int cl = env_int("RECGURU_CATALOG_CLUSTER", 1);
   if (cl != 1 && cl != 2) cl = 1;
   if (p.U <= kBlockM) cl = 1;
   CUtensorMap mi;
-  int rc = make_rowmajor_map(&mi, items, p.n_items, D, kBlockN / cl);
+  if (bn == 256) {
+    // 2 epilogue sets <-> 2 accumulators of 256 columns; knobs for sets / cluster / TS apply to
+    // the 128-item variant only
+    int rc = make_rowmajor_map(&mi, items, p.n_items, D, 256);
+    if (rc) return rc;
+    return launch_sweep_n<D, MODE, 2, 1, false, 256>(mu, mi, p, st);
+  }
+  int rc = make_rowmajor_map(&mi, items, p.n_items, D, 128 / cl);
   if (rc) return rc;
   const bool ts = D == 128 && env_int("RECGURU_CATALOG_TS", 0) != 0;
   if (ts) {   // experimental knob: measured no faster than SS; 2 epilogue sets only
-    if constexpr (D == 128) return launch_sweep_n<D, MODE, 2, 1, true>(mu, mi, p, st);
+    if constexpr (D == 128) return launch_sweep_n<D, MODE, 2, 1, true, 128>(mu, mi, p, st);
   }
-  if (nsets == 4) return cl == 2 ? launch_sweep_n<D, MODE, 4, 2, false>(mu, mi, p, st) : launch_sweep_n<D, MODE, 4, 1, false>(mu, mi, p, st);
-  return cl == 2 ? launch_sweep_n<D, MODE, 2, 2, false>(mu, mi, p, st) : launch_sweep_n<D, MODE, 2, 1, false>(mu, mi, p, st);
+  if (nsets == 4) return cl == 2 ? launch_sweep_n<D, MODE, 4, 2, false, 128>(mu, mi, p, st) : launch_sweep_n<D, MODE, 4, 1, false, 128>(mu, mi, p, st);
+  return cl == 2 ? launch_sweep_n<D, MODE, 2, 2, false, 128>(mu, mi, p, st) : launch_sweep_n<D, MODE, 2, 1, false, 128>(mu, mi, p, st);
 }
 
 static int check_catalog(const char* who, const void* users, int64_t U, const void* items,
                          int64_t n_items, int64_t d) {
   RG_REQUIRE(users && items, RECGURU_E_SHAPE, "%s: null pointer", who);
   RG_REQUIRE(aligned16(users) && aligned16(items), RECGURU_E_SHAPE, "%s: operands must be 16-byte aligned", who);
-  RG_REQUIRE(U > 0 && n_items > 0 && n_items < (1ll << 31) - kBlockN && U < (1ll << 31),
+  RG_REQUIRE(U > 0 && n_items > 0 && n_items < (1ll << 31) - 256 && U < (1ll << 31),
              RECGURU_E_SHAPE, "%s: bad sizes U=%lld n_items=%lld", who, (long long)U, (long long)n_items);
   RG_REQUIRE(d == 64 || d == 128, RECGURU_E_UNSUPPORTED, "%s: d=%lld not in {64,128}", who, (long long)d);
   return RECGURU_OK;
@@ -713,7 +733,7 @@ extern "C" int64_t recguru_catalog_workspace_bytes(int64_t U, int64_t n_items, i
                                                    int64_t k) {
   (void)d;
   if (U <= 0 || n_items <= 0 || k < 1 || k > rg::kMaxK) return RECGURU_E_SHAPE;
-  const int s = rg::pick_splits(U, n_items);
+  const int s = rg::pick_splits(U, n_items, rg::catalog_bn());
   if (s == 1) return 256;
   return rg::align_up(static_cast<int64_t>(s) * U * k * 12, 256) +
          rg::align_up(static_cast<int64_t>(s) * U * 8, 256) + 512;
@@ -769,9 +789,8 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
   p.U = U; p.n_items = n_items; p.id_lo = id_lo; p.target = target; p.tscore = target_score;
   p.k = static_cast<int>(k); p.dense = nullptr; p.two = 2u;
   p.users = static_cast<const __nv_bfloat16*>(users_bf16);
-  p.n_splits = pick_splits(U, n_items);
-  const int64_t n_tiles = ceil_div(n_items, kBlockN);
-  p.tiles_per_split = static_cast<int>(ceil_div(n_tiles, p.n_splits));
+  const int bn = catalog_bn();
+  p.n_splits = pick_splits(U, n_items, bn);
   if (p.n_splits == 1) {
     p.out_val = topk_val; p.out_id = topk_id; p.out_cnt = rank_count;
   } else {
@@ -785,7 +804,7 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
     p.out_id = reinterpret_cast<int64_t*>(ws + sv);
     p.out_cnt = reinterpret_cast<int64_t*>(ws + sv + si);
   }
-  rc = d == 64 ? launch_sweep<64, kModeTopK>(items_bf16, mu, p, st) : launch_sweep<128, kModeTopK>(items_bf16, mu, p, st);
+  rc = d == 64 ? launch_sweep<64, kModeTopK>(items_bf16, mu, p, bn, st) : launch_sweep<128, kModeTopK>(items_bf16, mu, p, bn, st);
   if (rc) return rc;
   if (p.n_splits > 1)
     return recguru_topk_merge(p.out_val, p.out_id, p.out_cnt, p.n_splits, U, k, topk_val, topk_id,
@@ -807,8 +826,7 @@ extern "C" int recguru_catalog_scores_dense(const void* users_bf16, int64_t U,
   memset(&p, 0, sizeof(p));
   p.U = U; p.n_items = n_items; p.k = 1; p.dense = scores; p.two = 2u;
   p.users = static_cast<const __nv_bfloat16*>(users_bf16);
-  p.n_splits = pick_splits(U, n_items);
-  p.tiles_per_split = static_cast<int>(ceil_div(ceil_div(n_items, kBlockN), p.n_splits));
+  p.n_splits = pick_splits(U, n_items, 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return d == 64 ? launch_sweep<64, kModeDense>(items_bf16, mu, p, st) : launch_sweep<128, kModeDense>(items_bf16, mu, p, st);
+  return d == 64 ? launch_sweep<64, kModeDense>(items_bf16, mu, p, 128, st) : launch_sweep<128, kModeDense>(items_bf16, mu, p, 128, st);
 }

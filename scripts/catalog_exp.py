@@ -39,8 +39,9 @@ def run(n_items, label, **env):
 
 
 n_items = 1_000_000
-run(n_items, "SS sets=2 (2 MMA warps)", RECGURU_CATALOG_DEBUG=512)
-run(n_items, "SS sets=4", RECGURU_CATALOG_SETS=4)
-run(n_items, "MMA + acc ring, no TMEM ld", RECGURU_CATALOG_DEBUG=6 + 32)
-run(n_items, "no compute", RECGURU_CATALOG_DEBUG=1)
-run(4_000_000, "SS sets=2 4M")
+run(n_items, "BN=256 full", RECGURU_CATALOG_DEBUG=512)
+run(n_items, "BN=128 full", RECGURU_CATALOG_BN=128)
+run(n_items, "BN=256 idle epilogue", RECGURU_CATALOG_DEBUG=2)
+run(n_items, "BN=256 no compute", RECGURU_CATALOG_DEBUG=1)
+run(4_000_000, "BN=256 4M")
+run(4_000_000, "BN=128 4M", RECGURU_CATALOG_BN=128)
