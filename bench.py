@@ -211,10 +211,20 @@ def bench_train(D: Dist, args, peaks):
         ops.raw_embedding_bwd(sites, hp.V1, hp.d, 0, out=hp.dW, zero_fill=True, workspace=hp.ws_bwd)
         if rec: rec[4].record()
 
+    # per-stage breakdown: eager launches with events between the stages
     l0 = _lib.launch_count()
-    with ClockSampler(torch.cuda.current_device()) as cs:
-        ms = timed_loop(D, step, K, Wm)
+    ms_eager = timed_loop(D, step, K, Wm)
     launches = (_lib.launch_count() - l0) * K // (K + Wm)
+    # the timed number: the same step (same kernels, same buffers) replayed as one CUDA graph
+    # per rotating batch -- the way a launch-bound chain of short kernels is meant to be driven
+    if args.no_graph:
+        with ClockSampler(torch.cuda.current_device()) as cs:
+            ms = timed_loop(D, step, K, Wm)
+    else:
+        graphs = [hp.capture_step(b["tb"].dec_in, b["tb"].dec_out, b["tb"].n_items, b["h"], b["g"])
+                  for b in batches]
+        with ClockSampler(torch.cuda.current_device()) as cs:
+            ms = timed_loop(D, lambda i: graphs[i % n_batches].replay(), K, Wm)
     stage_names = ["gather_pe_mask", "sampled_score_loss_fwd", "sampled_score_bwd_dh", "embedding_bwd"]
     stage_ms = {nme: sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)) / K
                 for j, nme in enumerate(stage_names)}
@@ -268,11 +278,21 @@ def bench_train(D: Dist, args, peaks):
         cur.wait_event(copied[slot])
         enqueue_copy(i + 1)                                  # overlaps this step's kernels
         state["primed"] = i + 1
-        loss, _, _ = hp.step(d_in[slot]["dec_in"], d_in[slot]["dec_out"], d_in[slot]["n_items"], b["h"], b["g"])
+        if e2e_graphs is None:
+            hp.step(d_in[slot]["dec_in"], d_in[slot]["dec_out"], d_in[slot]["n_items"], b["h"], b["g"])
+        else:
+            e2e_graphs[i % n_batches].replay()
         consumed[slot].record(cur)
-        loss_host.copy_(loss.view(1), non_blocking=True)
+        loss_host.copy_(hp.sbuf["aux"][0:1], non_blocking=True)
         cur.synchronize()                                    # the reference reads loss.item() every step
 
+    # batch b always lands in id slot b % 2 (n_batches is even), so one graph per batch suffices
+    for slot in range(2):                       # valid ids in the static buffers while capturing
+        for k in d_in[slot]:
+            d_in[slot][k].copy_(pin[slot][k])
+    e2e_graphs = None if (args.no_graph or not args.e2e_graph) else [
+        hp.capture_step(d_in[b % 2]["dec_in"], d_in[b % 2]["dec_out"], d_in[b % 2]["n_items"],
+                        batches[b]["h"], batches[b]["g"]) for b in range(n_batches)]
     ms_e2e = timed_loop(D, e2e_step, K, Wm)
     h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
     seqs = cfg["B"] * D.world
@@ -280,10 +300,13 @@ def bench_train(D: Dist, args, peaks):
         "value": seqs * K / (ms / 1e3), "ms_per_step": ms / K, "stages": stages, "roofline": roof,
         "e2e": {"value": seqs * K / (ms_e2e / 1e3), "unit": "seqs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
+                "launch_mode": "cuda_graph" if e2e_graphs is not None else "eager (TrainHotPath.step)",
                 "note": "ids from pinned host memory each step, loss read back each step; h and the "
                         "gradient w.r.t. the input activations come from the (out-of-scope) transformer "
                         "and are device resident"},
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
+        "launch_mode": "eager" if args.no_graph else "cuda_graph (one graph per rotating batch)",
+        "ms_per_step_eager": ms_eager / K,
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
         "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,
                            "distinct_rows": distinct,
@@ -497,6 +520,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "catalog"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-graph", action="store_true",
+                    help="replay CUDA graphs in the e2e loop too (measured slower than eager launches there: after "
+                         "the per-step host sync a graph launch starts later than the first eager kernel)")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--only", default="", help="comma list of sections: train,gather,cfg4,cfg5")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
@@ -559,7 +586,8 @@ def main():
                     "roofline": train["roofline"], "stages": train["stages"], "e2e": train["e2e"],
                     "gpu_launches": train["gpu_launches"], "clocks": train["clocks"],
                     "algorithmic_mb_per_step": train["algorithmic_mb_per_step"],
-                    "table_backward": train["table_backward"]}
+                    "table_backward": train["table_backward"], "launch_mode": train["launch_mode"],
+                    "ms_per_step_eager": train["ms_per_step_eager"]}
             if gather is not None:
                 line["gather"] = gather
             line["catalog"] = cat

@@ -39,6 +39,11 @@ extern "C" {
 #define RECGURU_LOSS_BPR 0     /* tools/lossfunctions.py:52-72  BPRLoss               */
 #define RECGURU_LOSS_BPR_SAS 1 /* tools/lossfunctions.py:75-96  BPRLoss_sas           */
 #define RECGURU_LOSS_SCE 2     /* tools/lossfunctions.py:29-49  SampledCrossEntropyLoss (label 0) */
+/* OR-ed into `kind` of recguru_sampled_score_loss_fwd: positions with mask[i] == 0 are not scored.
+ * The reference scores them and then multiplies their loss term by 0 (lossfunctions.py:44-48,
+ * :66-71,:90-95), so loss, dp_unit and dn_unit are unchanged; only p[i], n[i,:] of those
+ * positions differ (reported as 0).  On a padded batch this removes most of the row gathers. */
+#define RECGURU_LOSS_SKIP_MASKED 0x100
 
 typedef void* recguru_stream_t; /* cudaStream_t */
 
@@ -93,12 +98,36 @@ typedef struct {
   const float* scale; /* device scalar or NULL (e.g. upstream grad of the scalar loss) */
   const float* scale2;/* second device scalar or NULL (e.g. 1/sum(mask), loss_out[1]) */
   int64_t group;      /* gathered indices per row of X (1, or K) */
+  const float* live;  /* [count / group] or NULL: liveness mask per row of X (e.g. the pad mask).
+                         An occurrence carries gradient iff id != padding_idx and
+                         (live ? live[j/group] != 0 : coef == NULL || coef[j] != 0).           */
 } recguru_lookup_site_t;
+
+/* `zero_fill` modes of dW */
+#define RECGURU_DW_ACCUMULATE 0 /* dW += gradient (rows read-modify-written)                    */
+#define RECGURU_DW_ZERO_FILL 1  /* dW = gradient, untouched rows zeroed here (dense-grad contract
+                                   of the reference's Adam)                                     */
+#define RECGURU_DW_PREZEROED 2  /* dW = gradient, the caller zeroed dW (recguru_fill_zero), e.g.
+                                   on another stream                                            */
 
 int64_t recguru_embedding_bwd_workspace_bytes(int64_t total_count, int64_t V1, int64_t d);
 int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites, int64_t d,
                           int64_t V1, int64_t padding_idx, float* dW, int zero_fill,
                           void* workspace, int64_t workspace_bytes, recguru_stream_t stream);
+/* The same computation in two stages, so that a training step can overlap the first with its
+ * forward pass (it depends on the ids and the pad mask only, not on any activation):
+ *   plan  : stable compaction of the live (id, occurrence) pairs + LSD radix sort -> workspace.
+ *           Reads site.ids and site.live (else site.coef); X/scale may still be unset.
+ *   apply : segmented reduce of coef * X rows over the plan, for the SAME ids/counts/groups.
+ * recguru_embedding_bwd == plan followed by apply on one stream.                              */
+int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_host, int n_sites, int64_t V1,
+                               int64_t padding_idx, void* workspace, int64_t workspace_bytes,
+                               recguru_stream_t stream);
+int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_host, int n_sites, int64_t d,
+                                int64_t V1, float* dW, int zero_fill, void* workspace,
+                                int64_t workspace_bytes, recguru_stream_t stream);
+/* p[0 .. n_floats) = 0 (n_floats a multiple of 4, p 16-byte aligned). */
+int recguru_fill_zero(float* p, int64_t n_floats, recguru_stream_t stream);
 
 /* The sort stage on its own (parity: bit-exact vs torch.sort(ids, stable=True)).
  *   sorted_ids[i] = ids[perm[i]], ascending, ties in ascending perm.  ids in [0, V1).   */
@@ -140,6 +169,16 @@ int recguru_sampled_score_bwd_dh(const float* dp, const float* dn, const float* 
                                  const float* scale2, const float* weight, int64_t V1, int64_t d, const int64_t* pos,
                                  const int64_t* neg, int64_t n_pos, int64_t K, float* dh,
                                  recguru_stream_t stream);
+
+/* E1 + R1 -- the reference's own (sampled-candidate) evaluation protocol, fused:
+ *   get_scores (train_auto.py:164-199; gan_training.py:58-87; tools/utils.py:130-141) followed by
+ *   argsort(argsort(-score))[:, 0] (train_auto.py:234-237).
+ *   scores[b,0] = u[b].W[target[b]], scores[b,1+c] = u[b].W[cand[b,c]]  (fp32; scores may be NULL)
+ *   rank[b] = #{c : scores[b,1+c] > scores[b,0]}   -- column 0 (the target) wins every tie, the
+ *   stable reading of the reference idiom.  C = candidate_size (199 / 19999).              */
+int recguru_candidate_scores_rank(const float* u, const float* weight, int64_t V1, int64_t d,
+                                  const int64_t* target, const int64_t* cand, int64_t B, int64_t C,
+                                  float* scores, int64_t* rank, recguru_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Piece 4 -- full-catalog scoring: tcgen05/TMEM GEMM + running top-K + target rank

@@ -11,9 +11,10 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "librecguru_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_SITES = 8
 LOSS_KINDS = {"bpr": 0, "bpr_sas": 1, "sce": 2}
+LOSS_SKIP_MASKED = 0x100
 
 c_i64 = C.c_int64
 c_ptr = C.c_void_p
@@ -23,7 +24,7 @@ class LookupSite(C.Structure):
     """recguru_lookup_site_t"""
     _fields_ = [
         ("ids", c_ptr), ("count", c_i64), ("X", c_ptr), ("coef", c_ptr),
-        ("scale", c_ptr), ("scale2", c_ptr), ("group", c_i64),
+        ("scale", c_ptr), ("scale2", c_ptr), ("group", c_i64), ("live", c_ptr),
     ]
 
 
@@ -38,6 +39,11 @@ SIGNATURES = {
     "recguru_embedding_bwd_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "recguru_embedding_bwd": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_i64, c_ptr,
                                         C.c_int, c_ptr, c_i64, c_ptr]),
+    "recguru_embedding_bwd_plan": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_ptr, c_i64,
+                                             c_ptr]),
+    "recguru_embedding_bwd_apply": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_ptr,
+                                              C.c_int, c_ptr, c_i64, c_ptr]),
+    "recguru_fill_zero": (C.c_int, [c_ptr, c_i64, c_ptr]),
     "recguru_sort_ids_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "recguru_sort_ids": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "recguru_sampled_workspace_bytes": (c_i64, [c_i64, c_i64]),
@@ -48,6 +54,8 @@ SIGNATURES = {
                                            c_ptr, c_ptr, c_i64, c_ptr]),
     "recguru_sampled_score_bwd_dh": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64,
                                                c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "recguru_candidate_scores_rank": (C.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64,
+                                              c_ptr, c_ptr, c_ptr]),
     "recguru_cast_bf16": (C.c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "recguru_catalog_target_scores": (C.c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr,
                                                 c_ptr, c_ptr]),

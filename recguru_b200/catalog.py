@@ -79,6 +79,15 @@ def mrr_at_k_batch(r, k: int) -> float:
     return rank_metrics(t if t.is_cuda else t.cuda(), (k,))[k]["mrr"]
 
 
+def get_scores_rank(u: Tensor, table_weight: Tensor, target: Tensor, n_items: Tensor,
+                    want_scores: bool = False):
+    """The reference's sampled-candidate evaluation step -- ``get_scores`` (train_auto.py:164-199)
+    followed by ``argsort(argsort(-score))[:, 0]`` (:234-237) -- as one kernel.  ``u`` is
+    ``dec_embedding[:, -1, :]``; ``n_items`` the ``[B, candidate_size]`` sampled negatives.
+    Returns ``(scores [B, C+1] | None, rank [B])``; the target (column 0) wins ties."""
+    return ops.raw_candidate_scores_rank(u, table_weight, target, n_items, want_scores)
+
+
 # --------------------------------------------------------------------------------------
 # shard arithmetic
 # --------------------------------------------------------------------------------------

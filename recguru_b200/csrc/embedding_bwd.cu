@@ -42,6 +42,7 @@ struct SiteTable {
   const float* coef[RECGURU_MAX_SITES];
   const float* scale[RECGURU_MAX_SITES];
   const float* scale2[RECGURU_MAX_SITES];
+  const float* live[RECGURU_MAX_SITES];   // optional liveness mask, one entry per row of X
   int64_t offset[RECGURU_MAX_SITES + 1];  // prefix sum of counts
   int group[RECGURU_MAX_SITES];
   int n_sites;
@@ -55,18 +56,19 @@ struct SiteRef {
   const float* coef;
   const float* scale;
   const float* scale2;
+  const float* live;
   int64_t offset;
   int group;
   int index;
 };
 template <int NS>  // compile-time bound on the number of sites (the select chain is per element)
 __device__ __forceinline__ SiteRef find_site(const SiteTable& st, int64_t occ) {
-  SiteRef r = {st.ids[0], st.X[0], st.coef[0], st.scale[0], st.scale2[0], 0, st.group[0], 0};
+  SiteRef r = {st.ids[0], st.X[0], st.coef[0], st.scale[0], st.scale2[0], st.live[0], 0, st.group[0], 0};
 #pragma unroll
   for (int i = 1; i < NS; ++i) {
     if (i < st.n_sites && occ >= st.offset[i]) {
       r.ids = st.ids[i]; r.X = st.X[i]; r.coef = st.coef[i]; r.scale = st.scale[i];
-      r.scale2 = st.scale2[i]; r.offset = st.offset[i]; r.group = st.group[i]; r.index = i;
+      r.scale2 = st.scale2[i]; r.live = st.live[i]; r.offset = st.offset[i]; r.group = st.group[i]; r.index = i;
     }
   }
   return r;
@@ -89,7 +91,11 @@ __device__ __forceinline__ bool occurrence_live(const SiteTable& st, int64_t i, 
   const int64_t j = i - r.offset;
   const int64_t id = r.ids[j];
   *key = static_cast<uint32_t>(id);
-  return !(id == padding_idx || (r.coef != nullptr && r.coef[j] == 0.f));
+  if (id == padding_idx) return false;
+  // a site with a liveness mask is planned from the mask alone (its coefficients may not exist
+  // yet: the plan of a step can run while the forward pass is still computing them)
+  if (r.live != nullptr) return r.live[j / r.group] != 0.f;
+  return !(r.coef != nullptr && r.coef[j] == 0.f);
 }
 
 // pass 1: live occurrences per tile (same warp-striped tile layout as the sort)
@@ -401,7 +407,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
   uint32_t cur = first_key;
   bool cur_is_lead = lead_open;
 
-  constexpr int kBatch = 8;
+  constexpr int kBatch = 8;                  // rows in flight per warp (12/16 measured slower: spills)
   for (int b0 = 0; b0 < n; b0 += kBatch) {
     float4 x[kBatch][VPL];
     uint32_t k[kBatch];
@@ -680,43 +686,105 @@ extern "C" int64_t recguru_embedding_bwd_workspace_bytes(int64_t total_count, in
   return p.end + rg::align_up(n_chunks * 2 * d * 4, 256);
 }
 
-extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites,
-                                     int64_t d, int64_t V1, int64_t padding_idx, float* dW,
-                                     int zero_fill, void* workspace, int64_t workspace_bytes,
-                                     recguru_stream_t stream) {
-  using namespace rg;
+namespace rg {
+// validate + flatten the host site array
+static int build_site_table(const char* who, const recguru_lookup_site_t* sites_host, int n_sites,
+                            bool need_x, SiteTable* tab, int64_t* total_out) {
   RG_REQUIRE(sites_host && n_sites >= 1 && n_sites <= RECGURU_MAX_SITES, RECGURU_E_SHAPE,
-             "embedding_bwd: n_sites=%d out of range [1,%d]", n_sites, RECGURU_MAX_SITES);
+             "%s: n_sites=%d out of range [1,%d]", who, n_sites, RECGURU_MAX_SITES);
+  memset(tab, 0, sizeof(*tab));
+  tab->n_sites = n_sites;
+  int64_t total = 0;
+  for (int s = 0; s < n_sites; ++s) {
+    const recguru_lookup_site_t& site = sites_host[s];
+    RG_REQUIRE(site.count >= 0 && site.group >= 1 && site.count % site.group == 0, RECGURU_E_SHAPE,
+               "%s: site %d count=%lld group=%lld", who, s, (long long)site.count, (long long)site.group);
+    RG_REQUIRE(site.count == 0 || (site.ids && (!need_x || (site.X && aligned16(site.X)))), RECGURU_E_SHAPE,
+               "%s: site %d null/unaligned pointer", who, s);
+    tab->ids[s] = site.ids; tab->X[s] = site.X; tab->coef[s] = site.coef; tab->scale[s] = site.scale;
+    tab->scale2[s] = site.scale2; tab->live[s] = site.live;
+    tab->group[s] = static_cast<int>(site.group);
+    tab->offset[s] = total;
+    total += site.count;
+  }
+  for (int s = n_sites; s <= RECGURU_MAX_SITES; ++s) tab->offset[s] = total;
+  RG_REQUIRE(total < (1ll << 32), RECGURU_E_UNSUPPORTED, "%s: total count >= 2^32", who);
+  *total_out = total;
+  return RECGURU_OK;
+}
+}  // namespace rg
+
+extern "C" int recguru_fill_zero(float* p, int64_t n_floats, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(n_floats >= 0 && n_floats % 4 == 0 && (n_floats == 0 || (p && aligned16(p))), RECGURU_E_SHAPE,
+             "fill_zero: need a 16-byte aligned buffer of a multiple of 4 floats");
+  if (n_floats == 0) return RECGURU_OK;
+  const int64_t n_vec = n_floats / 4;
+  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 4), kNumSMs * 16);
+  zero_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(p), n_vec);
+  RG_CHECK_LAUNCH("zero_fill");
+  return RECGURU_OK;
+}
+
+// Stage A of the table backward: stable compaction of the live (id, occurrence) pairs and the
+// LSD radix sort.  Reads ids and the liveness source only (site.live, else site.coef).
+extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_host, int n_sites,
+                                          int64_t V1, int64_t padding_idx, void* workspace,
+                                          int64_t workspace_bytes, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "embedding_bwd_plan: bad V1");
+  SiteTable tab;
+  int64_t total = 0;
+  int rc = build_site_table("embedding_bwd_plan", sites_host, n_sites, false, &tab, &total);
+  if (rc) return rc;
+  if (total == 0) return RECGURU_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SortPlan p = make_sort_plan(total, V1);
+  RG_REQUIRE(workspace && workspace_bytes >= p.end, RECGURU_E_WORKSPACE,
+             "embedding_bwd_plan: workspace %lld < %lld", (long long)workspace_bytes, (long long)p.end);
+  char* ws = static_cast<char*>(workspace);
+  uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(ws + p.off_tilecnt);
+  uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
+  const unsigned tiles = static_cast<unsigned>(ceil_div(total, kCompactTile));
+  uint32_t* ka = reinterpret_cast<uint32_t*>(ws + p.off_keys_a);
+  uint32_t* va = reinterpret_cast<uint32_t*>(ws + p.off_vals_a);
+  if (n_sites <= 1) compact_count_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+  else if (n_sites <= 3) compact_count_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+  else compact_count_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+  RG_CHECK_LAUNCH("compact_count");
+  compact_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, static_cast<int>(tiles), n_live);
+  RG_CHECK_LAUNCH("compact_scan");
+  if (n_sites <= 1) compact_scatter_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
+  else if (n_sites <= 3) compact_scatter_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
+  else compact_scatter_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
+  RG_CHECK_LAUNCH("compact_scatter");
+  uint32_t *sk, *sv;
+  return run_radix_sort(p, ws, total, n_live, false, st, &sk, &sv, nullptr, nullptr);
+}
+
+// Stage B: (optional zero fill,) chunked segmented reduce + span fix-up over the plan that
+// recguru_embedding_bwd_plan left in `workspace` for the SAME sites (ids, counts, groups).
+extern "C" int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_host, int n_sites,
+                                           int64_t d, int64_t V1, float* dW, int zero_fill,
+                                           void* workspace, int64_t workspace_bytes,
+                                           recguru_stream_t stream) {
+  using namespace rg;
   RG_REQUIRE(dW && aligned16(dW), RECGURU_E_SHAPE, "embedding_bwd: dW null or unaligned");
   RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "embedding_bwd: bad V1");
   RG_REQUIRE(d > 0 && d % 4 == 0 && d <= 512, RECGURU_E_UNSUPPORTED,
              "embedding_bwd: d=%lld must be a multiple of 4 and <= 512", (long long)d);
   SiteTable tab;
-  memset(&tab, 0, sizeof(tab));
-  tab.n_sites = n_sites;
   int64_t total = 0;
-  for (int s = 0; s < n_sites; ++s) {
-    const recguru_lookup_site_t& site = sites_host[s];
-    RG_REQUIRE(site.count >= 0 && site.group >= 1 && site.count % site.group == 0, RECGURU_E_SHAPE,
-               "embedding_bwd: site %d count=%lld group=%lld", s, (long long)site.count,
-               (long long)site.group);
-    RG_REQUIRE(site.count == 0 || (site.ids && site.X && aligned16(site.X)), RECGURU_E_SHAPE,
-               "embedding_bwd: site %d null/unaligned pointer", s);
-    tab.ids[s] = site.ids; tab.X[s] = site.X; tab.coef[s] = site.coef; tab.scale[s] = site.scale; tab.scale2[s] = site.scale2;
-    tab.group[s] = static_cast<int>(site.group);
-    tab.offset[s] = total;
-    total += site.count;
-  }
-  for (int s = n_sites; s <= RECGURU_MAX_SITES; ++s) tab.offset[s] = total;
-  RG_REQUIRE(total < (1ll << 32), RECGURU_E_UNSUPPORTED, "embedding_bwd: total count >= 2^32");
+  int rc = build_site_table("embedding_bwd", sites_host, n_sites, true, &tab, &total);
+  if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int vec = static_cast<int>(d / 4);
-  if (zero_fill) {
-    const int64_t n_vec = V1 * vec;
-    const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 4), kNumSMs * 16);
-    zero_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(dW),
-                                                                    n_vec);
-    RG_CHECK_LAUNCH("zero_fill");
+  RG_REQUIRE(zero_fill >= 0 && zero_fill <= RECGURU_DW_PREZEROED, RECGURU_E_SHAPE,
+             "embedding_bwd: zero_fill=%d", zero_fill);
+  if (zero_fill == RECGURU_DW_ZERO_FILL) {
+    rc = recguru_fill_zero(dW, V1 * d, stream);
+    if (rc) return rc;
   }
   if (total == 0) return RECGURU_OK;
   const SortPlan p = make_sort_plan(total, V1);
@@ -725,29 +793,14 @@ extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, in
   RG_REQUIRE(workspace && workspace_bytes >= need, RECGURU_E_WORKSPACE,
              "embedding_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)need);
   char* ws = static_cast<char*>(workspace);
-  uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(ws + p.off_tilecnt);
-  uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
-  {
-    const unsigned tiles = static_cast<unsigned>(ceil_div(total, kCompactTile));
-    uint32_t* ka = reinterpret_cast<uint32_t*>(ws + p.off_keys_a);
-    uint32_t* va = reinterpret_cast<uint32_t*>(ws + p.off_vals_a);
-    if (n_sites <= 1) compact_count_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
-    else if (n_sites <= 3) compact_count_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
-    else compact_count_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
-    RG_CHECK_LAUNCH("compact_count");
-    compact_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, static_cast<int>(tiles), n_live);
-    RG_CHECK_LAUNCH("compact_scan");
-    if (n_sites <= 1) compact_scatter_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
-    else if (n_sites <= 3) compact_scatter_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
-    else compact_scatter_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
-    RG_CHECK_LAUNCH("compact_scatter");
-  }
-  uint32_t *sk, *sv;
-  int rc = run_radix_sort(p, ws, total, n_live, false, st, &sk, &sv, nullptr, nullptr);
-  if (rc != RECGURU_OK) return rc;
+  const uint32_t* n_live = reinterpret_cast<const uint32_t*>(ws + p.off_nlive);
+  // the sort ping-pongs between the two key/value arrays: after `passes` passes the result
+  // sits in array (passes & 1)
+  const uint32_t* sk = reinterpret_cast<const uint32_t*>(ws + ((p.passes & 1) ? p.off_keys_b : p.off_keys_a));
+  const uint32_t* sv = reinterpret_cast<const uint32_t*>(ws + ((p.passes & 1) ? p.off_vals_b : p.off_vals_a));
   float4* partial = reinterpret_cast<float4*>(ws + p.end);
   float4* dW4 = reinterpret_cast<float4*>(dW);
-  const int accumulate = zero_fill ? 0 : 1;
+  const int accumulate = zero_fill == RECGURU_DW_ACCUMULATE ? 1 : 0;
   const unsigned grid = static_cast<unsigned>(ceil_div(n_chunks, kReduceWarps));
   const int vpl = (vec + 31) / 32;
 #define RG_LAUNCH_REDUCE(V)                                                                   \
@@ -781,4 +834,14 @@ extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, in
   }
 #undef RG_LAUNCH_REDUCE
   return RECGURU_OK;
+}
+
+extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites,
+                                     int64_t d, int64_t V1, int64_t padding_idx, float* dW,
+                                     int zero_fill, void* workspace, int64_t workspace_bytes,
+                                     recguru_stream_t stream) {
+  int rc = recguru_embedding_bwd_plan(sites_host, n_sites, V1, padding_idx, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return recguru_embedding_bwd_apply(sites_host, n_sites, d, V1, dW, zero_fill, workspace, workspace_bytes,
+                                     stream);
 }

@@ -96,12 +96,13 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
                          int64_t n_pos, int K, const float* __restrict__ mask, int kind,
                          float* __restrict__ p_out, float* __restrict__ n_out,
                          float* __restrict__ dp_unit, float* __restrict__ dn_unit,
-                         float2* __restrict__ block_partial) {
+                         float2* __restrict__ block_partial, bool skip_masked) {
   constexpr int LANES = VEC < 32 ? VEC : 32;  // lanes cooperating on one row
   constexpr int G = 32 / LANES;               // row groups per warp step
   constexpr int VPL = VEC / LANES;            // float4 per lane per row
   constexpr int UN = 8 / G;                   // rows per group per step: 8 rows in flight per warp
   __shared__ float s_sc[kScoreWarps][kFwdPosPerWarp][kRowPad];
+  __shared__ int s_id[kScoreWarps][kFwdPosPerWarp][32];
   __shared__ float2 s_part[kScoreWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / LANES, sub = lane % LANES;
@@ -109,41 +110,93 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
   const int64_t base = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kFwdPosPerWarp;
   const int n_here = static_cast<int>(rg::min64(kFwdPosPerWarp, n_pos - base));  // may be <= 0
 
-  for (int q = 0; q < n_here; ++q) {
+  // Positions this warp scores.  RECGURU_LOSS_SKIP_MASKED: positions under the pad mask are not
+  // scored (their loss term and derivatives are multiplied by 0 anyway); logits reported as 0.
+  uint32_t live_bits = n_here > 0 ? (0xffffffffu >> (32 - n_here)) : 0u;
+  if (skip_masked) live_bits &= __ballot_sync(0xffffffffu, lane < n_here && __ldg(mask + base + lane) != 0.f);
+  // ids of the scored positions, staged once, coalesced, narrowed to int32; zero scores for the rest
+  {
+    int (*ids)[32] = s_id[warp];
+    if (lane < n_here && ((live_bits >> lane) & 1u)) ids[lane][0] = static_cast<int>(pos[base + lane]);
+    const int tot = max(n_here, 0) * K;
+    for (int idx = lane; idx < tot; idx += 32) {
+      const int q = idx / K, k = idx - q * K;
+      if ((live_bits >> q) & 1u) ids[q][1 + k] = static_cast<int>(neg[base * K + idx]);
+    }
+    for (int q = 0; q < n_here; ++q)
+      if (!((live_bits >> q) & 1u) && lane < C) s_sc[warp][q][lane] = 0.f;
+  }
+  __syncwarp();
+
+  // ---- phase 1: a stream of (position, 8-row step) work items, software pipelined ----------
+  // The loads of item i+1 (the h row and up to 8 table rows) are issued before the dot products
+  // and the butterfly reduction of item i, so a warp always has one gather in flight.
+  uint32_t rem = live_bits;
+  int cq = -1, cc = 0;
+  auto advance = [&](int& q, int& c0) -> bool {
+    if (cq >= 0 && cc + 8 < C) {
+      cc += 8;
+    } else {
+      if (!rem) return false;
+      cq = __ffs(rem) - 1;
+      rem &= rem - 1;
+      cc = 0;
+    }
+    q = cq; c0 = cc;
+    return true;
+  };
+  auto issue = [&](int q, int c0, float4 (&hv)[VPL], float4 (&w)[UN][VPL]) {
     const int64_t i = base + q;
-    int64_t my_id = 0;
-    if (lane == 0) my_id = pos[i];
-    else if (lane <= K) my_id = neg[i * K + (lane - 1)];
-    float4 hv[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) hv[v] = ld_stream_f4(h + i * VEC + v * LANES + sub);
-    for (int c0 = 0; c0 < C; c0 += 8) {
-      float4 w[UN][VPL];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int c = c0 + u * G + g;
-        const int64_t id = __shfl_sync(0xffffffffu, my_id, c < C ? c : 0);
+    for (int u = 0; u < UN; ++u) {
+      const int c = c0 + u * G + g;
+      const int64_t id = s_id[warp][q][c < C ? c : 0];
 #pragma unroll
-        for (int v = 0; v < VPL; ++v)
-          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = 0; v < VPL; ++v)
+        w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto finish = [&](int q, int c0, const float4 (&hv)[VPL], const float4 (&w)[UN][VPL]) {
+    float acc[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      float a = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        a = fmaf(hv[v].x, w[u][v].x, a);
+        a = fmaf(hv[v].y, w[u][v].y, a);
+        a = fmaf(hv[v].z, w[u][v].z, a);
+        a = fmaf(hv[v].w, w[u][v].w, a);
       }
-      float acc[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        float a = 0.f;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          a = fmaf(hv[v].x, w[u][v].x, a);
-          a = fmaf(hv[v].y, w[u][v].y, a);
-          a = fmaf(hv[v].z, w[u][v].z, a);
-          a = fmaf(hv[v].w, w[u][v].w, a);
-        }
-        acc[u] = a;
-      }
-      const float r = group_multi_reduce<LANES, UN>(acc, sub);
-      constexpr int kRep = LANES / UN;          // lanes holding the same row's sum
-      const int c = c0 + (sub / kRep) * G + g;  // row (candidate) this lane ended up with
-      if (sub % kRep == 0 && c < C) s_sc[warp][q][c] = r;
+      acc[u] = a;
+    }
+    const float r = group_multi_reduce<LANES, UN>(acc, sub);
+    constexpr int kRep = LANES / UN;          // lanes holding the same row's sum
+    const int c = c0 + (sub / kRep) * G + g;  // row (candidate) this lane ended up with
+    if (sub % kRep == 0 && c < C) s_sc[warp][q][c] = r;
+  };
+  if constexpr (VPL == 1) {
+    float4 hA[VPL], wA[UN][VPL], hB[VPL], wB[UN][VPL];
+    int qa = 0, ca = 0, qb = 0, cb = 0;
+    bool more = advance(qa, ca);
+    if (more) issue(qa, ca, hA, wA);
+    while (more) {
+      const bool b = advance(qb, cb);
+      if (b) issue(qb, cb, hB, wB);
+      finish(qa, ca, hA, wA);
+      if (!b) break;
+      more = advance(qa, ca);
+      if (more) issue(qa, ca, hA, wA);
+      finish(qb, cb, hB, wB);
+    }
+  } else {   // 1 KB rows: the register file holds one work item per warp
+    float4 hA[VPL], wA[UN][VPL];
+    int qa = 0, ca = 0;
+    while (advance(qa, ca)) {
+      issue(qa, ca, hA, wA);
+      finish(qa, ca, hA, wA);
     }
   }
   __syncwarp();
@@ -350,6 +403,90 @@ sampled_score_bwd_dh_kernel(const float* __restrict__ dp, const float* __restric
   }
 }
 
+// E1 + R1: the reference's sampled-candidate evaluation (get_scores + double argsort), fused.
+//   scores[b, 0] = u[b] . W[target[b]],  scores[b, 1+c] = u[b] . W[cand[b, c]]
+//   rank[b] = #{c : scores[b, 1+c] > scores[b, 0]}        (the target wins every tie)
+// One CTA per user; its 8 warps stride over the candidates in steps of 8 rows per warp with the
+// same 8-rows-in-flight gather + butterfly reduction as the training kernel.  The [B, C+1, d]
+// candidate-embedding tensor of the reference (2.6 GB at C=19999, B=256) never exists.
+template <int VEC>
+__global__ void __launch_bounds__(kScoreWarps * 32)
+candidate_rank_kernel(const float4* __restrict__ u, const float4* __restrict__ weight,
+                      const int64_t* __restrict__ target, const int64_t* __restrict__ cand, int C,
+                      float* __restrict__ scores, int64_t* __restrict__ rank) {
+  constexpr int LANES = VEC < 32 ? VEC : 32;
+  constexpr int G = 32 / LANES;
+  constexpr int VPL = VEC / LANES;
+  constexpr int UN = 8 / G;
+  __shared__ int s_cnt[kScoreWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LANES, sub = lane % LANES;
+  const int64_t b = blockIdx.x;
+  float4 hv[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) hv[v] = __ldg(u + b * VEC + v * LANES + sub);
+  // every warp computes the target score itself (same instruction sequence => identical bits)
+  float s0;
+  {
+    const int64_t tid = target[b];
+    float a = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const float4 w = __ldg(weight + tid * VEC + v * LANES + sub);
+      a = fmaf(hv[v].x, w.x, a); a = fmaf(hv[v].y, w.y, a);
+      a = fmaf(hv[v].z, w.z, a); a = fmaf(hv[v].w, w.w, a);
+    }
+    float acc[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) acc[q] = a;           // same reduction tree as the candidates
+    const float r = group_multi_reduce<LANES, UN>(acc, sub);
+    s0 = __shfl_sync(0xffffffffu, r, 0);
+    if (scores && warp == 0 && lane == 0) scores[b * (C + 1)] = s0;
+  }
+  int cnt = 0;
+  constexpr int kRep = LANES / UN;
+  for (int c0 = warp * 8; c0 < C; c0 += kScoreWarps * 8) {
+    float4 w[UN][VPL];
+    int64_t my_id = 0;
+    if (lane < 8 && c0 + lane < C) my_id = cand[b * C + c0 + lane];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int c = q * G + g;                             // candidate slot within this step (0..7)
+      const int64_t id = __shfl_sync(0xffffffffu, my_id, c);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+        w[q][v] = c0 + c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float acc[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      float a = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        a = fmaf(hv[v].x, w[q][v].x, a); a = fmaf(hv[v].y, w[q][v].y, a);
+        a = fmaf(hv[v].z, w[q][v].z, a); a = fmaf(hv[v].w, w[q][v].w, a);
+      }
+      acc[q] = a;
+    }
+    const float r = group_multi_reduce<LANES, UN>(acc, sub);
+    const int c = c0 + (sub / kRep) * G + g;
+    if (sub % kRep == 0 && c < C) {
+      if (scores) scores[b * (C + 1) + 1 + c] = r;
+      cnt += r > s0 ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kScoreWarps; ++w2) t += s_cnt[w2];
+    rank[b] = t;
+  }
+}
+
 static int check_common(const char* who, int64_t V1, int64_t d, int64_t n_pos, int64_t K) {
   RG_REQUIRE(V1 > 0 && V1 < (1ll << 31) && n_pos >= 0, RECGURU_E_SHAPE, "%s: bad sizes", who);
   RG_REQUIRE(d == 32 || d == 64 || d == 128 || d == 256, RECGURU_E_UNSUPPORTED,
@@ -375,6 +512,8 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
                                               float* dp_unit, float* dn_unit, void* workspace,
                                               int64_t workspace_bytes, recguru_stream_t stream) {
   using namespace rg;
+  const bool skip_masked = kind >= 0 && (kind & RECGURU_LOSS_SKIP_MASKED) && mask != nullptr;
+  if (kind >= 0) kind &= ~RECGURU_LOSS_SKIP_MASKED;
   int rc = check_common("sampled_score_loss_fwd", V1, d, n_pos, K);
   if (rc) return rc;
   RG_REQUIRE(h && weight && pos && neg, RECGURU_E_SHAPE, "sampled_score_loss_fwd: null pointer");
@@ -395,7 +534,7 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
 #define RG_LAUNCH_SCORE(V)                                                                     \
   sampled_score_fwd_kernel<V><<<static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st>>>(     \
       h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, \
-      part)
+      part, skip_masked)
   switch (d / 4) {
     case 8: RG_LAUNCH_SCORE(8); break;
     case 16: RG_LAUNCH_SCORE(16); break;
@@ -463,5 +602,35 @@ extern "C" int recguru_sampled_score_bwd_dh(const float* dp, const float* dn, co
   }
 #undef RG_LAUNCH_DH
   RG_CHECK_LAUNCH("sampled_score_bwd_dh");
+  return RECGURU_OK;
+}
+
+extern "C" int recguru_candidate_scores_rank(const float* u, const float* weight, int64_t V1, int64_t d,
+                                             const int64_t* target, const int64_t* cand, int64_t B,
+                                             int64_t C, float* scores, int64_t* rank,
+                                             recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(u && weight && target && cand && rank, RECGURU_E_SHAPE, "candidate_scores_rank: null pointer");
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31) && B >= 0 && C >= 1 && C < (1ll << 30), RECGURU_E_SHAPE,
+             "candidate_scores_rank: bad sizes");
+  RG_REQUIRE(d == 32 || d == 64 || d == 128 || d == 256, RECGURU_E_UNSUPPORTED,
+             "candidate_scores_rank: d=%lld not in {32,64,128,256}", (long long)d);
+  RG_REQUIRE(aligned16(u) && aligned16(weight), RECGURU_E_SHAPE,
+             "candidate_scores_rank: u/weight must be 16-byte aligned");
+  if (B == 0) return RECGURU_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float4* u4 = reinterpret_cast<const float4*>(u);
+  const float4* w4 = reinterpret_cast<const float4*>(weight);
+#define RG_LAUNCH_CAND(V)                                                                         \
+  candidate_rank_kernel<V><<<static_cast<unsigned>(B), kScoreWarps * 32, 0, st>>>(                \
+      u4, w4, target, cand, static_cast<int>(C), scores, rank)
+  switch (d / 4) {
+    case 8: RG_LAUNCH_CAND(8); break;
+    case 16: RG_LAUNCH_CAND(16); break;
+    case 32: RG_LAUNCH_CAND(32); break;
+    default: RG_LAUNCH_CAND(64); break;
+  }
+#undef RG_LAUNCH_CAND
+  RG_CHECK_LAUNCH("candidate_rank");
   return RECGURU_OK;
 }

@@ -27,12 +27,14 @@ class TrainHotPath:
     """SASRec / AutoRec BPR step edges (MyRec.forward, AutoEnc4Rec.py:98-133 + BPRLoss_sas)."""
 
     def __init__(self, weight: Tensor, pe: Tensor, B: int, L: int, K: int, kind: str = "bpr_sas",
-                 pad_index: int = 0, padding_idx: Optional[int] = 0):
+                 pad_index: int = 0, padding_idx: Optional[int] = 0, skip_masked: bool = True,
+                 overlap_plan: bool = True):
         assert weight.is_cuda and weight.dtype == torch.float32
         self.weight = weight
         self.pe = pe[0] if pe.dim() == 3 else pe
         self.B, self.L, self.K, self.kind = B, L, K, kind
         self.pad_index = pad_index
+        self.skip_masked = skip_masked
         self.padding_idx = -1 if padding_idx is None else padding_idx
         V1, d = weight.shape
         self.V1, self.d = V1, d
@@ -52,6 +54,12 @@ class TrainHotPath:
         total = n * (2 + K)
         self.ws_bwd = torch.empty(ops.embedding_bwd_workspace_bytes(total, V1, d), dtype=torch.uint8, device=dev)
         self.one = torch.ones(1, **f32)
+        # side stream for the part of the table backward that does not depend on activations
+        self.overlap_plan = overlap_plan
+        self._side = torch.cuda.Stream(device=dev)
+        self._fork = torch.cuda.Event()
+        self._join = torch.cuda.Event()
+        self._planned = False
 
     # -- edge 1: ids -> activations ------------------------------------------------------
     def forward_in(self, dec_in: Tensor) -> Tensor:
@@ -61,8 +69,29 @@ class TrainHotPath:
     # -- edge 2: hidden states -> loss ---------------------------------------------------
     def forward_loss(self, h: Tensor, dec_out: Tensor, n_items: Tensor, mask: Optional[Tensor] = None) -> Tensor:
         m = self.mask if mask is None else mask
-        ops.raw_sampled_score_loss(h, self.weight, dec_out, n_items, m, self.kind, bufs=self.sbuf)
+        # the loss is all this edge exports: positions under the pad mask are not scored
+        ops.raw_sampled_score_loss(h, self.weight, dec_out, n_items, m, self.kind, bufs=self.sbuf,
+                                   skip_masked=self.skip_masked)
         return self.sbuf["aux"][0]
+
+    # -- table-backward plan: depends on the ids and the pad mask only -----------------------
+    def plan_backward(self, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, mask: Optional[Tensor] = None):
+        """Issue stage A of the table backward (zero fill of dW, compaction of the live lookups,
+        stable radix sort) on a side stream.  It needs nothing but the ids and the pad mask, so it
+        runs UNDER the forward pass (in a full model: under the whole transformer forward/backward)
+        instead of on the critical path; :meth:`backward` joins it."""
+        n = self.B * self.L
+        m = (self.mask if mask is None else mask).view(n)
+        cur = torch.cuda.current_stream()
+        self._fork.record(cur)
+        self._side.wait_event(self._fork)
+        with torch.cuda.stream(self._side):
+            ops.raw_fill_zero(self.dW)
+            sites = [Site(dec_in, None, live=m), Site(dec_out, None, live=m),
+                     Site(n_items, None, group=self.K, live=m)]
+            ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
+            self._join.record(self._side)
+        self._planned = True
 
     # -- backward of both edges ------------------------------------------------------------
     def backward(self, h: Tensor, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, g_x0: Tensor,
@@ -74,21 +103,48 @@ class TrainHotPath:
                                      scale=go, scale2=inv_m, out=self.dh)
         n = self.B * self.L
         h2 = h.view(n, self.d)
+        m = self.mask.view(n)
         sites = [
-            Site(dec_in, g_x0.view(n, self.d), coef=self.mask.view(n)),                       # input site
-            Site(dec_out, h2, coef=self.sbuf["dp"], scale=go, scale2=inv_m),                   # positives
-            Site(n_items, h2, coef=self.sbuf["dn"].view(-1), scale=go, scale2=inv_m, group=self.K),  # negatives
+            Site(dec_in, g_x0.view(n, self.d), coef=m, live=m),                                       # input site
+            Site(dec_out, h2, coef=self.sbuf["dp"], scale=go, scale2=inv_m, live=m),                   # positives
+            Site(n_items, h2, coef=self.sbuf["dn"].view(-1), scale=go, scale2=inv_m, group=self.K, live=m),  # negatives
         ]
-        ops.raw_embedding_bwd(sites, self.V1, self.d, self.padding_idx, out=self.dW, zero_fill=True,
-                              workspace=self.ws_bwd)
+        if self._planned:
+            torch.cuda.current_stream().wait_event(self._join)
+            ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
+            self._planned = False
+        else:
+            ops.raw_embedding_bwd(sites, self.V1, self.d, self.padding_idx, out=self.dW, zero_fill=True,
+                                  workspace=self.ws_bwd)
         return self.dh, self.dW
 
     def step(self, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, h: Tensor, g_x0: Tensor):
         """All edges of one step with the transformer replaced by given (h, g_x0)."""
         self.forward_in(dec_in)
+        if self.overlap_plan:
+            self.plan_backward(dec_in, dec_out, n_items)
         loss = self.forward_loss(h, dec_out, n_items)
         dh, dW = self.backward(h, dec_in, dec_out, n_items, g_x0)
         return loss, dh, dW
+
+    def capture_step(self, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, h: Tensor, g_x0: Tensor,
+                     warmup: int = 2) -> torch.cuda.CUDAGraph:
+        """Record :meth:`step` on these (static) input buffers into a CUDA graph.  The step is a
+        chain of ~17 short kernels (4-90 us each); replaying it as one graph removes the per-launch
+        host cost and the inter-kernel gaps.  Every entry point on the path is capture-safe: no
+        allocation, no synchronisation, the live-index count of the table backward stays on the
+        device.  Refill the input buffers in place, then ``graph.replay()``; results land in
+        ``sbuf['aux'][0]`` (loss), ``dh`` and ``dW``."""
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            for _ in range(warmup):
+                self.step(dec_in, dec_out, n_items, h, g_x0)
+        torch.cuda.current_stream().wait_stream(warm)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(dec_in, dec_out, n_items, h, g_x0)
+        return graph
 
     # algorithmic bytes per step (SURVEY.md section 8d), for roofline accounting
     def algorithmic_bytes(self, distinct_rows: Optional[int] = None, live: Optional[int] = None,
@@ -102,7 +158,9 @@ class TrainHotPath:
         live = total if live is None else live
         b = {
             "gather_pe_mask": n * (8 + 4 * d + 4 * d + 4),
-            "sampled_score_loss_fwd": n * (4 * d + (1 + K) * (8 + 4 * d) + 4 + 4 * (1 + K)),
+            # per position: mask + logits + derivatives; per SCORED position: h row, ids, table rows
+            "sampled_score_loss_fwd": n * (4 + 2 * 4 * (1 + K))
+            + (n if (live_pos is None or not self.skip_masked) else live_pos) * (4 * d + (1 + K) * (8 + 4 * d)),
             # positions whose coefficients are all zero (masked) need no table rows for dh
             "sampled_score_bwd_dh": n * ((1 + K) * (8 + 4) + 4 * d)
             + (n if live_pos is None else live_pos) * (1 + K) * 4 * d,

@@ -103,16 +103,54 @@ def raw_pe_mask(x: Tensor, pe: Tensor, mask: Tensor, out: Optional[Tensor] = Non
 
 
 class Site:
-    """One lookup site of the table backward: dW[ids[j]] += coef[j]*scale*scale2 * X[j//group]."""
-    __slots__ = ("ids", "X", "coef", "scale", "scale2", "group")
+    """One lookup site of the table backward: dW[ids[j]] += coef[j]*scale*scale2 * X[j//group].
+    ``live`` (optional, one entry per row of X, e.g. the pad mask) decides which occurrences
+    carry gradient when the plan is made before the coefficients exist."""
+    __slots__ = ("ids", "X", "coef", "scale", "scale2", "group", "live")
 
-    def __init__(self, ids: Tensor, X: Tensor, coef: Optional[Tensor] = None,
-                 scale: Optional[Tensor] = None, scale2: Optional[Tensor] = None, group: int = 1):
+    def __init__(self, ids: Tensor, X: Optional[Tensor], coef: Optional[Tensor] = None,
+                 scale: Optional[Tensor] = None, scale2: Optional[Tensor] = None, group: int = 1,
+                 live: Optional[Tensor] = None):
         self.ids, self.X, self.coef, self.scale, self.scale2, self.group = ids, X, coef, scale, scale2, group
+        self.live = live
+
+
+DW_ACCUMULATE, DW_ZERO_FILL, DW_PREZEROED = 0, 1, 2
 
 
 def embedding_bwd_workspace_bytes(total: int, V1: int, d: int) -> int:
     return int(_lib.load().recguru_embedding_bwd_workspace_bytes(total, V1, d))
+
+
+def _marshal_sites(sites: Sequence[Site], d: Optional[int]):
+    """-> (ctypes array, tensors kept alive, total count).  ``d=None``: plan only, X not needed."""
+    if not 1 <= len(sites) <= _lib.MAX_SITES:
+        raise RuntimeError(f"recguru: 1..{_lib.MAX_SITES} sites supported, got {len(sites)}")
+    arr = (LookupSite * len(sites))()
+    keep = []
+    total = 0
+    for i, s in enumerate(sites):
+        ids = _need(s.ids, torch.int64, "site.ids")
+        n = ids.numel()
+        if n % s.group:
+            raise RuntimeError(f"recguru: site {i}: {n} ids is not a multiple of group {s.group}")
+        X = None
+        if d is not None:
+            X = _need(s.X, torch.float32, "site.X")
+            if X.numel() != (n // s.group) * d:
+                raise RuntimeError(f"recguru: site {i}: ids {n}, group {s.group}, X {tuple(X.shape)}, d {d}")
+        coef = None if s.coef is None else _need(s.coef, torch.float32, "site.coef")
+        scale = None if s.scale is None else _need(s.scale, torch.float32, "site.scale")
+        scale2 = None if s.scale2 is None else _need(s.scale2, torch.float32, "site.scale2")
+        live = None if s.live is None else _need(s.live, torch.float32, "site.live")
+        if coef is not None and coef.numel() != n:
+            raise RuntimeError(f"recguru: site {i}: coef must have one entry per id")
+        if live is not None and live.numel() != n // s.group:
+            raise RuntimeError(f"recguru: site {i}: live must have one entry per row of X")
+        keep += [ids, X, coef, scale, scale2, live]
+        arr[i] = LookupSite(_ptr(ids), n, _ptr(X), _ptr(coef), _ptr(scale), _ptr(scale2), s.group, _ptr(live))
+        total += n
+    return arr, keep, total
 
 
 def raw_embedding_bwd(sites: Sequence[Site], V1: int, d: int, padding_idx: int = -1,
@@ -124,26 +162,8 @@ def raw_embedding_bwd(sites: Sequence[Site], V1: int, d: int, padding_idx: int =
     (train_auto.py:124).  ``padding_idx=-1`` means none (cross-domain tables,
     AutoEnc4Rec_cross.py:32,:35)."""
     lib = _lib.load()
-    if not 1 <= len(sites) <= _lib.MAX_SITES:
-        raise RuntimeError(f"recguru: 1..{_lib.MAX_SITES} sites supported, got {len(sites)}")
-    arr = (LookupSite * len(sites))()
-    keep = []
-    total = 0
+    arr, keep, total = _marshal_sites(sites, d)
     dev = sites[0].X.device
-    for i, s in enumerate(sites):
-        ids = _need(s.ids, torch.int64, "site.ids")
-        X = _need(s.X, torch.float32, "site.X")
-        coef = None if s.coef is None else _need(s.coef, torch.float32, "site.coef")
-        scale = None if s.scale is None else _need(s.scale, torch.float32, "site.scale")
-        scale2 = None if s.scale2 is None else _need(s.scale2, torch.float32, "site.scale2")
-        n = ids.numel()
-        if n % s.group or X.numel() != (n // s.group) * d:
-            raise RuntimeError(f"recguru: site {i}: ids {n}, group {s.group}, X {tuple(X.shape)}, d {d}")
-        if coef is not None and coef.numel() != n:
-            raise RuntimeError(f"recguru: site {i}: coef must have one entry per id")
-        keep += [ids, X, coef, scale, scale2]
-        arr[i] = LookupSite(_ptr(ids), n, _ptr(X), _ptr(coef), _ptr(scale), _ptr(scale2), s.group)
-        total += n
     if out is None:
         out = torch.empty(V1, d, dtype=torch.float32, device=dev)
     else:
@@ -154,9 +174,38 @@ def raw_embedding_bwd(sites: Sequence[Site], V1: int, d: int, padding_idx: int =
     if workspace is None or workspace.numel() < need:
         workspace = _workspace(need, dev)
     check(lib.recguru_embedding_bwd(arr, len(sites), d, V1, int(padding_idx), _ptr(out),
-                                    1 if zero_fill else 0, _ptr(workspace), workspace.numel(),
-                                    _stream()), "embedding_bwd")
+                                    DW_ZERO_FILL if zero_fill else DW_ACCUMULATE, _ptr(workspace),
+                                    workspace.numel(), _stream()), "embedding_bwd")
     return out
+
+
+def raw_embedding_bwd_plan(sites: Sequence[Site], V1: int, padding_idx: int, workspace: Tensor) -> None:
+    """Stage A (compaction + stable sort) on the current stream; needs ids and live/coef only."""
+    lib = _lib.load()
+    arr, keep, total = _marshal_sites(sites, None)
+    workspace = _need(workspace, torch.uint8, "workspace")
+    check(lib.recguru_embedding_bwd_plan(arr, len(sites), V1, int(padding_idx), _ptr(workspace),
+                                         workspace.numel(), _stream()), "embedding_bwd_plan")
+
+
+def raw_embedding_bwd_apply(sites: Sequence[Site], V1: int, d: int, out: Tensor, workspace: Tensor,
+                            mode: int = DW_ZERO_FILL) -> Tensor:
+    """Stage B (segmented reduce) over the plan left in ``workspace`` for the same ids."""
+    lib = _lib.load()
+    arr, keep, total = _marshal_sites(sites, d)
+    out = _need(out, torch.float32, "out")
+    if tuple(out.shape) != (V1, d):
+        raise RuntimeError("recguru: out must be [V1, d]")
+    workspace = _need(workspace, torch.uint8, "workspace")
+    check(lib.recguru_embedding_bwd_apply(arr, len(sites), d, V1, _ptr(out), int(mode), _ptr(workspace),
+                                          workspace.numel(), _stream()), "embedding_bwd_apply")
+    return out
+
+
+def raw_fill_zero(x: Tensor) -> Tensor:
+    x = _need(x, torch.float32, "x")
+    check(_lib.load().recguru_fill_zero(_ptr(x), x.numel(), _stream()), "fill_zero")
+    return x
 
 
 def raw_sort_ids(ids: Tensor, V1: int) -> Tuple[Tensor, Tensor]:
@@ -174,8 +223,10 @@ def raw_sort_ids(ids: Tensor, V1: int) -> Tuple[Tensor, Tensor]:
 
 def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
                            mask: Optional[Tensor], kind: Optional[str], want_grads: bool = True,
-                           bufs: Optional[dict] = None):
+                           bufs: Optional[dict] = None, skip_masked: bool = False):
     """p = h.W[pos], n = h.W[neg]; loss per tools/lossfunctions.py:36-49,:56-72,:79-96.
+    ``skip_masked``: do not score positions with mask == 0 (loss and derivatives unchanged, the
+    logits of those positions are reported as 0 instead of the values nobody consumes).
 
     Returns (p [..,1], n [..,K], loss_aux [2] or None, dp_unit, dn_unit).  loss_aux[0] is the
     loss, loss_aux[1] = 1/sum(mask)."""
@@ -200,6 +251,8 @@ def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
     p = b.get("p") if "p" in b else torch.empty(*pos.shape, 1, dtype=torch.float32, device=dev)
     n = b.get("n") if "n" in b else torch.empty(*pos.shape, K, dtype=torch.float32, device=dev)
     kind_i = -1 if kind is None else LOSS_KINDS[kind]
+    if skip_masked and kind is not None and mask is not None:
+        kind_i |= _lib.LOSS_SKIP_MASKED
     aux = dp = dn = ws = None
     if kind is not None:
         aux = b.get("aux") if "aux" in b else torch.empty(2, dtype=torch.float32, device=dev)
@@ -257,6 +310,27 @@ def raw_sampled_score_bwd_dh(dp: Tensor, dn: Tensor, weight: Tensor, pos: Tensor
                                            V1, d, _ptr(pos), _ptr(neg), n_pos, K, _ptr(out), _stream()),
           "sampled_score_bwd_dh")
     return out
+
+
+def raw_candidate_scores_rank(u: Tensor, weight: Tensor, target: Tensor, cand: Tensor,
+                              want_scores: bool = True):
+    """get_scores + rank-of-column-0 (train_auto.py:164-199,:234-237) in one kernel.
+    u [B,d] fp32, target [B], cand [B,C] int64 -> (scores [B,C+1] or None, rank [B] int64)."""
+    lib = _lib.load()
+    u = _need(u, torch.float32, "u")
+    weight = _need(weight, torch.float32, "weight")
+    target = _need(target, torch.int64, "target")
+    cand = _need(cand, torch.int64, "n_items")
+    B, d = u.shape
+    V1 = weight.shape[0]
+    if weight.shape[1] != d or target.numel() != B or cand.numel() % max(B, 1):
+        raise RuntimeError("recguru: candidate_scores_rank shape mismatch")
+    Cn = cand.numel() // max(B, 1)
+    scores = torch.empty(B, Cn + 1, dtype=torch.float32, device=u.device) if want_scores else None
+    rank = torch.empty(B, dtype=torch.int64, device=u.device)
+    check(lib.recguru_candidate_scores_rank(_ptr(u), _ptr(weight), V1, d, _ptr(target), _ptr(cand), B, Cn,
+                                            _ptr(scores), _ptr(rank), _stream()), "candidate_scores_rank")
+    return scores, rank
 
 
 def raw_cast_bf16(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
@@ -373,6 +447,7 @@ _lib_def.define("sampled_score_loss(Tensor h, Tensor weight, Tensor pos, Tensor 
                 " -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
 _lib_def.define("sampled_score_bwd(Tensor dp, Tensor dn, Tensor? scale, Tensor? scale2, Tensor h, Tensor weight,"
                 " Tensor pos, Tensor neg, int padding_idx) -> (Tensor, Tensor)")
+_lib_def.define("candidate_scores_rank(Tensor u, Tensor weight, Tensor target, Tensor cand) -> (Tensor, Tensor)")
 _lib_def.define("cast_bf16(Tensor x) -> Tensor")
 _lib_def.define("catalog_topk_rank(Tensor users, Tensor items_bf16, Tensor target, int k, int id_lo)"
                 " -> (Tensor, Tensor, Tensor)")
@@ -450,6 +525,11 @@ def _sampled_score_bwd(dp, dn, scale, scale2, h, weight, pos, neg, padding_idx):
     dW = raw_embedding_bwd([Site(pos, h2, dp, scale, scale2, 1), Site(neg, h2, dn, scale, scale2, K)],
                            V1, d, padding_idx)
     return dh, dW
+
+
+@_impl("candidate_scores_rank")
+def _candidate_scores_rank(u, weight, target, cand):
+    return raw_candidate_scores_rank(u, weight, target, cand, True)
 
 
 @_impl("cast_bf16")
@@ -535,6 +615,12 @@ def _(h, weight, pos, neg, mask, kind, padding_idx):
 @_fake("sampled_score_bwd")
 def _(dp, dn, scale, scale2, h, weight, pos, neg, padding_idx):
     return torch.empty_like(h), torch.empty_like(weight)
+
+
+@_fake("candidate_scores_rank")
+def _(u, weight, target, cand):
+    B = u.shape[0]
+    return u.new_empty(B, cand.numel() // max(B, 1) + 1), target.new_empty(B)
 
 
 @_fake("cast_bf16")

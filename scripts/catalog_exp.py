@@ -39,9 +39,6 @@ def run(n_items, label, **env):
 
 
 n_items = 1_000_000
-run(n_items, "BN=256 full", RECGURU_CATALOG_DEBUG=512)
-run(n_items, "BN=128 full", RECGURU_CATALOG_BN=128)
-run(n_items, "BN=256 idle epilogue", RECGURU_CATALOG_DEBUG=2)
-run(n_items, "BN=256 no compute", RECGURU_CATALOG_DEBUG=1)
-run(4_000_000, "BN=256 4M")
-run(4_000_000, "BN=128 4M", RECGURU_CATALOG_BN=128)
+run(n_items, "idle epilogue (MMA+TMA+rings)", RECGURU_CATALOG_DEBUG=2 + 512)
+run(n_items, "idle epilogue, no TMA", RECGURU_CATALOG_DEBUG=2 + 4 + 512)
+run(n_items, "idle epilogue, no TMA, no smem ring", RECGURU_CATALOG_DEBUG=2 + 4 + 32 + 512)

@@ -5,10 +5,10 @@ timeout 300 python bench.py --steps 20 --warmup 5 --only train,gather --skip-cpu
 python - <<'PY'
 import json
 j=json.load(open("gpurun_out/bt.json"))
-print("train seqs/s", round(j["value"]), "ms/step", round(j["ms_per_step"],4), "e2e", round(j["e2e"]["value"]), "launches", j["gpu_launches"])
+print("train seqs/s", round(j["value"]), "ms/step", round(j["ms_per_step"],4), "eager", round(j.get("ms_per_step_eager",0),4), "e2e ms", round(j["e2e"]["ms_per_step"],4), "e2e", round(j["e2e"]["value"]), "launches", j["gpu_launches"])
 for k,v in j["stages"].items(): print(" ", k, v)
 PY
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_train.csv python bench.py --steps 3 --warmup 3 --only train --skip-cpu > /dev/null 2>&1
+timeout 300 ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_train.csv python bench.py --steps 3 --warmup 3 --only train --skip-cpu --no-graph > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
 lines=[l for l in open('gpurun_out/launches_train.csv') if not l.startswith('==')]

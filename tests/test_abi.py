@@ -45,7 +45,7 @@ def test_ctypes_table_matches_header(built_lib):
     assert lib.recguru_abi_version() == _lib.ABI_VERSION
     assert lib.recguru_last_error() == b""
     assert _lib.launch_count() == 0
-    assert ctypes.sizeof(_lib.LookupSite) == 56
+    assert ctypes.sizeof(_lib.LookupSite) == 64      # 8 fields of 8 bytes (recguru_lookup_site_t)
 
 
 def test_argument_validation_without_gpu(built_lib):
