@@ -42,6 +42,24 @@ USERS_PER_STEP = 148 * 4 * 128          # 4 full waves of 128-user tiles on 148 
 # ----------------------------------------------------------------------------------------------
 # plumbing
 # ----------------------------------------------------------------------------------------------
+def ncu_traffic(*kernel_prefixes):
+    """DRAM bytes per launch (read + write) of the named kernels, summed, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json, written by scripts/ncu_summary.py)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    try:
+        tab = json.load(open(path))
+    except (OSError, ValueError):
+        return None
+    total, found = 0.0, 0
+    for pre in kernel_prefixes:
+        for name, rec in tab.items():
+            if name.startswith(pre):
+                total += rec["dram_bytes_per_launch"]
+                found += 1
+                break
+    return int(total) if found == len(kernel_prefixes) else None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -185,9 +203,12 @@ def bench_train(D: Dist, args, peaks):
     hp = TrainHotPath(W, pe, cfg["B"], cfg["L"], cfg["K"], cfg["kind"])
     K, Wm = args.steps, args.warmup
 
-    # ---- device-resident timing with per-stage events ----
-    n_ev = 5
+    # ---- per-stage durations: the step's kernels launched one after another on ONE stream,
+    # CUDA events between the stages (no overlap here: these are kernel times, not the schedule)
+    from recguru_b200 import ops
+    n_ev = 6
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(K)]
+    n = cfg["B"] * cfg["L"]
 
     def step(i):
         b = batches[i % n_batches]
@@ -198,34 +219,44 @@ def bench_train(D: Dist, args, peaks):
         if rec: rec[1].record()
         hp.forward_loss(b["h"], tb.dec_out, tb.n_items)
         if rec: rec[2].record()
-        from recguru_b200 import ops
         ops.raw_sampled_score_bwd_dh(hp.sbuf["dp"], hp.sbuf["dn"], hp.weight, tb.dec_out, tb.n_items,
                                      scale=hp.one, scale2=hp.sbuf["aux"][1:2], out=hp.dh)
         if rec: rec[3].record()
-        n = cfg["B"] * cfg["L"]
-        h2 = b["h"].view(n, cfg["d"])
-        sites = [ops.Site(tb.dec_in, b["g"].view(n, cfg["d"]), coef=hp.mask.view(n)),
-                 ops.Site(tb.dec_out, h2, coef=hp.sbuf["dp"], scale=hp.one, scale2=hp.sbuf["aux"][1:2]),
-                 ops.Site(tb.n_items, h2, coef=hp.sbuf["dn"].view(-1), scale=hp.one,
-                          scale2=hp.sbuf["aux"][1:2], group=cfg["K"])]
-        ops.raw_embedding_bwd(sites, hp.V1, hp.d, 0, out=hp.dW, zero_fill=True, workspace=hp.ws_bwd)
+        m = hp.mask.view(n)
+        ops.raw_fill_zero(hp.dW)
+        ops.raw_embedding_bwd_plan([ops.Site(tb.dec_in, None, live=m), ops.Site(tb.dec_out, None, live=m),
+                                    ops.Site(tb.n_items, None, group=cfg["K"], live=m)], hp.V1, 0, hp.ws_bwd)
         if rec: rec[4].record()
+        h2 = b["h"].view(n, cfg["d"])
+        sites = [ops.Site(tb.dec_in, b["g"].view(n, cfg["d"]), coef=m, live=m),
+                 ops.Site(tb.dec_out, h2, coef=hp.sbuf["dp"], scale=hp.one, scale2=hp.sbuf["aux"][1:2], live=m),
+                 ops.Site(tb.n_items, h2, coef=hp.sbuf["dn"].view(-1), scale=hp.one,
+                          scale2=hp.sbuf["aux"][1:2], group=cfg["K"], live=m)]
+        ops.raw_embedding_bwd_apply(sites, hp.V1, hp.d, hp.dW, hp.ws_bwd, mode=ops.DW_PREZEROED)
+        if rec: rec[5].record()
 
-    # per-stage breakdown: eager launches with events between the stages
     l0 = _lib.launch_count()
-    ms_eager = timed_loop(D, step, K, Wm)
+    ms_serial = timed_loop(D, step, K, Wm)
     launches = (_lib.launch_count() - l0) * K // (K + Wm)
-    # the timed number: the same step (same kernels, same buffers) replayed as one CUDA graph
-    # per rotating batch -- the way a launch-bound chain of short kernels is meant to be driven
+    # ---- the timed number: TrainHotPath.step -- same kernels, same buffers, the table-backward
+    # plan forked onto a side stream under the scoring kernels -- replayed as one CUDA graph per
+    # rotating batch (the way a launch-bound chain of short kernels is meant to be driven);
+    # eager launches of the same step are timed beside it
+    ms_eager = timed_loop(D, lambda i: hp.step(batches[i % n_batches]["tb"].dec_in, batches[i % n_batches]["tb"].dec_out,
+                                               batches[i % n_batches]["tb"].n_items, batches[i % n_batches]["h"],
+                                               batches[i % n_batches]["g"]), K, Wm)
     if args.no_graph:
         with ClockSampler(torch.cuda.current_device()) as cs:
-            ms = timed_loop(D, step, K, Wm)
+            ms = timed_loop(D, lambda i: hp.step(batches[i % n_batches]["tb"].dec_in, batches[i % n_batches]["tb"].dec_out,
+                                                 batches[i % n_batches]["tb"].n_items, batches[i % n_batches]["h"],
+                                                 batches[i % n_batches]["g"]), K, Wm)
     else:
         graphs = [hp.capture_step(b["tb"].dec_in, b["tb"].dec_out, b["tb"].n_items, b["h"], b["g"])
                   for b in batches]
         with ClockSampler(torch.cuda.current_device()) as cs:
             ms = timed_loop(D, lambda i: graphs[i % n_batches].replay(), K, Wm)
-    stage_names = ["gather_pe_mask", "sampled_score_loss_fwd", "sampled_score_bwd_dh", "embedding_bwd"]
+    stage_names = ["gather_pe_mask", "sampled_score_loss_fwd", "sampled_score_bwd_dh", "embedding_bwd_plan",
+                   "embedding_bwd_apply"]
     stage_ms = {nme: sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)) / K
                 for j, nme in enumerate(stage_names)}
     # distinct touched rows (for the algorithmic bytes of the table backward)
@@ -241,9 +272,24 @@ def bench_train(D: Dist, args, peaks):
                     "gbs": round(abytes[nme] / 1e6 / stage_ms[nme], 1),
                     "frac_of_hbm_peak": round(abytes[nme] / 1e6 / stage_ms[nme] / peaks["hbm"], 3)}
               for nme in stage_names}
-    dom = max(stage_names, key=lambda s: stage_ms[s])
+    stages["embedding_bwd_plan"]["schedule"] = ("off the critical path: forked onto a side stream after "
+                                                "gather_pe_mask, runs under the two scoring kernels")
+    # roofline: the longest stage ON the critical path of the timed schedule
+    critical = [s_ for s_ in stage_names if s_ != "embedding_bwd_plan"]
+    dom = max(critical, key=lambda s_: stage_ms[s_])
+    stage_kernels = {"gather_pe_mask": ("gather_pe_mask_kernel",), "sampled_score_loss_fwd": ("sampled_score_fwd",),
+                     "sampled_score_bwd_dh": ("sampled_score_bwd_dh",),
+                     "embedding_bwd_apply": ("chunk_reduce_kernel", "span_fixup_kernel")}
     roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
-            "frac": stages[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["src"]}
+            "frac": stages[dom]["frac_of_hbm_peak"], "traffic": ncu_traffic(*stage_kernels[dom]),
+            "traffic_source": "profiles/r01_traffic.json (ncu --set full, DRAM read+write per launch)",
+            "peak_source": peaks["src"],
+            "whole_step": {"algorithmic_mb": round(abytes["total"] / 1e6, 1),
+                           "gbs": round(abytes["total"] / 1e6 / (ms / K), 1),
+                           "frac": round(abytes["total"] / 1e6 / (ms / K) / peaks["hbm"], 3)},
+            "note": "longest stage on the critical path of the timed schedule; stage durations are measured "
+                    "with the kernels serialised on one stream; whole_step = all algorithmic bytes of a step "
+                    "over the timed step"}
 
     # ---- end to end through the public API with host buffers ----
     # A prefetching loader: the ids of step i+1 are copied (pinned host -> device, side stream)
@@ -290,27 +336,40 @@ def bench_train(D: Dist, args, peaks):
     for slot in range(2):                       # valid ids in the static buffers while capturing
         for k in d_in[slot]:
             d_in[slot][k].copy_(pin[slot][k])
-    e2e_graphs = None if (args.no_graph or not args.e2e_graph) else [
-        hp.capture_step(d_in[b % 2]["dec_in"], d_in[b % 2]["dec_out"], d_in[b % 2]["n_items"],
-                        batches[b]["h"], batches[b]["g"]) for b in range(n_batches)]
-    ms_e2e = timed_loop(D, e2e_step, K, Wm)
+    # both launch modes are timed (K steps each): eager TrainHotPath.step, and the same step replayed
+    # as a CUDA graph; the headline e2e is the faster one and says which it was
+    e2e_graphs = None
+    ms_e2e_eager = timed_loop(D, e2e_step, K, Wm)
+    ms_e2e_graph = None
+    if not args.no_graph:
+        state["primed"] = -1
+        torch.cuda.synchronize()
+        for ev in consumed:
+            ev.record()
+        e2e_graphs = [hp.capture_step(d_in[b % 2]["dec_in"], d_in[b % 2]["dec_out"], d_in[b % 2]["n_items"],
+                                      batches[b]["h"], batches[b]["g"]) for b in range(n_batches)]
+        ms_e2e_graph = timed_loop(D, e2e_step, K, Wm)
+    ms_e2e = ms_e2e_eager if ms_e2e_graph is None else min(ms_e2e_eager, ms_e2e_graph)
+    e2e_mode = "eager (TrainHotPath.step)" if ms_e2e == ms_e2e_eager else "cuda_graph (TrainHotPath.capture_step)"
     h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
     seqs = cfg["B"] * D.world
     out = {
         "value": seqs * K / (ms / 1e3), "ms_per_step": ms / K, "stages": stages, "roofline": roof,
         "e2e": {"value": seqs * K / (ms_e2e / 1e3), "unit": "seqs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
-                "launch_mode": "cuda_graph" if e2e_graphs is not None else "eager (TrainHotPath.step)",
+                "launch_mode": e2e_mode, "ms_per_step_eager": ms_e2e_eager / K,
+                "ms_per_step_graph": None if ms_e2e_graph is None else ms_e2e_graph / K,
                 "note": "ids from pinned host memory each step, loss read back each step; h and the "
                         "gradient w.r.t. the input activations come from the (out-of-scope) transformer "
                         "and are device resident"},
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
         "launch_mode": "eager" if args.no_graph else "cuda_graph (one graph per rotating batch)",
-        "ms_per_step_eager": ms_eager / K,
+        "ms_per_step_eager": ms_eager / K, "ms_per_step_serialised_stages": ms_serial / K,
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
         "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,
                            "distinct_rows": distinct,
-                           "algorithmic_mb_if_all_live": round(abytes_dense["embedding_bwd"] / 1e6, 1),
+                           "algorithmic_mb_if_all_live": round((abytes_dense["embedding_bwd_plan"]
+                                                                 + abytes_dense["embedding_bwd_apply"]) / 1e6, 1),
                            "note": "dead indices (pad id or zero coefficient under the pad mask) are compacted "
                                    "away before the sort; roofline numerator counts only their 12 B id+coef"},
     }
@@ -405,7 +464,9 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
     tflops = flops / (t_kernel * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "catalog_sweep_kernel", "achieved": round(tflops, 1),
             "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": round(tflops / peaks["tf_sust"], 3),
-            "frac_of_burst_peak": round(tflops / peaks["tf_burst"], 3), "traffic": None,
+            "frac_of_burst_peak": round(tflops / peaks["tf_burst"], 3),
+            # DRAM bytes of one sweep launch from the committed ncu capture (cfg4 shape only)
+            "traffic": ncu_traffic("catalog_sweep_kernel") if name == "cfg4" and D.world == 1 else None,
             "peak_source": peaks["src"] + " (sustained bf16 cuBLAS)"}
 
     # end to end: fp32 user reps + targets from pinned host memory, ranks read back
@@ -520,9 +581,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "catalog"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--e2e-graph", action="store_true",
-                    help="replay CUDA graphs in the e2e loop too (measured slower than eager launches there: after "
-                         "the per-step host sync a graph launch starts later than the first eager kernel)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--only", default="", help="comma list of sections: train,gather,cfg4,cfg5")
     args = ap.parse_args()
@@ -587,7 +645,8 @@ def main():
                     "gpu_launches": train["gpu_launches"], "clocks": train["clocks"],
                     "algorithmic_mb_per_step": train["algorithmic_mb_per_step"],
                     "table_backward": train["table_backward"], "launch_mode": train["launch_mode"],
-                    "ms_per_step_eager": train["ms_per_step_eager"]}
+                    "ms_per_step_eager": train["ms_per_step_eager"],
+                    "ms_per_step_serialised_stages": train["ms_per_step_serialised_stages"]}
             if gather is not None:
                 line["gather"] = gather
             line["catalog"] = cat

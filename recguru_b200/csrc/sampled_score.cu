@@ -80,15 +80,45 @@ __device__ __forceinline__ float position_loss(int kind, float* row, int K) {
   return l;
 }
 
-constexpr int kFwdPosPerWarp = 16;
-constexpr int kFwdPosPerBlock = kScoreWarps * kFwdPosPerWarp;   // 256
-constexpr int kRowPad = 33;                                     // 1+K <= 32 scores, +1 against bank conflicts
+constexpr int kRowPad = 33;   // 1+K <= 32 scores, +1 against bank conflicts
+constexpr int kDensePW = 16;  // positions per warp (measured best of 8/16/32)
 
-// One warp owns 16 consecutive positions (measured best of 8/16/32: more warps shorten the serial
-// chain of dependent row gathers, fewer lanes are idle in phase 2 than with 8).  Phase 1 (per position, whole warp): gather the 1+K
-// table rows, dot them with h (8 rows in flight, butterfly reduction), park the scores in shared
-// memory.  Phase 2 (lane = position): loss and derivatives with lane-parallel transcendental
-// math, all outputs written coalesced.
+// Dot products + butterfly reduction of one (position, 8-row step) work item; the lane that
+// ends up with row c's sum stores it to dst[c].
+template <int VEC>
+__device__ __forceinline__ void score_item(const float4 (&hv)[(VEC + 31) / 32],
+                                           const float4 (&w)[VEC < 32 ? 8 * VEC / 32 : 8][(VEC + 31) / 32],
+                                           int c0, int C, int g, int sub, float* dst) {
+  constexpr int LANES = VEC < 32 ? VEC : 32;
+  constexpr int G = 32 / LANES;
+  constexpr int VPL = VEC / LANES;
+  constexpr int UN = 8 / G;
+  float acc[UN];
+#pragma unroll
+  for (int u = 0; u < UN; ++u) {
+    float a = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      a = fmaf(hv[v].x, w[u][v].x, a);
+      a = fmaf(hv[v].y, w[u][v].y, a);
+      a = fmaf(hv[v].z, w[u][v].z, a);
+      a = fmaf(hv[v].w, w[u][v].w, a);
+    }
+    acc[u] = a;
+  }
+  const float r = group_multi_reduce<LANES, UN>(acc, sub);
+  constexpr int kRep = LANES / UN;          // lanes holding the same row's sum
+  const int c = c0 + (sub / kRep) * G + g;  // row (candidate) this lane ended up with
+  if (sub % kRep == 0 && c < C) dst[c] = r;
+}
+
+// Scores + loss, every position scored.  One warp owns 16 consecutive positions.
+// Phase 1 (per position, whole warp): gather the 1+K table rows (8 rows in flight; sub-warp
+// groups when a row is narrower than 512 B), dot with h, reduce all partial sums at once with a
+// multi-value butterfly, park the scores in shared memory.  Phase 2 (lane = position): loss and
+// derivatives with lane-parallel transcendental math, every output written coalesced;
+// fixed-order warp -> CTA reduction of the loss.  40 registers, 6 CTAs/SM: the bandwidth-bound
+// case wants occupancy.
 template <int VEC>  // float4 per row
 __global__ void __launch_bounds__(kScoreWarps * 32)
 sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ weight,
@@ -96,107 +126,39 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
                          int64_t n_pos, int K, const float* __restrict__ mask, int kind,
                          float* __restrict__ p_out, float* __restrict__ n_out,
                          float* __restrict__ dp_unit, float* __restrict__ dn_unit,
-                         float2* __restrict__ block_partial, bool skip_masked) {
+                         float2* __restrict__ block_partial) {
   constexpr int LANES = VEC < 32 ? VEC : 32;  // lanes cooperating on one row
   constexpr int G = 32 / LANES;               // row groups per warp step
   constexpr int VPL = VEC / LANES;            // float4 per lane per row
   constexpr int UN = 8 / G;                   // rows per group per step: 8 rows in flight per warp
-  __shared__ float s_sc[kScoreWarps][kFwdPosPerWarp][kRowPad];
-  __shared__ int s_id[kScoreWarps][kFwdPosPerWarp][32];
+  constexpr int PW = kDensePW;
+  __shared__ float s_sc[kScoreWarps][PW][kRowPad];
   __shared__ float2 s_part[kScoreWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / LANES, sub = lane % LANES;
   const int C = K + 1;
-  const int64_t base = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kFwdPosPerWarp;
-  const int n_here = static_cast<int>(rg::min64(kFwdPosPerWarp, n_pos - base));  // may be <= 0
+  const int64_t base = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * PW;
+  const int n_here = static_cast<int>(rg::min64(PW, n_pos - base));  // may be <= 0
 
-  // Positions this warp scores.  RECGURU_LOSS_SKIP_MASKED: positions under the pad mask are not
-  // scored (their loss term and derivatives are multiplied by 0 anyway); logits reported as 0.
-  uint32_t live_bits = n_here > 0 ? (0xffffffffu >> (32 - n_here)) : 0u;
-  if (skip_masked) live_bits &= __ballot_sync(0xffffffffu, lane < n_here && __ldg(mask + base + lane) != 0.f);
-  // ids of the scored positions, staged once, coalesced, narrowed to int32; zero scores for the rest
-  {
-    int (*ids)[32] = s_id[warp];
-    if (lane < n_here && ((live_bits >> lane) & 1u)) ids[lane][0] = static_cast<int>(pos[base + lane]);
-    const int tot = max(n_here, 0) * K;
-    for (int idx = lane; idx < tot; idx += 32) {
-      const int q = idx / K, k = idx - q * K;
-      if ((live_bits >> q) & 1u) ids[q][1 + k] = static_cast<int>(neg[base * K + idx]);
-    }
-    for (int q = 0; q < n_here; ++q)
-      if (!((live_bits >> q) & 1u) && lane < C) s_sc[warp][q][lane] = 0.f;
-  }
-  __syncwarp();
-
-  // ---- phase 1: a stream of (position, 8-row step) work items, software pipelined ----------
-  // The loads of item i+1 (the h row and up to 8 table rows) are issued before the dot products
-  // and the butterfly reduction of item i, so a warp always has one gather in flight.
-  uint32_t rem = live_bits;
-  int cq = -1, cc = 0;
-  auto advance = [&](int& q, int& c0) -> bool {
-    if (cq >= 0 && cc + 8 < C) {
-      cc += 8;
-    } else {
-      if (!rem) return false;
-      cq = __ffs(rem) - 1;
-      rem &= rem - 1;
-      cc = 0;
-    }
-    q = cq; c0 = cc;
-    return true;
-  };
-  auto issue = [&](int q, int c0, float4 (&hv)[VPL], float4 (&w)[UN][VPL]) {
+  for (int q = 0; q < n_here; ++q) {
     const int64_t i = base + q;
+    int64_t my_id = 0;
+    if (lane == 0) my_id = pos[i];
+    else if (lane <= K) my_id = neg[i * K + (lane - 1)];
+    float4 hv[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) hv[v] = ld_stream_f4(h + i * VEC + v * LANES + sub);
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float4 w[UN][VPL];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int c = c0 + u * G + g;
-      const int64_t id = s_id[warp][q][c < C ? c : 0];
+      for (int u = 0; u < UN; ++u) {
+        const int c = c0 + u * G + g;
+        const int64_t id = __shfl_sync(0xffffffffu, my_id, c < C ? c : 0);
 #pragma unroll
-      for (int v = 0; v < VPL; ++v)
-        w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto finish = [&](int q, int c0, const float4 (&hv)[VPL], const float4 (&w)[UN][VPL]) {
-    float acc[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      float a = 0.f;
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        a = fmaf(hv[v].x, w[u][v].x, a);
-        a = fmaf(hv[v].y, w[u][v].y, a);
-        a = fmaf(hv[v].z, w[u][v].z, a);
-        a = fmaf(hv[v].w, w[u][v].w, a);
+        for (int v = 0; v < VPL; ++v)
+          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      acc[u] = a;
-    }
-    const float r = group_multi_reduce<LANES, UN>(acc, sub);
-    constexpr int kRep = LANES / UN;          // lanes holding the same row's sum
-    const int c = c0 + (sub / kRep) * G + g;  // row (candidate) this lane ended up with
-    if (sub % kRep == 0 && c < C) s_sc[warp][q][c] = r;
-  };
-  if constexpr (VPL == 1) {
-    float4 hA[VPL], wA[UN][VPL], hB[VPL], wB[UN][VPL];
-    int qa = 0, ca = 0, qb = 0, cb = 0;
-    bool more = advance(qa, ca);
-    if (more) issue(qa, ca, hA, wA);
-    while (more) {
-      const bool b = advance(qb, cb);
-      if (b) issue(qb, cb, hB, wB);
-      finish(qa, ca, hA, wA);
-      if (!b) break;
-      more = advance(qa, ca);
-      if (more) issue(qa, ca, hA, wA);
-      finish(qb, cb, hB, wB);
-    }
-  } else {   // 1 KB rows: the register file holds one work item per warp
-    float4 hA[VPL], wA[UN][VPL];
-    int qa = 0, ca = 0;
-    while (advance(qa, ca)) {
-      issue(qa, ca, hA, wA);
-      finish(qa, ca, hA, wA);
+      score_item<VEC>(hv, w, c0, C, g, sub, s_sc[warp][q]);
     }
   }
   __syncwarp();
@@ -204,7 +166,7 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
   // ---- phase 2: lane <-> position ------------------------------------------------------
   const int64_t i = base + lane;
   const bool ok = lane < n_here;
-  float* row = s_sc[warp][lane];
+  float* row = s_sc[warp][lane < PW ? lane : 0];
   if (p_out && ok) p_out[i] = row[0];
   if (n_out) {
     const int tot = max(n_here, 0) * K;
@@ -246,6 +208,149 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
       block_partial[blockIdx.x] = t;
     }
   }
+}
+
+// Padding-aware variant (RECGURU_LOSS_SKIP_MASKED): positions under the pad mask are not scored.
+// On a padded batch (cfg2's Amazon-shaped one: 7 % of the positions are live, in runs of ~15 at
+// the tail of each sequence) the dense kernel's layout leaves the live work in a few warps, each
+// with a serial chain of dependent gathers.  Here one persistent 1024-thread CTA per SM owns a
+// contiguous range of positions and walks it in chunks:
+//   phase 0  thread = position: read the mask, stable compaction of the live positions into a
+//            CTA work list (ballot + warp-count scan), zeros written for the dead positions'
+//            logits/derivatives (coalesced), ids of the live ones staged as int32;
+//   phase 1  the 32 warps drain the work list round-robin: item = (live position, 8-row step),
+//            whole warp per item as in the dense kernel -- every SM has ~100 items for 32 warps;
+//   phase 2  thread = live position: loss + derivatives, outputs scattered to their positions.
+// Loss partials are reduced in a fixed order (lane tree, warps, chunks) => bit-reproducible.
+constexpr int kSparseThreads = 1024;
+template <int VEC>
+__global__ void __launch_bounds__(kSparseThreads, 1)
+sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __restrict__ weight,
+                                const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+                                int64_t n_pos, int K, const float* __restrict__ mask, int kind,
+                                float* __restrict__ p_out, float* __restrict__ n_out,
+                                float* __restrict__ dp_unit, float* __restrict__ dn_unit,
+                                float2* __restrict__ block_partial, int chunk, int64_t pos_per_cta) {
+  constexpr int LANES = VEC < 32 ? VEC : 32;
+  constexpr int G = 32 / LANES;
+  constexpr int VPL = VEC / LANES;
+  constexpr int UN = 8 / G;
+  constexpr int kWarps = kSparseThreads / 32;
+  extern __shared__ float s_dyn[];
+  const int C = K + 1;
+  const int RS = C | 1;                                       // odd row stride: no bank conflicts
+  float* s_sc = s_dyn;                                        // [chunk][RS] scores of the live list
+  int* s_id = reinterpret_cast<int*>(s_sc + chunk * RS);      // [chunk][RS] ids of the live list
+  int* s_rank = s_id + chunk * RS;                            // [chunk] position -> list slot, -1 = dead
+  int* s_list = s_rank + chunk;                               // [chunk] list slot -> position
+  __shared__ int s_wcnt[kWarps];
+  __shared__ float2 s_part[kWarps];
+  __shared__ int s_nlive;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane / LANES, sub = lane % LANES;
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.x) * pos_per_cta;
+  const int64_t r_end = rg::min64(n_pos, r_begin + pos_per_cta);
+  float tot_l = 0.f, tot_m = 0.f;                             // thread 0: running CTA partial
+
+  for (int64_t cb = r_begin; cb < r_end; cb += chunk) {
+    const int n_c = static_cast<int>(rg::min64(chunk, r_end - cb));
+    // ---- phase 0: compaction of the live positions (stable: list order = position order) ----
+    int my_slot = -1;
+    {
+      // chunk <= 1024 = one position per thread
+      const bool live = tid < n_c && __ldg(mask + cb + tid) != 0.f;
+      const uint32_t bal = __ballot_sync(0xffffffffu, live);
+      if (lane == 0) s_wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const int c = s_wcnt[w];
+        before += w < warp ? c : 0;
+        total += c;
+      }
+      if (tid == 0) s_nlive = total;
+      if (live) {
+        my_slot = before + __popc(bal & ((1u << lane) - 1u));
+        s_list[my_slot] = tid;
+        s_id[my_slot * RS] = static_cast<int>(pos[cb + tid]);
+      }
+      if (tid < n_c) {
+        s_rank[tid] = my_slot;
+        if (!live) {
+          if (p_out) p_out[cb + tid] = 0.f;
+          if (dp_unit && kind >= 0) dp_unit[cb + tid] = 0.f;
+        }
+      }
+      __syncthreads();
+      // negatives: coalesced sweep over the chunk's [n_c, K] id block
+      const int tot = n_c * K;
+      for (int idx = tid; idx < tot; idx += kSparseThreads) {
+        const int q = idx / K, k = idx - q * K;
+        const int slot = s_rank[q];
+        if (slot >= 0) {
+          s_id[slot * RS + 1 + k] = static_cast<int>(neg[cb * K + idx]);
+        } else {
+          if (n_out) n_out[cb * K + idx] = 0.f;
+          if (dn_unit && kind >= 0) dn_unit[cb * K + idx] = 0.f;
+        }
+      }
+      __syncthreads();
+    }
+    const int n_live = s_nlive;
+    // ---- phase 1: warps drain the work list ------------------------------------------------
+    const int steps = (C + 7) >> 3;
+    const int n_items = n_live * steps;
+    for (int t = warp; t < n_items; t += kWarps) {
+      const int slot = t / steps;
+      const int c0 = (t - slot * steps) << 3;
+      const int64_t i = cb + s_list[slot];
+      float4 hv[VPL];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) hv[v] = ld_stream_f4(h + i * VEC + v * LANES + sub);
+      float4 w[UN][VPL];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int c = c0 + u * G + g;
+        const int64_t id = s_id[slot * RS + (c < C ? c : 0)];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      score_item<VEC>(hv, w, c0, C, g, sub, s_sc + slot * RS);
+    }
+    __syncthreads();
+    // ---- phase 2: thread = live position ---------------------------------------------------
+    float lm = 0.f, m = 0.f;
+    if (tid < n_live) {
+      float* row = s_sc + tid * RS;
+      const int64_t i = cb + s_list[tid];
+      if (p_out) p_out[i] = row[0];
+      if (n_out)
+        for (int k = 0; k < K; ++k) n_out[i * K + k] = row[1 + k];
+      if (kind >= 0) {
+        m = __ldg(mask + i);
+        lm = position_loss(kind, row, K) * m;
+        if (dp_unit) dp_unit[i] = row[0] * m;
+        if (dn_unit)
+          for (int k = 0; k < K; ++k) dn_unit[i * K + k] = row[1 + k] * m;
+      }
+    }
+    if (kind >= 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lm += __shfl_xor_sync(0xffffffffu, lm, o);
+        m += __shfl_xor_sync(0xffffffffu, m, o);
+      }
+      if (lane == 0) s_part[warp] = make_float2(lm, m);
+    }
+    __syncthreads();                                // s_part complete; s_sc/s_id/s_list reusable
+    if (kind >= 0 && tid == 0) {
+#pragma unroll 1
+      for (int w = 0; w < kWarps; ++w) { tot_l += s_part[w].x; tot_m += s_part[w].y; }
+    }
+  }
+  if (kind >= 0 && tid == 0) block_partial[blockIdx.x] = make_float2(tot_l, tot_m);
 }
 
 // Loss from already computed logits: one thread per position.
@@ -349,13 +454,26 @@ sampled_score_bwd_dh_kernel(const float* __restrict__ dp, const float* __restric
   const int C = K + 1;
   float s = scale ? __ldg(scale) : 1.f;
   if (scale2) s *= __ldg(scale2);
+  // ids and coefficients of all the warp's positions first: one load latency instead of four
+  const int64_t base = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kPosPerWarp;
+  int64_t ids_q[kPosPerWarp];
+  float c_q[kPosPerWarp];
+#pragma unroll
   for (int q = 0; q < kPosPerWarp; ++q) {
-    const int64_t i = (static_cast<int64_t>(blockIdx.x) * kScoreWarps + warp) * kPosPerWarp + q;
+    const int64_t i = base + q;
+    ids_q[q] = 0;
+    c_q[q] = 0.f;
+    if (i < n_pos) {
+      if (lane == 0) { ids_q[q] = pos[i]; c_q[q] = dp[i]; }
+      else if (lane <= K) { ids_q[q] = neg[i * K + (lane - 1)]; c_q[q] = dn[i * K + (lane - 1)]; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kPosPerWarp; ++q) {
+    const int64_t i = base + q;
     if (i >= n_pos) break;
-    int64_t my_id = 0;
-    float my_c = 0.f;
-    if (lane == 0) { my_id = pos[i]; my_c = dp[i] * s; }
-    else if (lane <= K) { my_id = neg[i * K + (lane - 1)]; my_c = dn[i * K + (lane - 1)] * s; }
+    const int64_t my_id = ids_q[q];
+    const float my_c = c_q[q] * s;
     float4 acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -522,7 +640,16 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
   RG_REQUIRE(kind <= RECGURU_LOSS_SCE, RECGURU_E_UNSUPPORTED, "sampled_score_loss_fwd: kind=%d", kind);
   RG_REQUIRE(kind < 0 || loss_out, RECGURU_E_SHAPE, "sampled_score_loss_fwd: loss_out is null");
   if (n_pos == 0) return RECGURU_OK;
-  const int64_t blocks = ceil_div(n_pos, kFwdPosPerBlock);
+  // dense: one CTA per 128 positions; padding-aware: one persistent CTA per SM
+  const int RS = static_cast<int>(K + 1) | 1;
+  const int chunk = RS <= 13 ? 1024 : 512;                   // 2 * chunk * RS * 4 B of shared memory
+  int64_t blocks = ceil_div(n_pos, kScoreWarps * kDensePW);
+  int64_t pos_per_cta = 0;
+  if (skip_masked) {
+    blocks = rg::min64(kNumSMs, ceil_div(n_pos, chunk));
+    pos_per_cta = align_up(ceil_div(n_pos, blocks), 32);
+    blocks = ceil_div(n_pos, pos_per_cta);
+  }
   if (kind >= 0)
     RG_REQUIRE(workspace && workspace_bytes >= blocks * 8, RECGURU_E_WORKSPACE,
                "sampled_score_loss_fwd: workspace %lld < %lld", (long long)workspace_bytes,
@@ -531,10 +658,24 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
   float2* part = static_cast<float2*>(workspace);
   const float4* h4 = reinterpret_cast<const float4*>(h);
   const float4* w4 = reinterpret_cast<const float4*>(weight);
-#define RG_LAUNCH_SCORE(V)                                                                     \
-  sampled_score_fwd_kernel<V><<<static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st>>>(     \
-      h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, \
-      part, skip_masked)
+  const size_t sparse_smem = static_cast<size_t>(chunk) * (2 * RS + 2) * 4;
+#define RG_LAUNCH_SCORE(V)                                                                       \
+  do {                                                                                           \
+    if (skip_masked) {                                                                           \
+      static bool attr_set = false;                                                              \
+      if (!attr_set) {                                                                           \
+        cudaFuncSetAttribute(sampled_score_fwd_sparse_kernel<V>,                                 \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);           \
+        attr_set = true;                                                                         \
+      }                                                                                          \
+      sampled_score_fwd_sparse_kernel<V><<<static_cast<unsigned>(blocks), kSparseThreads, sparse_smem, st>>>( \
+          h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
+          chunk, pos_per_cta);                                                                   \
+    } else {                                                                                     \
+      sampled_score_fwd_kernel<V><<<static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st>>>(   \
+          h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part);    \
+    }                                                                                            \
+  } while (0)
   switch (d / 4) {
     case 8: RG_LAUNCH_SCORE(8); break;
     case 16: RG_LAUNCH_SCORE(16); break;

@@ -164,8 +164,10 @@ class TrainHotPath:
             # positions whose coefficients are all zero (masked) need no table rows for dh
             "sampled_score_bwd_dh": n * ((1 + K) * (8 + 4) + 4 * d)
             + (n if live_pos is None else live_pos) * (1 + K) * 4 * d,
-            "embedding_bwd": total * (8 + 4) + live * 4 * d + 4 * V1 * d
-            + (4 * d * distinct_rows if distinct_rows is not None else 0),
+            # plan: id + liveness/coefficient of every gathered index, dense zero fill of dW
+            "embedding_bwd_plan": total * (8 + 4) + 4 * V1 * d,
+            # apply: one source row per live index, one dW row per distinct id
+            "embedding_bwd_apply": live * 4 * d + (4 * d * distinct_rows if distinct_rows is not None else 0),
         }
         b["total"] = sum(b.values())
         return b

@@ -1,0 +1,48 @@
+"""Summarise .ncu-rep captures (ncu --set full) into text + a traffic table for bench.py.
+usage: python scripts/ncu_summary.py <rep> [<rep> ...] > summary.txt ; writes profiles/r01_traffic.json"""
+import csv
+import io
+import json
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size",
+        "launch__block_size", "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "sm__inst_executed_pipe_tensor.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+traffic = OrderedDict()
+for rep in sys.argv[1:]:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    print(f"# {rep}")
+    agg = OrderedDict()
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("rg::", "")
+        agg.setdefault(name, []).append(r)
+    for name, rs in agg.items():
+        print(f"{name}  (n={len(rs)})")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                vals = [float(r[i].replace(",", "")) for r in rs if r[i] not in ("", "n/a")]
+                if vals:
+                    print(f"    {k:85s} {sum(vals) / len(vals):14.3f} {units[i]}")
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        t = sum(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rs) / len(rs)
+        it = hdr.index("gpu__time_duration.sum")
+        traffic[name] = {"dram_bytes_per_launch": t, "launches_captured": len(rs),
+                         "us_under_ncu": sum(float(r[it].replace(",", "")) for r in rs) / len(rs)
+                         * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[it], 1.0), "source": rep}
+json.dump(traffic, open("profiles/r01_traffic.json", "w"), indent=1)

@@ -207,12 +207,14 @@ def test_sampled_score_loss_vs_oracle(ops, kind, d, K):
     # unmasked mean
     _, _, aux3, _, _ = ops.raw_sampled_score_loss(dev(h), dev(W), dev(pos), dev(neg), None, kind)
     assert torch.allclose(aux3[0].cpu(), O.LOSSES[kind](p_ref, n_ref, None), rtol=1e-5, atol=1e-6)
-    # padding-aware variant (RECGURU_LOSS_SKIP_MASKED): loss and derivatives bit-identical,
+    # padding-aware variant (RECGURU_LOSS_SKIP_MASKED): derivatives bit-identical, loss to 1e-6,
     # logits identical where mask != 0 and reported as 0 under the mask
     p4, n4, aux4, dp4, dn4 = ops.raw_sampled_score_loss(dev(h), dev(W), dev(pos), dev(neg), dev(mask), kind,
                                                         skip_masked=True)
     live = dev(mask) != 0
-    assert torch.equal(aux4, aux) and torch.equal(dp4, dp) and torch.equal(dn4, dn)
+    # (the padding-aware kernel reduces the loss over a different CTA partition: same terms,
+    # different fp32 summation order)
+    assert torch.allclose(aux4, aux, rtol=1e-6, atol=0) and torch.equal(dp4, dp) and torch.equal(dn4, dn)
     assert torch.equal(p4.view(-1)[live], p.view(-1)[live]) and torch.equal(n4.view(-1, K)[live], n.view(-1, K)[live])
     assert float(p4.view(-1)[~live].abs().sum()) == 0.0 and float(n4.view(-1, K)[~live].abs().sum()) == 0.0
 
