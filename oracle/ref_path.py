@@ -200,6 +200,32 @@ def mrr_at_k_batch(r, k):
     return float(mrr) / len(r)
 
 
+# ---- eval driver --- train_auto.py:202-253 (gan_training.py:90-149 is the same loop per domain) --
+def reference_evaluation(user_rep, weight: Tensor, batches, candidate_size: int, k_val=(5, 10, 20, 30)):
+    """The reference loop restated: four get_scores calls per batch (each recomputing the user
+    representation), double argsort, ranks appended to Python lists, metrics by per-user loops.
+    ``user_rep(enc_in, dec_in) -> [B, d]`` stands for ``get_embedding*(...)[:, -1, :]``."""
+    ranks = {"eval_f": [], "eval_r": [], "test_f": [], "test_r": []}
+    for eval_data, test_data, n_items_f, n_items_r in batches:
+        for split, (enc_in, dec_in, target) in (("eval", eval_data), ("test", test_data)):
+            for s, cand in (("f", n_items_f), ("r", n_items_r)):
+                u = user_rep(enc_in, dec_in)
+                score = candidate_scores(u, weight, target.reshape(-1), cand.reshape(-1), candidate_size)
+                ranks[f"{split}_{s}"].extend(rank_of_column0(score.reshape(u.shape[0], -1)).numpy())
+    out = []
+    for s in ("f", "r"):
+        res = {}
+        for k in k_val:
+            res[str(k)] = {}
+            for split in ("eval", "test"):
+                r = ranks[f"{split}_{s}"]
+                res[str(k)][f"ht_{split}"] = [hit_at_k_batch(r, k)]
+                res[str(k)][f"ndcg_{split}"] = [NDCG_at_k_batch(r, k)]
+                res[str(k)][f"mrr_{split}"] = [mrr_at_k_batch(r, k)]
+        out.append(res)
+    return out
+
+
 # ---- data layout helpers --- data/data_loader.py:25-36,:39-55 ---------------------------------
 def seq_padding(seq, length_enc, len_dec, eos):
     """Left-pad with 0, EOS last; dec_in / dec_out are enc_in shifted by two / one."""
