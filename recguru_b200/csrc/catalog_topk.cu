@@ -46,6 +46,12 @@ enum CatalogMode { kModeTopK = 0, kModeDense = 1 };
 
 // debug profile (RECGURU_CATALOG_PROF=1): cycles CTA (0,0) spends in each wait, per role
 __device__ long long g_prof[16];
+// debug flag 65536: per-tile timestamps (clock64, CTA 0) of a window of tiles:
+// [tile][0] MMA warp: accumulator slot seen empty   [1] operands seen full   [2] MMAs + commit issued
+// [tile][3] epilogue: accumulator seen full         [4] epilogue: slot handed back
+// [tile][5] producer: stage seen free               [6] producer: TMA issued
+constexpr int kTraceTiles = 64, kTraceFirst = 2000;
+__device__ long long g_trace[kTraceTiles][8];
 
 struct CatalogParams {
   int64_t U;
@@ -73,18 +79,20 @@ __device__ __forceinline__ float next_below(float t) {
 }
 
 // Shared-memory carve-up (dynamic, base aligned to 1024 for the 128-byte swizzle).
-// Ring depth: 4 stages / accumulators of 128 items, or 2 of 256 (TMEM has 512 columns).
-template <int D, int BN>
+// TMEM holds 512/BN accumulators (4 of 128 items, or 2 of 256); the shared-memory ring of item
+// tiles has NST stages (0 = same depth as the accumulator ring, one commit serves both).
+template <int D, int BN, int NST = 0>
 struct CatSmem {
   static constexpr int kKBlocks = D / 64;                 // 64-wide (128 B) K blocks
-  static constexpr int kRing = 512 / BN;                  // smem stages == TMEM accumulators
+  static constexpr int kRing = 512 / BN;                  // TMEM accumulators
+  static constexpr int kStages = NST > 0 ? NST : kRing;   // smem stages
   static constexpr int kATileBytes = kBlockM * D * 2;     // user tile
   static constexpr int kTileBytes = BN * D * 2;           // one item tile
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kATileBytes;
-  static constexpr int kOffBar = kOffB + kRing * kTileBytes;
-  // barriers: full[4], empty[4], acc_full[4], acc_empty[4], a_full (sized for the deepest ring)
-  static constexpr int kNumBars = 2 * 4 + 2 * 4 + 1;
+  static constexpr int kOffBar = kOffB + kStages * kTileBytes;
+  // barriers: full[8], empty[8], acc_full[8], acc_empty[8], a_full (sized for the deepest ring)
+  static constexpr int kNumBars = 4 * 8 + 1;
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr int kOffCnt = kOffTmemPtr + 8;         // int[nsets][128] (per-set rank counts)
   // then float[nsets*k*128] scores and int[nsets*k*128] ids of the per-thread top-k lists
@@ -99,15 +107,27 @@ struct CatSmem {
 // so every MMA reads only the item tile from shared memory -- in SS mode the 128 x 16 A slice is
 // re-read from smem by each instruction and the N=128 MMA is shared-memory-bandwidth bound.
 // TMEM then holds 3 accumulators (384 columns) + A (64 columns).
-template <int D, int MODE, int NSETS, int CL, bool TS, int BN>
+// NST: stages of the shared-memory item-tile ring.  0 couples it to the accumulator ring (one
+// tcgen05.commit per tile frees the stage and publishes the accumulator).  NST > NACC decouples
+// the two: the TMA for tile j+NST is issued as soon as tile j's MMAs retire, i.e. NST-NACC tiles
+// before the accumulator hand-off that gates its MMAs, so the TMA latency leaves the critical
+// chain commit -> epilogue -> MMA (measured: 35 -> see DESIGN.md).
+// PIPE: software-pipelined epilogue (two 64-column TMEM loads per tile, the second one and the
+// first one of the NEXT tile in flight while the rank count of the previous half runs).
+// DBG: the RECGURU_CATALOG_DEBUG bisection knobs are compiled in only in this variant; the
+// production instantiation carries none of their per-tile branches.
+template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST, bool PIPE, bool DBG>
 __global__ void __launch_bounds__(96 + NSETS * 128, 1)
 catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                      const __grid_constant__ CUtensorMap map_items, CatalogParams p) {
-  using L = CatSmem<D, BN>;
+  const uint32_t dflags = DBG ? p.debug_flags : 0u;
+  using L = CatSmem<D, BN, NST>;
   static_assert(!TS || BN == 128, "TS mode is only wired for 128-item tiles");
-  constexpr int NACC = TS ? 3 : L::kRing;   // accumulator ring == smem stage ring depth
+  constexpr int NACC = TS ? 3 : L::kRing;   // accumulator ring
+  constexpr int NSTG = NST > 0 ? NST : NACC;   // smem stage ring
+  constexpr bool kCoupled = NST == 0 && CL == 1;   // one commit per tile serves both rings
   constexpr uint32_t kTmemA = NACC * BN;    // TMEM column of the A operand (TS mode)
-  constexpr int kBarStride = 4;             // barrier arrays are laid out for the deepest ring
+  constexpr int kBarStride = 8;             // barrier arrays are laid out for the deepest ring
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -133,8 +153,8 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&map_users);
     ptx::tma_prefetch_desc(&map_items);
-    for (int i = 0; i < NACC; ++i) { ptx::mbar_init(&bar_full[i], 1); ptx::mbar_init(&bar_empty[i], CL); }
-    for (int i = 0; i < NACC; ++i) { ptx::mbar_init(&bar_acc_full[i], 1); ptx::mbar_init(&bar_acc_empty[i], (p.debug_flags & 16384u) ? 1 : 4); }
+    for (int i = 0; i < NSTG; ++i) { ptx::mbar_init(&bar_full[i], 1); ptx::mbar_init(&bar_empty[i], CL); }
+    for (int i = 0; i < NACC; ++i) { ptx::mbar_init(&bar_acc_full[i], 1); ptx::mbar_init(&bar_acc_empty[i], (dflags & 16384u) ? 1 : 4); }
     ptx::mbar_init(bar_a, TS ? 4 : 1);
     ptx::mbar_fence_init();
   }
@@ -146,8 +166,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
   constexpr uint16_t kClMask = (1u << CL) - 1u;
-  const bool spin = (p.debug_flags & 256u) != 0;   // debug: busy-poll barriers
-  const bool prof = (p.debug_flags & 512u) != 0 && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool spin = (dflags & 256u) != 0;   // debug: busy-poll barriers
+  const bool prof = (dflags & 512u) != 0 && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool trace = (dflags & 65536u) != 0 && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops; one elected lane issues) ========
@@ -159,17 +180,19 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                          static_cast<int32_t>(m0));
     }
     for (int j = 0; j < n_tiles; ++j) {
-      if (p.debug_flags & 32u) break;                 // debug: no smem-ring handshake at all
-      const int s = j % NACC;
-      const uint32_t ph = (j / NACC) & 1;
+      if (dflags & 32u) break;                 // debug: no smem-ring handshake at all
+      const int s = j % NSTG;
+      const uint32_t ph = (j / NSTG) & 1;
       const long long tp0 = prof ? clock64() : 0;
-      // CL == 1: the stage of tile j-4 is free exactly when that tile's MMAs have retired, which
-      // is what acc_full[j % 4] signals to the epilogue -- one tcgen05.commit per tile serves both
-      // (same ring depth).  CL == 2 needs the peer's MMAs too and keeps a separate barrier.
-      ptx::mbar_wait_warp(CL == 1 ? &bar_acc_full[s] : &bar_empty[s], ph ^ 1, spin);
+      // coupled rings: the stage of tile j-4 is free exactly when that tile's MMAs have retired,
+      // which is what acc_full[j % 4] signals to the epilogue -- one tcgen05.commit per tile serves
+      // both.  Otherwise (deeper smem ring, or a cluster whose peer's MMAs count too) the stage has
+      // its own barrier.
+      ptx::mbar_wait_warp(kCoupled ? &bar_acc_full[s] : &bar_empty[s], ph ^ 1, spin);
       if (prof && lane == 0) g_prof[0] += clock64() - tp0;
+      if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) g_trace[j - kTraceFirst][5] = clock64();
       if (leader) {
-        if ((p.debug_flags & 4u) && j >= NACC) {   // debug: no operand traffic (timing floor)
+        if ((dflags & 4u) && j >= NSTG) {   // debug: no operand traffic (timing floor)
           ptx::mbar_arrive(&bar_full[s]);
         } else {
           ptx::mbar_arrive_expect_tx(&bar_full[s], L::kTileBytes);
@@ -189,6 +212,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         }
       }
       __syncwarp();
+      if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) g_trace[j - kTraceFirst][6] = clock64();
     }
   } else if (warp == 1 || warp == 2) {
     // ===================== MMA issuers (whole warp loops; one elected lane issues) =========
@@ -197,19 +221,19 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     const bool leader = ptx::elect_one();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, BN);
     const uint32_t a_addr = ptx::smem_u32(smem + L::kOffA);
-    const int reps = (p.debug_flags & 16u) ? 0 : ((p.debug_flags & 8u) ? 2 : 1);  // debug knobs
+    const int reps = (dflags & 16u) ? 0 : ((dflags & 8u) ? 2 : 1);  // debug knobs
     ptx::mbar_wait_warp(bar_a, 0);
     ptx::tc_fence_after();
     for (int j = warp - 1; j < n_tiles; j += 2) {
-      const int s = j % NACC;
-      const uint32_t ph = (j / NACC) & 1;
+      const int s = j % NSTG;
+      const uint32_t ph = (j / NSTG) & 1;
       const int a = j % NACC;
       const uint32_t aph = (j / NACC) & 1;
       const long long tm0 = prof ? clock64() : 0;
-      if (!(p.debug_flags & 64u)) ptx::mbar_wait_warp(&bar_acc_empty[a], aph ^ 1, spin);
-      const long long tm1 = prof ? clock64() : 0;
-      if (!(p.debug_flags & 32u)) ptx::mbar_wait_warp(&bar_full[s], ph, spin);
-      const long long tm2 = prof ? clock64() : 0;
+      if (!(dflags & 64u)) ptx::mbar_wait_warp(&bar_acc_empty[a], aph ^ 1, spin);
+      const long long tm1 = (prof || trace) ? clock64() : 0;
+      if (!(dflags & 32u)) ptx::mbar_wait_warp(&bar_full[s], ph, spin);
+      const long long tm2 = (prof || trace) ? clock64() : 0;
       ptx::tc_fence_after();
       if (leader) {
         const uint32_t b_addr = ptx::smem_u32(smem + L::kOffB + s * L::kTileBytes);
@@ -218,7 +242,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           for (int k = 0; k < D / 16; ++k) {
             const uint32_t koff = (k / 4) * (kBlockM * 128) + (k % 4) * 32;   // bytes into the user tile
             const uint32_t koff_b = (k / 4) * (BN * 128) + (k % 4) * 32;      // bytes into the item tile
-            if (p.debug_flags & 1024u)   // debug: N=256 instruction rate (operands/accumulators overlap; timing only)
+            if (dflags & 1024u)   // debug: N=256 instruction rate (operands/accumulators overlap; timing only)
               ptx::umma_bf16(tmem_base + (a & 1) * 256, ptx::umma_smem_desc_sw128(a_addr + koff),
                              ptx::umma_smem_desc_sw128(ptx::smem_u32(smem + L::kOffB) + (k % 4) * 32),
                              ptx::umma_idesc_bf16(kBlockM, 256), (k > 0 || rep > 0) ? 1u : 0u);
@@ -230,15 +254,19 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                              ptx::umma_smem_desc_sw128(b_addr + koff_b), idesc, (k > 0 || rep > 0) ? 1u : 0u);
           }
         }
-        if (!(p.debug_flags & 32u)) {       // smem stage free (in every CTA of the cluster) once these MMAs retire
+        if (!(dflags & 32u)) {       // smem stage free (in every CTA of the cluster) once these MMAs retire
           if (CL > 1) ptx::umma_commit_mcast(&bar_empty[s], kClMask);
+          else if (!kCoupled) ptx::umma_commit(&bar_empty[s]);
         }
-        if (p.debug_flags & 128u) ptx::mbar_arrive(&bar_acc_full[a]);     // debug: plain arrive instead of commit
+        if (dflags & 128u) ptx::mbar_arrive(&bar_acc_full[a]);     // debug: plain arrive instead of commit
         else ptx::umma_commit(&bar_acc_full[a]);  // accumulator ready for the epilogue (and stage free)
       }
       __syncwarp();
       if (prof && lane == 0 && warp == 1) {
         g_prof[1] += tm1 - tm0; g_prof[2] += tm2 - tm1; g_prof[3] += clock64() - tm2; g_prof[4] += 1;
+      }
+      if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) {
+        g_trace[j - kTraceFirst][0] = tm1; g_trace[j - kTraceFirst][1] = tm2; g_trace[j - kTraceFirst][2] = clock64();
       }
     }
   } else {
@@ -302,17 +330,79 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       s_id[pos * kSlots + slot] = id;
       thr = s_val[(K - 1) * kSlots + slot];
     };
+    // ---- pieces of the fast path on one 64-column half held in registers -------------------
+    // (a) 8-column group maxima decide whether the top-k lists must be touched; if some lane's
+    //     threshold was beaten the warp re-reads just those groups from TMEM (the accumulator is
+    //     still ours; warp-uniform loop => convergent .sync.aligned load)
+    auto topk_check64 = [&](const uint32_t (&vr)[64], uint32_t taddr_half, int id0) {
+      float gm[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float* f = reinterpret_cast<const float*>(&vr[g * 8]);
+        gm[g] = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
+      }
+      float mx = gm[0];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) mx = fmaxf(mx, gm[g]);
+      if (__any_sync(0xffffffffu, mx > thr)) {
+        uint32_t gmask = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) gmask |= (gm[g] > thr ? 1u : 0u) << g;
+        uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
+        while (wmask) {
+          const int g = __ffs(wmask) - 1;
+          wmask &= wmask - 1;
+          uint32_t w8[8];
+          ptx::tmem_ld_32x8(taddr_half + g * 8, w8);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float v = __uint_as_float(w8[c]);
+            if (v > thr) insert(v, id0 + g * 8 + c);
+          }
+        }
+      }
+    };
+    // (b) rank count: sign bit of (tcmp - v); two differences per FADD2, sign bits accumulated
+    //     half on the FMA pipe (IMAD.HI by a run-time 2), half on the ALU pipe (LEA.HI)
+    auto rank_count64 = [&](const uint32_t (&vr)[64], uint64_t tt) {
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        uint64_t dd[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint64_t vv;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "r"(vr[c + 2 * q]), "r"(vr[c + 2 * q + 1]));
+          asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dd[q]) : "l"(tt), "l"(vv));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t d0, d1;
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(d0), "=r"(d1) : "l"(dd[q]));
+          if (((c + 2 * q) & 31) < kFmaSignCols) {
+            asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf[q]) : "r"(d0), "r"(two));
+            asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf2[q]) : "r"(d1), "r"(two));
+          } else {
+            ca[q] += d0 >> 31;
+            ca2[q] += d1 >> 31;
+          }
+        }
+      }
+    };
+    uint32_t vrA[PIPE ? 64 : 1], vrB[PIPE ? 64 : 1];   // PIPE: the two halves of a tile's accumulator row
+    bool a_inflight = false;                            // PIPE: this tile's first half was requested last iteration
     for (int j = e; j < n_tiles; j += NSETS) {
-      if ((p.debug_flags & 16384u) && quarter != 0) break;   // debug: one warp per set in the handshake
+      if ((dflags & 16384u) && quarter != 0) break;   // debug: one warp per set in the handshake
       const int a = j % NACC;
       const uint32_t aph = (j / NACC) & 1;
       const int tile = tile_begin + j;
       const int n0 = tile * BN;                                   // slice-local item index
       const int valid = static_cast<int>(rg::min64(BN, p.n_items - n0));
-      if (p.debug_flags & 64u) break;                 // debug: no accumulator handshake at all
+      const bool free_run = (dflags & 32768u) != 0;   // debug: epilogue ignores the accumulator barriers
+      if ((dflags & 64u) && !free_run) break;  // debug: no accumulator handshake at all
       const long long te0 = prof ? clock64() : 0;
-      ptx::mbar_wait_warp(&bar_acc_full[a], aph, spin);
-      const long long te1 = prof ? clock64() : 0;
+      if (!free_run && !a_inflight) ptx::mbar_wait_warp(&bar_acc_full[a], aph, spin);
+      const long long te1 = (prof || trace) ? clock64() : 0;
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + a * BN;
       bool released = false;
@@ -352,6 +442,49 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
             }
           }
         }
+      } else if constexpr (PIPE) {
+        // fast tile, software pipelined.  TMEM reads are slow next to a running tensor core
+        // (a 64 KB tile takes ~1000 cycles) and a warp's rank count another ~900, so neither may
+        // wait for the other:   A(j) ready | request B(j) | top-k + count A | B ready | top-k B |
+        // release accumulator | request A(j+2) if that tile is already full | count B
+        const float tcmp = tile < tgt_tile ? t_below : t;
+        uint64_t tt;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(tt) : "f"(tcmp));
+        if (!a_inflight) ptx::tmem_ld_32x64(taddr, vrA);
+        ptx::tmem_ld_wait_regs(vrA);
+        ptx::tmem_ld_32x64(taddr + 64, vrB);
+        if (!(dflags & 1u)) {
+          topk_check64(vrA, taddr, n0);
+          rank_count64(vrA, tt);
+        } else {
+          ca[0] += vrA[0] ^ vrA[63];                  // debug: TMEM-load-only floor
+        }
+        ptx::tmem_ld_wait_regs(vrB);
+        if (!(dflags & 1u)) topk_check64(vrB, taddr + 64, n0 + 64);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+        released = true;
+        a_inflight = false;
+        const int jn = j + NSETS;
+        if (jn < n_tiles && !free_run) {
+          const int tile_n = tile_begin + jn;
+          const bool fast_n = !__any_sync(0xffffffffu, tile_n == tgt_tile) &&
+                              static_cast<int64_t>(tile_n + 1) * BN <= p.n_items;
+          if (fast_n) {
+            const int an = jn % NACC;
+            int ready = 0;
+            if (lane == 0) ready = ptx::mbar_test(&bar_acc_full[an], (jn / NACC) & 1) ? 1 : 0;
+            ready = __shfl_sync(0xffffffffu, ready, 0);
+            if (ready) {
+              ptx::tc_fence_after();
+              ptx::tmem_ld_32x64(tmem_base + lane_base + an * BN, vrA);
+              a_inflight = true;
+            }
+          }
+        }
+        if (!(dflags & 1u)) rank_count64(vrB, tt);
+        else ca[1] += vrB[0] ^ vrB[63];
       } else {
         // fast tile: d = tcmp - v has its sign bit set iff v > tcmp (exact: IEEE subtraction is
         // zero only for equal operands, tcmp is never -0).  FADD2 forms two differences per
@@ -367,15 +500,18 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         constexpr int CH = NSETS == 2 ? 128 : 64;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
-          if (p.debug_flags & 2u) break;               // debug: no TMEM reads, no compute (timing floor)
+          if (dflags & 2u) break;               // debug: no TMEM reads, no compute (timing floor)
           uint32_t vr[CH];
           ptx::tmem_ld_cols<CH>(taddr + c0, vr);
           ptx::tmem_ld_wait();
-          if (p.debug_flags & 1u) {
+          if (dflags & 1u) {
             ca[0] += vr[0] ^ vr[CH - 1];   // debug: TMEM-load-only floor (results meaningless)
             continue;
           }
-          // (a) 8-column group maxima first: they decide whether the top-k lists must be touched
+          // (a) 8-column group maxima first: they decide whether the top-k lists must be touched.
+          // (A single row maximum + full re-read was measured: 54 vs 32 ms at cfg4 -- with 32 users
+          // per warp SOME lane's threshold is beaten in about every second tile of a 1M-item
+          // sweep, so the re-read must stay confined to the groups that did it.)
           float gm[CH / 8];
 #pragma unroll
           for (int g = 0; g < CH / 8; ++g) {
@@ -386,7 +522,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
 #pragma unroll
           for (int g = 1; g < CH / 8; ++g) mx = fmaxf(mx, gm[g]);
           if (__any_sync(0xffffffffu, mx > thr)) {
-            // rare: some lane's threshold was beaten.  Per-lane bitmask of the 8-column groups
+            // some lane's threshold was beaten.  Per-lane bitmask of the 8-column groups
             // that did it; the warp walks the union and re-reads just those groups from TMEM
             // (the accumulator is still ours; warp-uniform loop => convergent .sync.aligned load)
             uint32_t gmask = 0;
@@ -445,6 +581,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+      }
+      if (trace && lane == 0 && quarter == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) {
+        g_trace[j - kTraceFirst][3] = te1; g_trace[j - kTraceFirst][4] = clock64();
       }
       if (prof && lane == 0 && (warp == 3 || warp == 7)) {
         const int o = warp == 3 ? 5 : 8;
@@ -645,15 +784,20 @@ static int catalog_bn() {
   return bn == 256 ? 256 : 128;
 }
 
-template <int D, int MODE, int NSETS, int CL, bool TS, int BN>
+template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST = 0, bool PIPE = false>
 static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const CatalogParams& p,
                           cudaStream_t st) {
-  const int smem = CatSmem<D, BN>::bytes(MODE == kModeTopK ? p.k : 0, NSETS);
+  const int smem = CatSmem<D, BN, NST>::bytes(MODE == kModeTopK ? p.k : 0, NSETS);
   RG_REQUIRE(smem <= 227 * 1024, RECGURU_E_UNSUPPORTED, "catalog: k=%d needs %d B of shared memory", p.k, smem);
-  auto kern = catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN>;
+  auto kern = p.debug_flags ? catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true>
+                            : catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog: cudaFuncSetAttribute: %s",
                cudaGetErrorString(e));
     attr_set = true;
@@ -676,6 +820,16 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mu, mi, p);
   RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog_sweep: launch failed: %s", cudaGetErrorString(e));
   RG_CHECK_LAUNCH("catalog_sweep");
+  if (p.debug_flags & 65536u) {
+    static long long tr[kTraceTiles][8];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr));
+    const long long t0 = tr[0][2];
+    fprintf(stderr, "[trace cta0] tile: mma_saw_empty mma_saw_full mma_issued | epi_saw_full epi_released | prod_saw_free prod_issued  (cycles rel. to first)\n");
+    for (int i = 0; i < kTraceTiles; ++i)
+      fprintf(stderr, "[trace] %4d: %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld\n", kTraceFirst + i, tr[i][0] - t0,
+              tr[i][1] - t0, tr[i][2] - t0, tr[i][3] - t0, tr[i][4] - t0, tr[i][5] - t0, tr[i][6] - t0);
+  }
   if (p.debug_flags & 512u) {
     long long h[16];
     cudaStreamSynchronize(st);
@@ -714,7 +868,21 @@ static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams 
     if constexpr (D == 128) return launch_sweep_n<D, MODE, 2, 1, true, 128>(mu, mi, p, st);
   }
   if (nsets == 4) return cl == 2 ? launch_sweep_n<D, MODE, 4, 2, false, 128>(mu, mi, p, st) : launch_sweep_n<D, MODE, 4, 1, false, 128>(mu, mi, p, st);
-  return cl == 2 ? launch_sweep_n<D, MODE, 2, 2, false, 128>(mu, mi, p, st) : launch_sweep_n<D, MODE, 2, 1, false, 128>(mu, mi, p, st);
+  if (cl == 2) return launch_sweep_n<D, MODE, 2, 2, false, 128>(mu, mi, p, st);
+  // RECGURU_CATALOG_STAGES=5|6: item-tile ring deeper than (and decoupled from) the accumulator ring
+  int nst = env_int("RECGURU_CATALOG_STAGES", 0);
+  const int k_eff = MODE == kModeTopK ? p.k : 0;
+  if (nst == 0) nst = 4;   // measured: 5 decoupled stages 34.4 ms vs 34.7 coupled (cfg4): within noise
+  // measured slower (41.8 vs 34.5 ms at cfg4): a warp's 64-column TMEM load is rate limited per warp
+  const bool pipe = MODE == kModeTopK && env_int("RECGURU_CATALOG_PIPE", 0) != 0;
+  if (nst == 6 && CatSmem<D, 128, 6>::bytes(k_eff, 2) <= 227 * 1024)
+    return pipe ? launch_sweep_n<D, MODE, 2, 1, false, 128, 6, MODE == kModeTopK>(mu, mi, p, st)
+                : launch_sweep_n<D, MODE, 2, 1, false, 128, 6>(mu, mi, p, st);
+  if (nst >= 5 && CatSmem<D, 128, 5>::bytes(k_eff, 2) <= 227 * 1024)
+    return pipe ? launch_sweep_n<D, MODE, 2, 1, false, 128, 5, MODE == kModeTopK>(mu, mi, p, st)
+                : launch_sweep_n<D, MODE, 2, 1, false, 128, 5>(mu, mi, p, st);
+  return pipe ? launch_sweep_n<D, MODE, 2, 1, false, 128, 0, MODE == kModeTopK>(mu, mi, p, st)
+              : launch_sweep_n<D, MODE, 2, 1, false, 128>(mu, mi, p, st);
 }
 
 static int check_catalog(const char* who, const void* users, int64_t U, const void* items,

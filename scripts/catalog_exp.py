@@ -39,6 +39,6 @@ def run(n_items, label, **env):
 
 
 n_items = 1_000_000
-run(n_items, "idle epilogue (MMA+TMA+rings)", RECGURU_CATALOG_DEBUG=2 + 512)
-run(n_items, "idle epilogue, no TMA", RECGURU_CATALOG_DEBUG=2 + 4 + 512)
-run(n_items, "idle epilogue, no TMA, no smem ring", RECGURU_CATALOG_DEBUG=2 + 4 + 32 + 512)
+run(n_items, "production variant (no debug knobs)")
+run(n_items, "debug variant, no knob active", RECGURU_CATALOG_DEBUG=131072)
+run(10_000_000, "production variant, 10M items")
