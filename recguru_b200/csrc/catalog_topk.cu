@@ -504,6 +504,14 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           uint32_t vr[CH];
           ptx::tmem_ld_cols<CH>(taddr + c0, vr);
           ptx::tmem_ld_wait();
+          // the scores now live in registers only (the top-k re-scan reads registers too): hand
+          // the accumulator back to the MMA warp before any arithmetic
+          if (c0 + CH == BN) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+            released = true;
+          }
           if (dflags & 1u) {
             ca[0] += vr[0] ^ vr[CH - 1];   // debug: TMEM-load-only floor (results meaningless)
             continue;
@@ -516,15 +524,27 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
 #pragma unroll
           for (int g = 0; g < CH / 8; ++g) {
             const float* f = reinterpret_cast<const float*>(&vr[g * 8]);
-            gm[g] = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
+            // four 3-input maxima (FMNMX3) per 8 columns
+            const float m1 = fmaxf(fmaxf(f[0], f[1]), f[2]);
+            const float m2 = fmaxf(fmaxf(f[3], f[4]), f[5]);
+            const float m3 = fmaxf(fmaxf(f[6], f[7]), m1);
+            gm[g] = fmaxf(m2, m3);
           }
-          float mx = gm[0];
+          float mx;
+          {
+            static_assert(CH / 8 == 16 || CH / 8 == 8, "group count");
+            float r[8];
 #pragma unroll
-          for (int g = 1; g < CH / 8; ++g) mx = fmaxf(mx, gm[g]);
+            for (int q = 0; q < 8; ++q) r[q] = CH / 8 == 16 ? fmaxf(gm[q], gm[q + 8]) : gm[q];
+            const float a3 = fmaxf(fmaxf(r[0], r[1]), r[2]);
+            const float b3 = fmaxf(fmaxf(r[3], r[4]), r[5]);
+            mx = fmaxf(fmaxf(r[6], r[7]), fmaxf(a3, b3));
+          }
           if (__any_sync(0xffffffffu, mx > thr)) {
-            // some lane's threshold was beaten.  Per-lane bitmask of the 8-column groups
-            // that did it; the warp walks the union and re-reads just those groups from TMEM
-            // (the accumulator is still ours; warp-uniform loop => convergent .sync.aligned load)
+            // some lane's threshold was beaten.  Per-lane bitmask of the 8-column groups that did
+            // it; the warp walks the union (warp-uniform g) and every lane checks that group's
+            // eight scores, fetched from its registers through a jump table -- no TMEM re-read,
+            // so the accumulator is not held while the lists are updated.
             uint32_t gmask = 0;
 #pragma unroll
             for (int g = 0; g < CH / 8; ++g) gmask |= (gm[g] > thr ? 1u : 0u) << g;
@@ -533,22 +553,27 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
               const int g = __ffs(wmask) - 1;
               wmask &= wmask - 1;
               uint32_t w8[8];
-              ptx::tmem_ld_32x8(taddr + c0 + g * 8, w8);
-              ptx::tmem_ld_wait();
+#define RG_GRP(G) case G: _Pragma("unroll") for (int c = 0; c < 8; ++c) w8[c] = vr[(G) * 8 + c]; break;
+              switch (g) {
+                RG_GRP(0) RG_GRP(1) RG_GRP(2) RG_GRP(3) RG_GRP(4) RG_GRP(5) RG_GRP(6) RG_GRP(7)
+                default:
+                  if constexpr (CH / 8 == 16) {
+                    switch (g) {
+                      RG_GRP(8) RG_GRP(9) RG_GRP(10) RG_GRP(11) RG_GRP(12) RG_GRP(13) RG_GRP(14)
+                      default: _Pragma("unroll") for (int c = 0; c < 8; ++c) w8[c] = vr[(CH / 8 - 1) * 8 + c]; break;
+                    }
+                  } else {
+                    _Pragma("unroll") for (int c = 0; c < 8; ++c) w8[c] = vr[7 * 8 + c];
+                  }
+                  break;
+              }
+#undef RG_GRP
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
                 const float v = __uint_as_float(w8[c]);
                 if (v > thr) insert(v, n0 + c0 + g * 8 + c);
               }
             }
-          }
-          // (b) the scores now live in registers only: hand the accumulator back to the MMA warp
-          // before the (long) rank count
-          if (c0 + CH == BN) {
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
-            released = true;
           }
           // (c) rank count: four differences (two FADD2) ahead of their sign accumulation so the
           // FMA-pipe latency overlaps
