@@ -51,6 +51,9 @@ __device__ long long g_prof[16];
 // [tile][3] epilogue: accumulator seen full         [4] epilogue: slot handed back
 // [tile][5] producer: stage seen free               [6] producer: TMA issued
 constexpr int kTraceTiles = 64, kTraceFirst = 2000;
+// setmaxnreg budget with 12 warps (NSETS == 2): 4*32*kCtlRegs + 8*32*kEpiRegs <= 12*32*168
+constexpr int kCtlRegs = 56, kEpiRegs = 224;
+static_assert(4 * kCtlRegs + 8 * kEpiRegs <= 12 * 168, "register budget");
 __device__ long long g_trace[kTraceTiles][8];
 
 struct CatalogParams {
@@ -117,7 +120,7 @@ struct CatSmem {
 // DBG: the RECGURU_CATALOG_DEBUG bisection knobs are compiled in only in this variant; the
 // production instantiation carries none of their per-tile branches.
 template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST, bool PIPE, bool DBG>
-__global__ void __launch_bounds__(96 + NSETS * 128, 1)
+__global__ void __launch_bounds__(128 + NSETS * 128, 1)
 catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                      const __grid_constant__ CUtensorMap map_items, CatalogParams p) {
   const uint32_t dflags = DBG ? p.debug_flags : 0u;
@@ -170,6 +173,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
   const bool prof = (dflags & 512u) != 0 && blockIdx.x == 0 && blockIdx.y == 0;
   const bool trace = (dflags & 65536u) != 0 && blockIdx.x == 0 && blockIdx.y == 0;
 
+  if constexpr (NSETS == 2) {
+    if (warp < 4) ptx::setmaxnreg_dec<kCtlRegs>();
+  }
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops; one elected lane issues) ========
     const bool leader = ptx::elect_one();
@@ -269,9 +275,16 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         g_trace[j - kTraceFirst][0] = tm1; g_trace[j - kTraceFirst][1] = tm2; g_trace[j - kTraceFirst][2] = clock64();
       }
     }
+  } else if (warp == 3) {
+    // idle: fills the control warpgroup (setmaxnreg acts on aligned groups of four warps)
   } else {
     // ===================== epilogue =====================
-    const int e = (warp - 3) >> 2;            // epilogue set: handles tiles j == e (mod NSETS)
+    // The kernel is compiled for 128 + NSETS*128 threads (168 registers each with two sets); the
+    // control warpgroup gives most of its registers back and the epilogue warpgroups take them,
+    // so the 128-register accumulator row, the sign counters and the group maxima fit without
+    // spilling.
+    if constexpr (NSETS == 2) ptx::setmaxnreg_inc<kEpiRegs>();
+    const int e = (warp - 4) >> 2;            // epilogue set: handles tiles j == e (mod NSETS)
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int64_t u = m0 + row;
@@ -334,16 +347,19 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     // (a) 8-column group maxima decide whether the top-k lists must be touched; if some lane's
     //     threshold was beaten the warp re-reads just those groups from TMEM (the accumulator is
     //     still ours; warp-uniform loop => convergent .sync.aligned load)
-    auto topk_check64 = [&](const uint32_t (&vr)[64], uint32_t taddr_half, int id0) {
+    auto topk_check64 = [&](const uint32_t (&vr)[64], int id0) {
       float gm[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float* f = reinterpret_cast<const float*>(&vr[g * 8]);
-        gm[g] = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
+        const float m1 = fmaxf(fmaxf(f[0], f[1]), f[2]);
+        const float m2 = fmaxf(fmaxf(f[3], f[4]), f[5]);
+        const float m3 = fmaxf(fmaxf(f[6], f[7]), m1);
+        gm[g] = fmaxf(m2, m3);
       }
-      float mx = gm[0];
-#pragma unroll
-      for (int g = 1; g < 8; ++g) mx = fmaxf(mx, gm[g]);
+      const float a3 = fmaxf(fmaxf(gm[0], gm[1]), gm[2]);
+      const float b3 = fmaxf(fmaxf(gm[3], gm[4]), gm[5]);
+      const float mx = fmaxf(fmaxf(gm[6], gm[7]), fmaxf(a3, b3));
       if (__any_sync(0xffffffffu, mx > thr)) {
         uint32_t gmask = 0;
 #pragma unroll
@@ -353,8 +369,12 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           const int g = __ffs(wmask) - 1;
           wmask &= wmask - 1;
           uint32_t w8[8];
-          ptx::tmem_ld_32x8(taddr_half + g * 8, w8);
-          ptx::tmem_ld_wait();
+#define RG_GRP(G) case G: _Pragma("unroll") for (int c = 0; c < 8; ++c) w8[c] = vr[(G) * 8 + c]; break;
+          switch (g) {
+            RG_GRP(0) RG_GRP(1) RG_GRP(2) RG_GRP(3) RG_GRP(4) RG_GRP(5) RG_GRP(6)
+            default: _Pragma("unroll") for (int c = 0; c < 8; ++c) w8[c] = vr[7 * 8 + c]; break;
+          }
+#undef RG_GRP
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float v = __uint_as_float(w8[c]);
@@ -380,11 +400,11 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           uint32_t d0, d1;
           asm("mov.b64 {%0, %1}, %2;" : "=r"(d0), "=r"(d1) : "l"(dd[q]));
           if (((c + 2 * q) & 31) < kFmaSignCols) {
-            asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf[q]) : "r"(d0), "r"(two));
-            asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf2[q]) : "r"(d1), "r"(two));
+            asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf[q & 1]) : "r"(d0), "r"(two));
+            asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf2[q & 1]) : "r"(d1), "r"(two));
           } else {
-            ca[q] += d0 >> 31;
-            ca2[q] += d1 >> 31;
+            ca[q & 1] += d0 >> 31;
+            ca2[q & 1] += d1 >> 31;
           }
         }
       }
@@ -454,13 +474,12 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         ptx::tmem_ld_wait_regs(vrA);
         ptx::tmem_ld_32x64(taddr + 64, vrB);
         if (!(dflags & 1u)) {
-          topk_check64(vrA, taddr, n0);
+          topk_check64(vrA, n0);
           rank_count64(vrA, tt);
         } else {
           ca[0] += vrA[0] ^ vrA[63];                  // debug: TMEM-load-only floor
         }
         ptx::tmem_ld_wait_regs(vrB);
-        if (!(dflags & 1u)) topk_check64(vrB, taddr + 64, n0 + 64);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
@@ -483,8 +502,12 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
             }
           }
         }
-        if (!(dflags & 1u)) rank_count64(vrB, tt);
-        else ca[1] += vrB[0] ^ vrB[63];
+        if (!(dflags & 1u)) {
+          topk_check64(vrB, n0 + 64);
+          rank_count64(vrB, tt);
+        } else {
+          ca[1] += vrB[0] ^ vrB[63];
+        }
       } else {
         // fast tile: d = tcmp - v has its sign bit set iff v > tcmp (exact: IEEE subtraction is
         // zero only for equal operands, tcmp is never -0).  FADD2 forms two differences per
@@ -591,11 +614,11 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
               uint32_t d0, d1;
               asm("mov.b64 {%0, %1}, %2;" : "=r"(d0), "=r"(d1) : "l"(dd[q]));
               if (((c + 2 * q) & 31) < kFmaSignCols) {
-                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf[q]) : "r"(d0), "r"(two));
-                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf2[q]) : "r"(d1), "r"(two));
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf[q & 1]) : "r"(d0), "r"(two));
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(cf2[q & 1]) : "r"(d1), "r"(two));
               } else {
-                ca[q] += d0 >> 31;
-                ca2[q] += d1 >> 31;
+                ca[q & 1] += d0 >> 31;
+                ca2[q & 1] += d1 >> 31;
               }
             }
           }
@@ -610,8 +633,8 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       if (trace && lane == 0 && quarter == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) {
         g_trace[j - kTraceFirst][3] = te1; g_trace[j - kTraceFirst][4] = clock64();
       }
-      if (prof && lane == 0 && (warp == 3 || warp == 7)) {
-        const int o = warp == 3 ? 5 : 8;
+      if (prof && lane == 0 && (warp == 4 || warp == 8)) {
+        const int o = warp == 4 ? 5 : 8;
         g_prof[o] += te1 - te0; g_prof[o + 1] += clock64() - te1; g_prof[o + 2] += 1;
       }
     }
@@ -834,7 +857,7 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
   cudaLaunchConfig_t cfg = {};
   const int64_t m_tiles = ceil_div(p.U, kBlockM);
   cfg.gridDim = dim3(static_cast<unsigned>(ceil_div(m_tiles, CL) * CL), static_cast<unsigned>(p.n_splits));
-  cfg.blockDim = dim3(96 + NSETS * 128);
+  cfg.blockDim = dim3(128 + NSETS * 128);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -263,6 +263,16 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 
+// Warpgroup-wide register re-allocation (all four warps of an aligned warpgroup must execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---- UMMA descriptors ------------------------------------------------------------------
 // K-major operand tile stored as [rows][64 bf16] (128-byte rows) with the 128-byte swizzle,
 // exactly what a TMA box {64, rows} with CU_TENSOR_MAP_SWIZZLE_128B writes:

@@ -39,6 +39,5 @@ def run(n_items, label, **env):
 
 
 n_items = 1_000_000
-run(n_items, "production variant (no debug knobs)")
-run(n_items, "debug variant, no knob active", RECGURU_CATALOG_DEBUG=131072)
-run(10_000_000, "production variant, 10M items")
+run(n_items, "production")
+run(10_000_000, "production, 10M items")
