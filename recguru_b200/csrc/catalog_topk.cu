@@ -119,7 +119,8 @@ struct CatSmem {
 // first one of the NEXT tile in flight while the rank count of the previous half runs).
 // DBG: the RECGURU_CATALOG_DEBUG bisection knobs are compiled in only in this variant; the
 // production instantiation carries none of their per-tile branches.
-template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST, bool PIPE, bool DBG>
+// RL: the per-thread top-k list (k <= 16) lives in registers instead of shared memory.
+template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST, bool PIPE, bool DBG, bool RL>
 __global__ void __launch_bounds__(128 + NSETS * 128, 1)
 catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                      const __grid_constant__ CUtensorMap map_items, CatalogParams p) {
@@ -308,8 +309,18 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
 
     int cnt = 0;
     float thr = -CUDART_INF_F;
-    if (MODE == kModeTopK) {
+    if (MODE == kModeTopK && !RL) {
       for (int i = 0; i < K; ++i) { s_val[i * kSlots + slot] = -CUDART_INF_F; s_id[i * kSlots + slot] = -1; }
+    }
+    // RL: 16 register slots, descending; the k live entries sit at the BOTTOM (slots 16-k .. 15)
+    // and the slots above them are blocked with +inf, so the k-th best -- the insertion
+    // threshold -- is always lv[15] whatever k is, and an insertion is a fully unrolled
+    // compare-exchange chain with no memory access and no data-dependent loop.
+    float lv[RL ? 16 : 1];
+    int li[RL ? 16 : 1];
+    if constexpr (RL) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { lv[i] = i < 16 - K ? CUDART_INF_F : -CUDART_INF_F; li[i] = -1; }
     }
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     if (TS && e == 0) {
@@ -333,6 +344,24 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
 
     // sorted insert into this thread's list (desc score; equal scores keep arrival = id order)
     auto insert = [&](float v, int id) {
+      if constexpr (RL) {
+        bool sw = false;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          // strict: an equal score stays below earlier ones; once the new entry is placed every
+          // later slot just shifts down (a carried entry must not be compared again, or it would
+          // slip below an equal neighbour and break the id order of ties)
+          sw = sw || (v > lv[i]);
+          const float ov = lv[i];
+          const int oi = li[i];
+          lv[i] = sw ? v : ov;
+          li[i] = sw ? id : oi;
+          v = sw ? ov : v;
+          id = sw ? oi : id;
+        }
+        thr = lv[15];
+        return;
+      }
       int pos = K - 1;
       while (pos > 0 && s_val[(pos - 1) * kSlots + slot] < v) {
         s_val[pos * kSlots + slot] = s_val[(pos - 1) * kSlots + slot];
@@ -342,6 +371,33 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       s_val[pos * kSlots + slot] = v;
       s_id[pos * kSlots + slot] = id;
       thr = s_val[(K - 1) * kSlots + slot];
+    };
+    // Offer eight scores (columns id0 .. id0+7, bit c of `ok` = column c is a real item) to the list.
+    auto offer8 = [&](const uint32_t (&w8)[8], int id0, uint32_t ok) {
+      if constexpr (RL) {
+        // one inlined insertion site: lanes queue the columns that beat their threshold and the
+        // warp drains the queues together (usually one lane, one column)
+        uint32_t pend = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pend |= (__uint_as_float(w8[c]) > thr ? 1u : 0u) << c;
+        pend &= ok;
+        while (__any_sync(0xffffffffu, pend != 0u)) {
+          if (pend) {
+            const int c = __ffs(pend) - 1;
+            pend &= pend - 1;
+            float v = __uint_as_float(w8[0]);
+#pragma unroll
+            for (int q = 1; q < 8; ++q) v = (c == q) ? __uint_as_float(w8[q]) : v;
+            if (v > thr) insert(v, id0 + c);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float v = __uint_as_float(w8[c]);
+          if (((ok >> c) & 1u) && v > thr) insert(v, id0 + c);
+        }
+      }
     };
     // ---- pieces of the fast path on one 64-column half held in registers -------------------
     // (a) 8-column group maxima decide whether the top-k lists must be touched; if some lane's
@@ -375,11 +431,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
             default: _Pragma("unroll") for (int c = 0; c < 8; ++c) w8[c] = vr[7 * 8 + c]; break;
           }
 #undef RG_GRP
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float v = __uint_as_float(w8[c]);
-            if (v > thr) insert(v, id0 + g * 8 + c);
-          }
+          offer8(w8, id0 + g * 8, 0xffu);
         }
       }
     };
@@ -458,9 +510,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
               } else {
                 cnt += (v > (tile < tgt_tile ? t_below : t)) ? 1 : 0;
               }
-              if (v > thr) insert(v, n0 + col);
             }
           }
+          offer8(w, n0 + c0, valid - c0 >= 8 ? 0xffu : (valid > c0 ? (1u << (valid - c0)) - 1u : 0u));
         }
       } else if constexpr (PIPE) {
         // fast tile, software pipelined.  TMEM reads are slow next to a running tensor core
@@ -591,11 +643,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
                   break;
               }
 #undef RG_GRP
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float v = __uint_as_float(w8[c]);
-                if (v > thr) insert(v, n0 + c0 + g * 8 + c);
-              }
+              offer8(w8, n0 + c0 + g * 8, 0xffu);
             }
           }
           // (c) rank count: four differences (two FADD2) ahead of their sign accumulation so the
@@ -641,6 +689,15 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     cnt += static_cast<int>(cf[0] + cf[1] + cf[2] + cf[3] + ca[0] + ca[1] + ca[2] + ca[3] + cf2[0] + cf2[1] +
                             cf2[2] + cf2[3] + ca2[0] + ca2[1] + ca2[2] + ca2[3]);
 
+    if constexpr (MODE == kModeTopK && RL) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if (q >= 16 - K) {
+          s_val[(q - (16 - K)) * kSlots + slot] = lv[q];
+          s_id[(q - (16 - K)) * kSlots + slot] = li[q];
+        }
+      }
+    }
     if (MODE == kModeTopK) {
       s_cnt[e * 128 + row] = cnt;
       asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128) : "memory");
@@ -832,19 +889,19 @@ static int catalog_bn() {
   return bn == 256 ? 256 : 128;
 }
 
-template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST = 0, bool PIPE = false>
+template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST = 0, bool PIPE = false, bool RL = false>
 static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const CatalogParams& p,
                           cudaStream_t st) {
   const int smem = CatSmem<D, BN, NST>::bytes(MODE == kModeTopK ? p.k : 0, NSETS);
   RG_REQUIRE(smem <= 227 * 1024, RECGURU_E_UNSUPPORTED, "catalog: k=%d needs %d B of shared memory", p.k, smem);
-  auto kern = p.debug_flags ? catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true>
-                            : catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false>;
+  auto kern = p.debug_flags ? catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true, RL>
+                            : catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false, RL>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true>,
+    cudaError_t e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true, RL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false>,
+      e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false, RL>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog: cudaFuncSetAttribute: %s",
                cudaGetErrorString(e));
@@ -929,8 +986,11 @@ static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams 
   if (nst >= 5 && CatSmem<D, 128, 5>::bytes(k_eff, 2) <= 227 * 1024)
     return pipe ? launch_sweep_n<D, MODE, 2, 1, false, 128, 5, MODE == kModeTopK>(mu, mi, p, st)
                 : launch_sweep_n<D, MODE, 2, 1, false, 128, 5>(mu, mi, p, st);
-  return pipe ? launch_sweep_n<D, MODE, 2, 1, false, 128, 0, MODE == kModeTopK>(mu, mi, p, st)
-              : launch_sweep_n<D, MODE, 2, 1, false, 128>(mu, mi, p, st);
+  if (pipe) return launch_sweep_n<D, MODE, 2, 1, false, 128, 0, MODE == kModeTopK>(mu, mi, p, st);
+  // default: k <= 16 keeps the top-k lists in registers (RECGURU_CATALOG_REGLIST=0: shared memory)
+  if (MODE == kModeTopK && p.k <= 16 && env_int("RECGURU_CATALOG_REGLIST", 1) != 0)
+    return launch_sweep_n<D, MODE, 2, 1, false, 128, 0, false, MODE == kModeTopK>(mu, mi, p, st);
+  return launch_sweep_n<D, MODE, 2, 1, false, 128>(mu, mi, p, st);
 }
 
 static int check_catalog(const char* who, const void* users, int64_t U, const void* items,

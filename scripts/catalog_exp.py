@@ -39,5 +39,6 @@ def run(n_items, label, **env):
 
 
 n_items = 1_000_000
-run(n_items, "production")
-run(10_000_000, "production, 10M items")
+run(n_items, "register top-k lists (default)")
+run(n_items, "shared-memory top-k lists", RECGURU_CATALOG_REGLIST=0)
+run(10_000_000, "register lists, 10M items")
