@@ -466,7 +466,7 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
             "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": round(tflops / peaks["tf_sust"], 3),
             "frac_of_burst_peak": round(tflops / peaks["tf_burst"], 3),
             # DRAM bytes of one sweep launch from the committed ncu capture (cfg4 shape only)
-            "traffic": ncu_traffic("catalog_sweep_kernel") if name == "cfg4" and D.world == 1 else None,
+            "traffic": ncu_traffic("catalog_sweep_kernel") if name.startswith("cfg4") and D.world == 1 else None,
             "peak_source": peaks["src"] + " (sustained bf16 cuBLAS)"}
 
     # end to end: fp32 user reps + targets from pinned host memory, ranks read back

@@ -986,6 +986,7 @@ static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams 
   if (nst >= 5 && CatSmem<D, 128, 5>::bytes(k_eff, 2) <= 227 * 1024)
     return pipe ? launch_sweep_n<D, MODE, 2, 1, false, 128, 5, MODE == kModeTopK>(mu, mi, p, st)
                 : launch_sweep_n<D, MODE, 2, 1, false, 128, 5>(mu, mi, p, st);
+  if (pipe && p.k <= 16) return launch_sweep_n<D, MODE, 2, 1, false, 128, 0, MODE == kModeTopK, MODE == kModeTopK>(mu, mi, p, st);
   if (pipe) return launch_sweep_n<D, MODE, 2, 1, false, 128, 0, MODE == kModeTopK>(mu, mi, p, st);
   // default: k <= 16 keeps the top-k lists in registers (RECGURU_CATALOG_REGLIST=0: shared memory)
   if (MODE == kModeTopK && p.k <= 16 && env_int("RECGURU_CATALOG_REGLIST", 1) != 0)

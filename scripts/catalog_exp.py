@@ -39,6 +39,9 @@ def run(n_items, label, **env):
 
 
 n_items = 1_000_000
-run(n_items, "register top-k lists (default)")
+run(n_items, "default (x128 epilogue, register top-k lists)")
 run(n_items, "shared-memory top-k lists", RECGURU_CATALOG_REGLIST=0)
-run(10_000_000, "register lists, 10M items")
+run(n_items, "pipelined epilogue", RECGURU_CATALOG_PIPE=1)
+run(n_items, "4 epilogue sets", RECGURU_CATALOG_SETS=4)
+run(n_items, "5 decoupled smem stages", RECGURU_CATALOG_STAGES=5)
+run(10_000_000, "default, 10M items")

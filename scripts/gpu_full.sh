@@ -6,6 +6,7 @@ echo "== smoke"; timeout 200 python -c "import __graft_entry__ as g; g.build(); 
 echo "== bench"; timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo rc=$?; tail -2 gpurun_out/bench_full.err
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref.json 2>/dev/null; cat gpurun_out/bench_ref.json | cut -c1-300
 echo "== candidate protocol"; timeout 200 python scripts/candidate_bench.py 2>&1 | tee gpurun_out/candidate_bench.log
+echo "== catalog knobs"; timeout 300 python scripts/catalog_exp.py 2>&1 | tee gpurun_out/catalog_exp_final.log
 echo "== launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 3 --warmup 3 --only train,cfg4 --skip-cpu --no-graph > /dev/null 2>&1; echo rc=$?
 echo "== full captures"
