@@ -60,6 +60,15 @@ def ncu_traffic(*kernel_prefixes):
     return int(total) if found == len(kernel_prefixes) else None
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -131,8 +140,9 @@ class Dist:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             # NCCL prints its version banner on stdout at INFO/VERSION level; the bench line must be
             # the only thing there
-            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-                os.environ["NCCL_DEBUG"] = "WARN"
+            # (any level >= VERSION, WARN included, prints it): keep whatever level the launcher
+            # asked for but send NCCL's log to stderr
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             torch.cuda.set_device(self.local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
@@ -569,7 +579,7 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf,
             "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -585,6 +595,13 @@ def main():
     ap.add_argument("--only", default="", help="comma list of sections: train,gather,cfg4,cfg5")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    # The JSON line must be the only thing on stdout.  Libraries write there too (NCCL prints its
+    # version banner on fd 1 at any NCCL_DEBUG level >= VERSION), so fd 1 is pointed at stderr for
+    # the duration of the run and the line goes to a duplicate of the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():
@@ -661,7 +678,7 @@ def main():
                 line["train"] = {k: train[k] for k in ("value", "ms_per_step", "stages", "e2e")}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if D.dist is not None:
         D.dist.destroy_process_group()
 

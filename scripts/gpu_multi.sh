@@ -9,7 +9,7 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -3 gpurun_out/bench_n$N.err
 python - <<PY
 import json
-j=json.load(open("gpurun_out/bench_n$N.json"))
+j=[json.loads(l) for l in open("gpurun_out/bench_n$N.json") if l.startswith("{")][-1]; n_lines=sum(1 for _ in open("gpurun_out/bench_n$N.json")); print("stdout lines:", n_lines)
 print("train", round(j["value"]), "seqs/s n_gpus", j["n_gpus"], "ms/step", round(j["ms_per_step"],4))
 for k,c in j["catalog"].items(): print(k, round(c["value"]), "users/s", round(c["ms_per_step"],2), "ms", c["roofline"]["achieved"], "TF/GPU-kernel", c["config"]["sharding"], "e2e", round(c["e2e"]["value"]))
 PY
