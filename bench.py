@@ -220,34 +220,67 @@ def bench_train(D: Dist, args, peaks):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(K)]
     n = cfg["B"] * cfg["L"]
 
-    def step(i):
-        b = batches[i % n_batches]
+    def stage_fns(b):
         tb = b["tb"]
+        m = hp.mask.view(n)
+        h2 = b["h"].view(n, cfg["d"])
+
+        def f_gather():
+            hp.forward_in(tb.dec_in)
+
+        def f_fwd():
+            hp.forward_loss(b["h"], tb.dec_out, tb.n_items)
+
+        def f_dh():
+            ops.raw_sampled_score_bwd_dh(hp.sbuf["dp"], hp.sbuf["dn"], hp.weight, tb.dec_out, tb.n_items,
+                                         scale=hp.one, scale2=hp.sbuf["aux"][1:2], out=hp.dh)
+
+        def f_plan():
+            ops.raw_fill_zero(hp.dW)
+            ops.raw_embedding_bwd_plan([ops.Site(tb.dec_in, None, live=m), ops.Site(tb.dec_out, None, live=m),
+                                        ops.Site(tb.n_items, None, group=cfg["K"], live=m)], hp.V1, 0, hp.ws_bwd)
+
+        def f_apply():
+            sites = [ops.Site(tb.dec_in, b["g"].view(n, cfg["d"]), coef=m, live=m),
+                     ops.Site(tb.dec_out, h2, coef=hp.sbuf["dp"], scale=hp.one, scale2=hp.sbuf["aux"][1:2], live=m),
+                     ops.Site(tb.n_items, h2, coef=hp.sbuf["dn"].view(-1), scale=hp.one,
+                              scale2=hp.sbuf["aux"][1:2], group=cfg["K"], live=m)]
+            ops.raw_embedding_bwd_apply(sites, hp.V1, hp.d, hp.dW, hp.ws_bwd, mode=ops.DW_PREZEROED)
+        return [f_gather, f_fwd, f_dh, f_plan, f_apply]
+
+    fns = [stage_fns(b) for b in batches]
+    # one eager pass counts the launches of a step; the timing itself replays one small CUDA graph
+    # per stage, so that a slow host cannot stretch the gaps between the events
+    l0 = _lib.launch_count()
+    for f in fns[0]:
+        f()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - l0
+    stage_graphs = None
+    if not args.no_graph:
+        stage_graphs = []
+        for fb in fns:
+            gs = []
+            for f in fb:
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    f()
+                gs.append(g_)
+            stage_graphs.append(gs)
+
+    def step(i):
+        bi = i % n_batches
         rec = evs[i - Wm] if i >= Wm else None
         if rec: rec[0].record()
-        hp.forward_in(tb.dec_in)
-        if rec: rec[1].record()
-        hp.forward_loss(b["h"], tb.dec_out, tb.n_items)
-        if rec: rec[2].record()
-        ops.raw_sampled_score_bwd_dh(hp.sbuf["dp"], hp.sbuf["dn"], hp.weight, tb.dec_out, tb.n_items,
-                                     scale=hp.one, scale2=hp.sbuf["aux"][1:2], out=hp.dh)
-        if rec: rec[3].record()
-        m = hp.mask.view(n)
-        ops.raw_fill_zero(hp.dW)
-        ops.raw_embedding_bwd_plan([ops.Site(tb.dec_in, None, live=m), ops.Site(tb.dec_out, None, live=m),
-                                    ops.Site(tb.n_items, None, group=cfg["K"], live=m)], hp.V1, 0, hp.ws_bwd)
-        if rec: rec[4].record()
-        h2 = b["h"].view(n, cfg["d"])
-        sites = [ops.Site(tb.dec_in, b["g"].view(n, cfg["d"]), coef=m, live=m),
-                 ops.Site(tb.dec_out, h2, coef=hp.sbuf["dp"], scale=hp.one, scale2=hp.sbuf["aux"][1:2], live=m),
-                 ops.Site(tb.n_items, h2, coef=hp.sbuf["dn"].view(-1), scale=hp.one,
-                          scale2=hp.sbuf["aux"][1:2], group=cfg["K"], live=m)]
-        ops.raw_embedding_bwd_apply(sites, hp.V1, hp.d, hp.dW, hp.ws_bwd, mode=ops.DW_PREZEROED)
-        if rec: rec[5].record()
+        for si in range(5):
+            if stage_graphs is None:
+                fns[bi][si]()
+            else:
+                stage_graphs[bi][si].replay()
+            if rec: rec[si + 1].record()
 
-    l0 = _lib.launch_count()
     ms_serial = timed_loop(D, step, K, Wm)
-    launches = (_lib.launch_count() - l0) * K // (K + Wm)
+    launches = launches_per_step * K
     # ---- the timed number: TrainHotPath.step -- same kernels, same buffers, the table-backward
     # plan forked onto a side stream under the scoring kernels -- replayed as one CUDA graph per
     # rotating batch (the way a launch-bound chain of short kernels is meant to be driven);
