@@ -334,6 +334,19 @@ def bench_train(D: Dist, args, peaks):
                     "with the kernels serialised on one stream; whole_step = all algorithmic bytes of a step "
                     "over the timed step"}
 
+    # ---- next row: the optimizer step of the table, timed on its own (NOT part of
+    # the step above: north_star stops at the dense gradient)
+    from recguru_b200.optim import FusedTableAdam
+    w_adam = W.clone()
+    opt = FusedTableAdam(w_adam, lr=1e-3)
+    ms_adam = timed_loop(D, lambda i: opt.step(hp.dW), max(K, 10), Wm) / max(K, 10)
+    adam_mb = 7 * W.numel() * 4 / 1e6
+    table_adam = {"ms": round(ms_adam, 4), "algorithmic_mb": round(adam_mb, 1),
+                  "gbs": round(adam_mb / ms_adam, 1), "frac_of_hbm_peak": round(adam_mb / ms_adam / peaks["hbm"], 3),
+                  "note": "torch.optim.Adam arithmetic for the [V1,d] table in one kernel (read W,m,v,g; write W,m,v); "
+                          "not included in the timed step"}
+    del w_adam, opt
+
     # ---- end to end through the public API with host buffers ----
     # A prefetching loader: the ids of step i+1 are copied (pinned host -> device, side stream)
     # while step i computes; the loss of every step is read back and waited for, as the
@@ -407,6 +420,7 @@ def bench_train(D: Dist, args, peaks):
                         "and are device resident"},
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
         "launch_mode": "eager" if args.no_graph else "cuda_graph (one graph per rotating batch)",
+        "table_adam": table_adam,
         "ms_per_step_eager": ms_eager / K, "ms_per_step_serialised_stages": ms_serial / K,
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
         "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,
@@ -696,7 +710,8 @@ def main():
                     "algorithmic_mb_per_step": train["algorithmic_mb_per_step"],
                     "table_backward": train["table_backward"], "launch_mode": train["launch_mode"],
                     "ms_per_step_eager": train["ms_per_step_eager"],
-                    "ms_per_step_serialised_stages": train["ms_per_step_serialised_stages"]}
+                    "ms_per_step_serialised_stages": train["ms_per_step_serialised_stages"],
+                    "table_adam": train["table_adam"]}
             if gather is not None:
                 line["gather"] = gather
             line["catalog"] = cat

@@ -227,6 +227,16 @@ int recguru_topk_merge(const float* vals, const int64_t* ids, const int64_t* cou
 int recguru_rank_histogram(const int64_t* rank, int64_t U, int64_t kmax, int64_t* hist,
                            int accumulate, recguru_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * SURVEY 8f rank 2 -- optimizer step of the item table: torch.optim.Adam's arithmetic
+ *   (train_auto.py:354-364: betas (0.9, 0.99), eps 1e-9, dense gradient, no weight decay /
+ *   amsgrad) in one pass over weight, exp_avg, exp_avg_sq and grad.  `step` counts from 1;
+ *   bias corrections are formed in fp64 on the host as torch does.  All buffers [n_floats].
+ * ---------------------------------------------------------------------------------- */
+int recguru_table_adam(float* weight, float* exp_avg, float* exp_avg_sq, const float* grad,
+                       int64_t n_floats, double lr, double beta1, double beta2, double eps,
+                       int64_t step, recguru_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

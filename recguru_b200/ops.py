@@ -431,6 +431,21 @@ def raw_rank_histogram(rank: Tensor, kmax: int, hist: Optional[Tensor] = None,
     return hist
 
 
+def raw_table_adam(weight: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, grad: Tensor, lr: float,
+                   beta1: float, beta2: float, eps: float, step: int) -> None:
+    """One torch.optim.Adam step of the item table (train_auto.py:354-364) in a single pass."""
+    lib = _lib.load()
+    bufs = [_need(t, torch.float32, n) for t, n in ((weight, "weight"), (exp_avg, "exp_avg"),
+                                                    (exp_avg_sq, "exp_avg_sq"), (grad, "grad"))]
+    if any(not t.is_contiguous() for t in (weight, exp_avg, exp_avg_sq)):
+        raise RuntimeError("recguru: table_adam updates in place: weight and moments must be contiguous")
+    if len({t.numel() for t in bufs}) != 1:
+        raise RuntimeError("recguru: table_adam: weight, moments and grad must have the same size")
+    check(lib.recguru_table_adam(_ptr(weight), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(bufs[3]), weight.numel(),
+                                 float(lr), float(beta1), float(beta2), float(eps), int(step), _stream()),
+          "table_adam")
+
+
 # --------------------------------------------------------------------------------------
 # op layer: torch.library custom ops + autograd
 # --------------------------------------------------------------------------------------
