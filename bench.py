@@ -516,7 +516,12 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
         def sweep(i):
             ops.raw_catalog_topk_rank(users_bf[i % n_chunks], items, targets[i % n_chunks], ts, k, ev.id_lo, bufs=bufs)
         sweep_ms = timed_loop(D, sweep, steps, warm) / steps
+    # rank-only mode (k = 0; what HR/NDCG/MRR need -- CatalogEvaluator.target_rank / evaluate)
+    ms_rank = timed_loop(D, lambda i: ev.target_rank(users[i % n_chunks], targets[i % n_chunks]), steps, warm) / steps
     flops = 2.0 * u_step * (hi - lo) * d
+    rank_only = {"ms_per_step": round(ms_rank, 3), "users_per_s": round(u_step / (ms_rank * 1e-3)),
+                 "tflops": round(flops / (ms_rank * 1e-3) / 1e12, 1),
+                 "note": "target rank only: the sweep skips the maxima and the top-k lists"}
     t_kernel = sweep_ms if sweep_ms is not None else per
     tflops = flops / (t_kernel * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "catalog_sweep_kernel", "achieved": round(tflops, 1),
@@ -546,7 +551,7 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
                    "users_total_cfg": cfg["users_total"], "sharding": f"rows/{G}" if sharded else "none",
                    "l2": "4 rotating user chunks; item table 256 MB-2.5 GB > L2"},
         "scaling": "strong" if sharded else None,
-        "sweep_kernel_ms": sweep_ms, "roofline": roof,
+        "sweep_kernel_ms": sweep_ms, "rank_only": rank_only, "roofline": roof,
         "e2e": {"value": u_step / (ms_e2e * 1e-3), "unit": "users/s",
                 "h2d_bytes_per_step": u_loc * (d * 4 + 8), "d2h_bytes_per_step": u_loc * 8, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "clocks": cs.summary(),

@@ -200,6 +200,7 @@ int recguru_catalog_target_scores(const void* users_bf16, int64_t U, const void*
                                   const int64_t* target, float* target_score,
                                   recguru_stream_t stream);
 int64_t recguru_catalog_workspace_bytes(int64_t U, int64_t n_items, int64_t d, int64_t k);
+/* k == 0: rank only (topk_val / topk_id may be NULL) -- the sweep skips the maxima and the lists. */
 int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, const void* items_bf16,
                               int64_t id_lo, int64_t n_items, int64_t d, const int64_t* target,
                               const float* target_score, int64_t k, float* topk_val,

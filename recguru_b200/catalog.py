@@ -176,14 +176,36 @@ class CatalogEvaluator:
         # (5) merge the G per-shard lists (desc score, asc id) and sum the rank counts
         return self._merge(val_x, idx_x, cnt_x)
 
+    def _local_rank(self, users_bf16: Tensor, target: Tensor, tscore: Tensor) -> Tensor:
+        return ops.raw_catalog_topk_rank(users_bf16, self.items, target, tscore, 0, self.id_lo)[2]
+
+    def target_rank(self, users: Tensor, target: Tensor) -> Tensor:
+        """Target ranks only (what HR/NDCG/MRR need): the sweep runs in its rank-only mode -- no
+        group maxima, no top-k lists -- and the shards exchange one count per user."""
+        u = self._prepare_users(users)
+        if self.world == 1:
+            return self._local_rank(u, target, self._local_target_scores(u, target))
+        G = self.world
+        U_loc = u.shape[0]
+        u_all = torch.empty(G * U_loc, self.d, dtype=u.dtype, device=u.device)
+        t_all = torch.empty(G * U_loc, dtype=torch.int64, device=u.device)
+        dist.all_gather_into_tensor(u_all, u, group=self.group)
+        dist.all_gather_into_tensor(t_all, target.contiguous(), group=self.group)
+        ts = self._local_target_scores(u_all, t_all)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=self.group)
+        cnt = self._local_rank(u_all, t_all, ts)
+        cnt_x = torch.empty(G, U_loc, dtype=cnt.dtype, device=cnt.device)
+        dist.all_to_all_single(cnt_x, cnt.view(G, U_loc), group=self.group)
+        return cnt_x.sum(0)
+
     def evaluate(self, users: Tensor, target: Tensor, ks: Sequence[int] = (5, 10, 20, 30)):
         """Ranks + HR/NDCG/MRR@k for this rank's users (global metrics need a sum of the
         histograms over ranks: see :meth:`evaluate_global`)."""
-        _, _, rank = self.rank_topk(users, target)
+        rank = self.target_rank(users, target)
         return rank, rank_metrics(rank, ks)
 
     def evaluate_global(self, users: Tensor, target: Tensor, ks: Sequence[int] = (5, 10, 20, 30)):
-        _, _, rank = self.rank_topk(users, target)
+        rank = self.target_rank(users, target)
         kmax = int(max(ks))
         hist = ops.raw_rank_histogram(rank, kmax)
         n = torch.tensor([rank.numel()], dtype=torch.int64, device=rank.device)

@@ -42,7 +42,7 @@ constexpr int kAccum = 4;        // TMEM accumulator buffers (4 x 128 columns)
 constexpr int kMaxK = 32;
 constexpr int kFmaSignCols = 16;  // of every 32 columns, sign bits accumulated on the FMA pipe
 
-enum CatalogMode { kModeTopK = 0, kModeDense = 1 };
+enum CatalogMode { kModeTopK = 0, kModeDense = 1, kModeRank = 2 };   // Rank: target rank only (k = 0)
 
 // debug profile (RECGURU_CATALOG_PROF=1): cycles CTA (0,0) spends in each wait, per role
 __device__ long long g_prof[16];
@@ -296,7 +296,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
 
     float t = 0.f;
     int64_t tgt_local = -1;                   // target's row index inside the slice
-    if (MODE == kModeTopK && u_ok) {
+    if (MODE != kModeDense && u_ok) {
       t = p.tscore[u];
       if (t == 0.f) t = 0.f;                // -0 -> +0 (the sign-bit count relies on it)
       tgt_local = p.target[u] - p.id_lo;
@@ -512,7 +512,8 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
               }
             }
           }
-          offer8(w, n0 + c0, valid - c0 >= 8 ? 0xffu : (valid > c0 ? (1u << (valid - c0)) - 1u : 0u));
+          if constexpr (MODE == kModeTopK)
+            offer8(w, n0 + c0, valid - c0 >= 8 ? 0xffu : (valid > c0 ? (1u << (valid - c0)) - 1u : 0u));
         }
       } else if constexpr (PIPE) {
         // fast tile, software pipelined.  TMEM reads are slow next to a running tensor core
@@ -591,6 +592,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
             ca[0] += vr[0] ^ vr[CH - 1];   // debug: TMEM-load-only floor (results meaningless)
             continue;
           }
+          if constexpr (MODE == kModeTopK) {
           // (a) 8-column group maxima first: they decide whether the top-k lists must be touched.
           // (A single row maximum + full re-read was measured: 54 vs 32 ms at cfg4 -- with 32 users
           // per warp SOME lane's threshold is beaten in about every second tile of a 1M-item
@@ -646,6 +648,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
               offer8(w8, n0 + c0 + g * 8, 0xffu);
             }
           }
+          }
           // (c) rank count: four differences (two FADD2) ahead of their sign accumulation so the
           // FMA-pipe latency overlaps
 #pragma unroll
@@ -696,6 +699,16 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           s_val[(q - (16 - K)) * kSlots + slot] = lv[q];
           s_id[(q - (16 - K)) * kSlots + slot] = li[q];
         }
+      }
+    }
+    if (MODE == kModeRank) {
+      s_cnt[e * 128 + row] = cnt;
+      asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128) : "memory");
+      if (e == 0 && u_ok) {
+        int total = 0;
+#pragma unroll
+        for (int q = 0; q < NSETS; ++q) total += s_cnt[q * 128 + row];
+        p.out_cnt[static_cast<int64_t>(blockIdx.y) * p.U + u] = total;
       }
     }
     if (MODE == kModeTopK) {
@@ -1009,7 +1022,7 @@ static int check_catalog(const char* who, const void* users, int64_t U, const vo
 extern "C" int64_t recguru_catalog_workspace_bytes(int64_t U, int64_t n_items, int64_t d,
                                                    int64_t k) {
   (void)d;
-  if (U <= 0 || n_items <= 0 || k < 1 || k > rg::kMaxK) return RECGURU_E_SHAPE;
+  if (U <= 0 || n_items <= 0 || k < 0 || k > rg::kMaxK) return RECGURU_E_SHAPE;
   const int s = rg::pick_splits(U, n_items, rg::catalog_bn());
   if (s == 1) return 256;
   return rg::align_up(static_cast<int64_t>(s) * U * k * 12, 256) +
@@ -1054,9 +1067,9 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
   using namespace rg;
   int rc = check_catalog("catalog_topk_rank", users_bf16, U, items_bf16, n_items, d);
   if (rc) return rc;
-  RG_REQUIRE(target && target_score && topk_val && topk_id && rank_count, RECGURU_E_SHAPE,
+  RG_REQUIRE(target && target_score && rank_count && (k == 0 || (topk_val && topk_id)), RECGURU_E_SHAPE,
              "catalog_topk_rank: null pointer");
-  RG_REQUIRE(k >= 1 && k <= kMaxK, RECGURU_E_UNSUPPORTED, "catalog_topk_rank: k=%lld not in [1,%d]",
+  RG_REQUIRE(k >= 0 && k <= kMaxK, RECGURU_E_UNSUPPORTED, "catalog_topk_rank: k=%lld not in [0,%d]",
              (long long)k, kMaxK);
   CUtensorMap mu;
   rc = make_rowmajor_map(&mu, users_bf16, U, d);
@@ -1081,7 +1094,10 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
     p.out_id = reinterpret_cast<int64_t*>(ws + sv);
     p.out_cnt = reinterpret_cast<int64_t*>(ws + sv + si);
   }
-  rc = d == 64 ? launch_sweep<64, kModeTopK>(items_bf16, mu, p, bn, st) : launch_sweep<128, kModeTopK>(items_bf16, mu, p, bn, st);
+  if (k == 0)   // rank only: no maxima, no lists -- what HR/NDCG/MRR need
+    rc = d == 64 ? launch_sweep<64, kModeRank>(items_bf16, mu, p, 128, st) : launch_sweep<128, kModeRank>(items_bf16, mu, p, 128, st);
+  else
+    rc = d == 64 ? launch_sweep<64, kModeTopK>(items_bf16, mu, p, bn, st) : launch_sweep<128, kModeTopK>(items_bf16, mu, p, bn, st);
   if (rc) return rc;
   if (p.n_splits > 1)
     return recguru_topk_merge(p.out_val, p.out_id, p.out_cnt, p.n_splits, U, k, topk_val, topk_id,

@@ -120,11 +120,11 @@ extern "C" int recguru_topk_merge(const float* vals, const int64_t* ids, const i
                                   int64_t G, int64_t U, int64_t k, float* out_val, int64_t* out_id,
                                   int64_t* out_rank, recguru_stream_t stream) {
   using namespace rg;
-  RG_REQUIRE(vals && ids && out_val && out_id, RECGURU_E_SHAPE, "topk_merge: null pointer");
+  RG_REQUIRE(k == 0 || (vals && ids && out_val && out_id), RECGURU_E_SHAPE, "topk_merge: null pointer");
   RG_REQUIRE(out_rank == nullptr || counts != nullptr, RECGURU_E_SHAPE,
              "topk_merge: out_rank requires counts");
-  RG_REQUIRE(G >= 1 && G <= 64 && U >= 0 && k >= 1 && k <= 32, RECGURU_E_UNSUPPORTED,
-             "topk_merge: G=%lld (1..64) k=%lld (1..32)", (long long)G, (long long)k);
+  RG_REQUIRE(G >= 1 && G <= 64 && U >= 0 && k >= 0 && k <= 32, RECGURU_E_UNSUPPORTED,
+             "topk_merge: G=%lld (1..64) k=%lld (0..32)", (long long)G, (long long)k);
   if (U == 0) return RECGURU_OK;
   topk_merge_kernel<<<static_cast<unsigned>(ceil_div(U, 128)), 128, 0,
                       static_cast<cudaStream_t>(stream)>>>(vals, ids, counts, static_cast<int>(G),

@@ -96,7 +96,7 @@ class EvalDriver:
 
     def _rank(self, u: Tensor, target: Tensor, cand: Optional[Tensor]) -> Tensor:
         if self.evaluator is not None:
-            return self.evaluator.rank_topk(u, target)[2]
+            return self.evaluator.target_rank(u, target)
         return catalog.get_scores_rank(u, self.weight, target, cand.view(u.shape[0], -1))[1]
 
     @torch.no_grad()

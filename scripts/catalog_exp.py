@@ -15,7 +15,7 @@ g = torch.Generator(device=dev); g.manual_seed(1)
 users = ops.raw_cast_bf16(torch.randn(U, d, generator=g, device=dev))
 
 
-def run(n_items, label, **env):
+def run(n_items, label, k=k, **env):
     for kk, v in env.items():
         os.environ[kk] = str(v)
     items = ops.raw_cast_bf16(torch.randn(n_items, d, generator=g, device=dev))
@@ -39,9 +39,7 @@ def run(n_items, label, **env):
 
 
 n_items = 1_000_000
-run(n_items, "default (x128 epilogue, register top-k lists)")
-run(n_items, "shared-memory top-k lists", RECGURU_CATALOG_REGLIST=0)
-run(n_items, "pipelined epilogue", RECGURU_CATALOG_PIPE=1)
-run(n_items, "4 epilogue sets", RECGURU_CATALOG_SETS=4)
-run(n_items, "5 decoupled smem stages", RECGURU_CATALOG_STAGES=5)
-run(10_000_000, "default, 10M items")
+run(n_items, "top-10 + rank (default)")
+run(n_items, "rank only (k = 0)", k=0)
+run(10_000_000, "top-10 + rank, 10M items")
+run(10_000_000, "rank only, 10M items", k=0)

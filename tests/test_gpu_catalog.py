@@ -80,6 +80,9 @@ def _check_fused(ops, users, items, target, k, id_lo, scores):
     assert torch.equal(val.cpu()[:, :min(k, N)], rv)
     if N < k:
         assert bool((idx.cpu()[:, N:] == -1).all())
+    # rank-only mode (k = 0: no maxima, no lists) must give the same counts
+    _, _, cnt0 = ops.raw_catalog_topk_rank(bf16(users), bf16(items), target.cuda(), ts, 0, id_lo)
+    assert torch.equal(cnt0, cnt)
     return cnt
 
 

@@ -53,6 +53,9 @@ def _make_oracle_evaluator():
             val[:, :k] = v; idx[:, :k] = i + self.id_lo
             return val, idx, cnt.to(torch.int64)
 
+        def _local_rank(self, u, target, ts):
+            return self._local_topk_rank(u, target, ts)[2]
+
         def _merge(self, vals, ids, counts):
             G, U, k = vals.shape
             v = vals.permute(1, 0, 2).reshape(U, G * k)
@@ -86,6 +89,8 @@ def _worker(rank, world, port, n_items, U, k, out):
         per = U // world
         sl = slice(rank * per, (rank + 1) * per)
         val, idx, rk = ev.rank_topk(users[sl], target[sl])
+        rk_only = ev.target_rank(users[sl], target[sl])                            # rank-only exchange
+        assert torch.equal(rk_only, rk)
         out[rank] = (val, idx, rk, ev.id_lo, ev.n_local)
     finally:
         dist.destroy_process_group()
