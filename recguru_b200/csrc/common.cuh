@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "../../include/recguru_b200.h"
 
@@ -37,6 +40,41 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 constexpr int kNumSMs = 148;  // B200
+
+// ---- programmatic dependent launch ---------------------------------------------------
+// The training-step path is a chain of short kernels on one stream.  Every kernel of the chain
+// starts with griddepcontrol.wait (nothing is read or written before the previous grid has
+// completed and flushed) and ends with griddepcontrol.launch_dependents, and is launched with
+// the programmatic-stream-serialization attribute: the next kernel's launch and CTA scheduling
+// overlap this kernel's tail instead of waiting for the full drain.  RECGURU_PDL=0 turns the
+// attribute off (the device instructions are then no-ops).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RECGURU_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // error picked up by RG_CHECK_LAUNCH
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---- device helpers --------------------------------------------------------------
 #ifdef __CUDACC__

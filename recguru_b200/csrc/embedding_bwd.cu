@@ -102,6 +102,7 @@ __device__ __forceinline__ bool occurrence_live(const SiteTable& st, int64_t i, 
 template <int NS>
 __global__ void __launch_bounds__(kSortThreads)
 compact_count_kernel(SiteTable st, int64_t total, int64_t padding_idx, uint32_t* __restrict__ tile_count) {
+  rg::pdl_wait();
   __shared__ uint32_t s_w[kSortThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
@@ -122,11 +123,13 @@ compact_count_kernel(SiteTable st, int64_t total, int64_t padding_idx, uint32_t*
     for (int w = 0; w < kSortThreads / 32; ++w) t += s_w[w];
     tile_count[blockIdx.x] = t;
   }
+  rg::pdl_trigger();
 }
 
 // pass 2: exclusive scan of the tile counts (one CTA) + the live total
 __global__ void __launch_bounds__(1024)
 compact_scan_kernel(uint32_t* __restrict__ tile_count, int n_tiles, uint32_t* __restrict__ n_live) {
+  rg::pdl_wait();
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -152,6 +155,7 @@ compact_scan_kernel(uint32_t* __restrict__ tile_count, int n_tiles, uint32_t* __
     __syncthreads();
   }
   if (tid == 0) *n_live = s_carry;
+  rg::pdl_trigger();
 }
 
 // pass 3: stable scatter of the live (key, occurrence index) pairs
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(kSortThreads)
 compact_scatter_kernel(SiteTable st, int64_t total, int64_t padding_idx,
                        const uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ keys,
                        uint32_t* __restrict__ vals) {
+  rg::pdl_wait();
   __shared__ uint32_t s_w[kSortThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
@@ -188,14 +193,17 @@ compact_scatter_kernel(SiteTable st, int64_t total, int64_t padding_idx,
       vals[base + rank[j]] = static_cast<uint32_t>(warp0 + j * 32 + lane);
     }
   }
+  rg::pdl_trigger();
 }
 
 __global__ void __launch_bounds__(256)
 narrow_keys_kernel(const int64_t* __restrict__ ids, int64_t total, uint32_t* __restrict__ keys) {
+  rg::pdl_wait();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += stride)
     keys[i] = static_cast<uint32_t>(ids[i]);
+  rg::pdl_trigger();
 }
 
 // ---- 2. radix sort ---------------------------------------------------------------------
@@ -205,6 +213,7 @@ __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total_host,
                   const uint32_t* __restrict__ n_live, int shift, int bits,
                   uint32_t* __restrict__ block_hist /* [bins][gridDim.x] */) {
+  rg::pdl_wait();
   __shared__ uint32_t s_hist[kMaxBins];
   const int64_t total = n_live ? static_cast<int64_t>(*n_live) : total_host;
   const int bins = 1 << bits;
@@ -220,12 +229,14 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total_host,
   __syncthreads();
   for (int b = threadIdx.x; b < bins; b += kSortThreads)
     block_hist[static_cast<int64_t>(b) * gridDim.x + blockIdx.x] = s_hist[b];
+  rg::pdl_trigger();
 }
 
 // Exclusive scan of one digit's row of the digit-major histogram (CTA b <-> digit b); the row
 // total goes to totals[b].  The scatter kernel adds the digit base (scan over totals) itself.
 __global__ void __launch_bounds__(256)
 radix_scan_rows_kernel(uint32_t* __restrict__ hist, int n_tiles, uint32_t* __restrict__ totals) {
+  rg::pdl_wait();
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -254,6 +265,7 @@ radix_scan_rows_kernel(uint32_t* __restrict__ hist, int n_tiles, uint32_t* __res
     __syncthreads();
   }
   if (tid == 0) totals[blockIdx.x] = s_carry;
+  rg::pdl_trigger();
 }
 
 template <bool kFirstPass, typename OutVal>
@@ -264,6 +276,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
                      const uint32_t* __restrict__ totals /* [bins] */,
                      uint32_t* __restrict__ keys_out, OutVal* __restrict__ vals_out,
                      int64_t* __restrict__ keys_out64 /* optional widened copy (last pass) */) {
+  rg::pdl_wait();
   __shared__ uint32_t s_cnt[kSortThreads / 32][kMaxBins];
   __shared__ uint32_t s_base[kMaxBins];      // exclusive scan of the digit totals
   __shared__ uint32_t s_wsum[kSortThreads / 32];
@@ -340,15 +353,18 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
       if (keys_out64) keys_out64[dst] = static_cast<int64_t>(key[j]);
     }
   }
+  rg::pdl_trigger();
 }
 
 // ---- 3. zero fill -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n_vec) {
+  rg::pdl_wait();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
        i += stride)
     p[i] = z;
+  rg::pdl_trigger();
 }
 
 // ---- 4. chunked segmented reduce -----------------------------------------------------
@@ -360,6 +376,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
                     int vec /* d/4 */,
                     int64_t padding_idx, int accumulate, float4* __restrict__ dW,
                     float4* __restrict__ partial /* [n_chunks][2][vec] */) {
+  rg::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total = *n_live;
   const int64_t chunk = static_cast<int64_t>(blockIdx.x) * kReduceWarps + warp;
@@ -498,6 +515,7 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
       }
     }
   }
+  rg::pdl_trigger();
 }
 
 // ---- 5. runs that cross chunk edges --------------------------------------------------
@@ -508,6 +526,7 @@ __global__ void __launch_bounds__(kReduceWarps * 32)
 span_fixup_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ n_live, int vec,
                   int64_t padding_idx, int accumulate, float4* __restrict__ dW,
                   const float4* __restrict__ partial) {
+  rg::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total = *n_live;
   const int64_t n_chunks = (total + kChunk - 1) / kChunk;
@@ -572,6 +591,7 @@ span_fixup_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict
       *dst = o;
     }
   }
+  rg::pdl_trigger();
 }
 
 // ---- host orchestration -------------------------------------------------------------
@@ -622,24 +642,24 @@ static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, const uint
   for (int pass = 0; pass < p.passes; ++pass) {
     const int shift = pass * p.bits_per_pass;
     const int bits = min(p.bits_per_pass, p.total_bits - shift);
-    radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(keys[cur], count, n_live, shift, bits, hist);
+    rg::launch_pdl((radix_hist_kernel), grid, kSortThreads, 0, st, keys[cur], count, n_live, shift, bits, hist);
     RG_CHECK_LAUNCH("radix_hist");
-    radix_scan_rows_kernel<<<1u << bits, 256, 0, st>>>(hist, static_cast<int>(p.n_tiles), totals);
+    rg::launch_pdl((radix_scan_rows_kernel), 1u << bits, 256, 0, st, hist, static_cast<int>(p.n_tiles), totals);
     RG_CHECK_LAUNCH("radix_scan_rows");
     const bool last = pass == p.passes - 1;
     if (last && out_perm64) {
       if (pass == 0 && identity_vals)
-        radix_scatter_kernel<true, int64_t><<<grid, kSortThreads, 0, st>>>(
+        rg::launch_pdl((radix_scatter_kernel<true, int64_t>), grid, kSortThreads, 0, st, 
             keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
       else
-        radix_scatter_kernel<false, int64_t><<<grid, kSortThreads, 0, st>>>(
+        rg::launch_pdl((radix_scatter_kernel<false, int64_t>), grid, kSortThreads, 0, st, 
             keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], out_perm64, out_keys64);
     } else {
       if (pass == 0 && identity_vals)
-        radix_scatter_kernel<true, uint32_t><<<grid, kSortThreads, 0, st>>>(
+        rg::launch_pdl((radix_scatter_kernel<true, uint32_t>), grid, kSortThreads, 0, st, 
             keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
       else
-        radix_scatter_kernel<false, uint32_t><<<grid, kSortThreads, 0, st>>>(
+        rg::launch_pdl((radix_scatter_kernel<false, uint32_t>), grid, kSortThreads, 0, st, 
             keys[cur], vals[cur], count, n_live, shift, bits, hist, totals, keys[cur ^ 1], vals[cur ^ 1], nullptr);
     }
     RG_CHECK_LAUNCH("radix_scatter");
@@ -671,7 +691,7 @@ extern "C" int recguru_sort_ids(const int64_t* ids, int64_t count, int64_t V1, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   int64_t blocks = rg::min64(ceil_div(count, 256 * 4), kNumSMs * 8);
-  narrow_keys_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+  rg::launch_pdl((narrow_keys_kernel), static_cast<unsigned>(blocks), 256, 0, st, 
       ids, count, reinterpret_cast<uint32_t*>(ws + p.off_keys_a));
   RG_CHECK_LAUNCH("narrow_keys");
   uint32_t *sk, *sv;
@@ -721,7 +741,7 @@ extern "C" int recguru_fill_zero(float* p, int64_t n_floats, recguru_stream_t st
   if (n_floats == 0) return RECGURU_OK;
   const int64_t n_vec = n_floats / 4;
   const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 4), kNumSMs * 16);
-  zero_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  rg::launch_pdl((zero_fill_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<float4*>(p), n_vec);
   RG_CHECK_LAUNCH("zero_fill");
   return RECGURU_OK;
@@ -749,15 +769,15 @@ extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_hos
   const unsigned tiles = static_cast<unsigned>(ceil_div(total, kCompactTile));
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + p.off_keys_a);
   uint32_t* va = reinterpret_cast<uint32_t*>(ws + p.off_vals_a);
-  if (n_sites <= 1) compact_count_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
-  else if (n_sites <= 3) compact_count_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
-  else compact_count_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt);
+  if (n_sites <= 1) rg::launch_pdl((compact_count_kernel<1>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt);
+  else if (n_sites <= 3) rg::launch_pdl((compact_count_kernel<3>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt);
+  else rg::launch_pdl((compact_count_kernel<RECGURU_MAX_SITES>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt);
   RG_CHECK_LAUNCH("compact_count");
-  compact_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, static_cast<int>(tiles), n_live);
+  rg::launch_pdl((compact_scan_kernel), 1, 1024, 0, st, tile_cnt, static_cast<int>(tiles), n_live);
   RG_CHECK_LAUNCH("compact_scan");
-  if (n_sites <= 1) compact_scatter_kernel<1><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
-  else if (n_sites <= 3) compact_scatter_kernel<3><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
-  else compact_scatter_kernel<RECGURU_MAX_SITES><<<tiles, kSortThreads, 0, st>>>(tab, total, padding_idx, tile_cnt, ka, va);
+  if (n_sites <= 1) rg::launch_pdl((compact_scatter_kernel<1>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt, ka, va);
+  else if (n_sites <= 3) rg::launch_pdl((compact_scatter_kernel<3>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt, ka, va);
+  else rg::launch_pdl((compact_scatter_kernel<RECGURU_MAX_SITES>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt, ka, va);
   RG_CHECK_LAUNCH("compact_scatter");
   uint32_t *sk, *sv;
   return run_radix_sort(p, ws, total, n_live, false, st, &sk, &sv, nullptr, nullptr);
@@ -806,18 +826,18 @@ extern "C" int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_ho
 #define RG_LAUNCH_REDUCE(V)                                                                   \
   do {                                                                                        \
     if (n_sites <= 1)                                                                         \
-      chunk_reduce_kernel<V, 1><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, n_live, vec, -1, \
+      rg::launch_pdl((chunk_reduce_kernel<V, 1>), grid, kReduceWarps * 32, 0, st, tab, sk, sv, n_live, vec, -1, \
                                                                     accumulate, dW4, partial);    \
     else if (n_sites <= 3)                                                                    \
-      chunk_reduce_kernel<V, 3><<<grid, kReduceWarps * 32, 0, st>>>(tab, sk, sv, n_live, vec, -1, \
+      rg::launch_pdl((chunk_reduce_kernel<V, 3>), grid, kReduceWarps * 32, 0, st, tab, sk, sv, n_live, vec, -1, \
                                                                     accumulate, dW4, partial);    \
     else                                                                                      \
-      chunk_reduce_kernel<V, RECGURU_MAX_SITES><<<grid, kReduceWarps * 32, 0, st>>>(          \
+      rg::launch_pdl((chunk_reduce_kernel<V, RECGURU_MAX_SITES>), grid, kReduceWarps * 32, 0, st,           \
           tab, sk, sv, n_live, vec, -1, accumulate, dW4, partial);                            \
     RG_CHECK_LAUNCH("chunk_reduce");                                                          \
     if (n_chunks > 1) {                                                                       \
       const unsigned g2 = static_cast<unsigned>(ceil_div(n_chunks - 1, kReduceWarps));        \
-      span_fixup_kernel<V><<<g2, kReduceWarps * 32, 0, st>>>(sk, n_live, vec,                 \
+      rg::launch_pdl((span_fixup_kernel<V>), g2, kReduceWarps * 32, 0, st, sk, n_live, vec,                 \
                                                              -1, accumulate, dW4,             \
                                                              partial);                        \
       RG_CHECK_LAUNCH("span_fixup");                                                          \

@@ -27,6 +27,7 @@ gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restri
                       const float4* __restrict__ pe, const float* __restrict__ mask_in,
                       int64_t pad_index, int64_t n_tokens, int L, int vec_rt,
                       float4* __restrict__ out, float* __restrict__ mask_out) {
+  rg::pdl_wait();
   extern __shared__ int smem_raw[];
   const int vec = VEC > 0 ? VEC : vec_rt;
   const int tok_per_block = (kGatherThreads * kGatherUnroll) / vec;
@@ -84,6 +85,7 @@ gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restri
       if (tok < n_tokens) st_stream_f4(out + tok * vec + vv[u], row[u]);
     }
   }
+  rg::pdl_trigger();
 }
 
 // PositionalEncoding.forward(x, mask) on an already materialised x.
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(256)
 pe_mask_kernel(const float4* __restrict__ x, const float4* __restrict__ pe,
                const float* __restrict__ mask, int64_t n_vec, int vec, int L,
                float4* __restrict__ out) {
+  rg::pdl_wait();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
        i += stride) {
@@ -106,6 +109,7 @@ pe_mask_kernel(const float4* __restrict__ x, const float4* __restrict__ pe,
     r.w = __fmul_rn(__fadd_rn(r.w, p.w), m);
     st_stream_f4(out + i, r);
   }
+  rg::pdl_trigger();
 }
 
 }  // namespace rg
@@ -134,7 +138,7 @@ extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d
   const float4* pe4 = reinterpret_cast<const float4*>(pe);
   float4* o4 = reinterpret_cast<float4*>(out);
 #define RG_LAUNCH_GATHER(V)                                                              \
-  gather_pe_mask_kernel<V><<<static_cast<unsigned>(blocks), kGatherThreads, smem, st>>>( \
+  rg::launch_pdl((gather_pe_mask_kernel<V>), static_cast<unsigned>(blocks), kGatherThreads, smem, st,  \
       w4, ids, pe4, mask_in, pad_index, n_tokens, static_cast<int>(L), vec, o4, mask_out)
   switch (vec) {
     case 8: RG_LAUNCH_GATHER(8); break;
@@ -163,7 +167,7 @@ extern "C" int recguru_pe_mask(const float* x, const float* pe, const float* mas
   const int64_t n_vec = n_tokens * vec;
   int64_t blocks = ceil_div(n_vec, 256 * 4);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  pe_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  rg::launch_pdl((pe_mask_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pe), mask, n_vec, vec,
       static_cast<int>(L), reinterpret_cast<float4*>(out));
   RG_CHECK_LAUNCH("pe_mask");

@@ -127,6 +127,7 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
                          float* __restrict__ p_out, float* __restrict__ n_out,
                          float* __restrict__ dp_unit, float* __restrict__ dn_unit,
                          float2* __restrict__ block_partial) {
+  rg::pdl_wait();
   constexpr int LANES = VEC < 32 ? VEC : 32;  // lanes cooperating on one row
   constexpr int G = 32 / LANES;               // row groups per warp step
   constexpr int VPL = VEC / LANES;            // float4 per lane per row
@@ -208,6 +209,7 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
       block_partial[blockIdx.x] = t;
     }
   }
+  rg::pdl_trigger();
 }
 
 // Padding-aware variant (RECGURU_LOSS_SKIP_MASKED): positions under the pad mask are not scored.
@@ -231,6 +233,7 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
                                 float* __restrict__ p_out, float* __restrict__ n_out,
                                 float* __restrict__ dp_unit, float* __restrict__ dn_unit,
                                 float2* __restrict__ block_partial, int chunk, int64_t pos_per_cta) {
+  rg::pdl_wait();
   constexpr int LANES = VEC < 32 ? VEC : 32;
   constexpr int G = 32 / LANES;
   constexpr int VPL = VEC / LANES;
@@ -351,6 +354,7 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
     }
   }
   if (kind >= 0 && tid == 0) block_partial[blockIdx.x] = make_float2(tot_l, tot_m);
+  rg::pdl_trigger();
 }
 
 // Loss from already computed logits: one thread per position.
@@ -358,6 +362,7 @@ __global__ void __launch_bounds__(256)
 sampled_loss_kernel(const float* __restrict__ p, const float* __restrict__ n, int64_t n_pos, int K,
                     const float* __restrict__ mask, int kind, float* __restrict__ dp_unit,
                     float* __restrict__ dn_unit, float2* __restrict__ block_partial) {
+  rg::pdl_wait();
   __shared__ float2 s_part[256 / 32];
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   float l = 0.f, m = 0.f;
@@ -412,6 +417,7 @@ sampled_loss_kernel(const float* __restrict__ p, const float* __restrict__ n, in
     for (int w = 0; w < 256 / 32; ++w) { t.x += s_part[w].x; t.y += s_part[w].y; }
     block_partial[blockIdx.x] = t;
   }
+  rg::pdl_trigger();
 }
 
 // loss_out[0] = sum(l*m)/sum(m);  loss_out[1] = 1/sum(m)  (the factor still missing from
@@ -419,6 +425,7 @@ sampled_loss_kernel(const float* __restrict__ p, const float* __restrict__ n, in
 __global__ void __launch_bounds__(256)
 loss_finalize_kernel(const float2* __restrict__ block_partial, int64_t n_blocks,
                      float* __restrict__ loss_out) {
+  rg::pdl_wait();
   __shared__ float2 s[256];
   float2 t = make_float2(0.f, 0.f);
   for (int64_t b = threadIdx.x; b < n_blocks; b += 256) {
@@ -435,6 +442,7 @@ loss_finalize_kernel(const float2* __restrict__ block_partial, int64_t n_blocks,
     loss_out[0] = s[0].x / s[0].y;
     loss_out[1] = 1.f / s[0].y;
   }
+  rg::pdl_trigger();
 }
 
 // dh[i,:] = s * (dp[i] * W[pos[i],:] + sum_k dn[i,k] * W[neg[i,k],:])
@@ -445,6 +453,7 @@ sampled_score_bwd_dh_kernel(const float* __restrict__ dp, const float* __restric
                             const float4* __restrict__ weight, const int64_t* __restrict__ pos,
                             const int64_t* __restrict__ neg, int64_t n_pos, int K,
                             float4* __restrict__ dh) {
+  rg::pdl_wait();
   constexpr int LANES = VEC < 32 ? VEC : 32;
   constexpr int G = 32 / LANES;
   constexpr int VPL = VEC / LANES;
@@ -519,6 +528,7 @@ sampled_score_bwd_dh_kernel(const float* __restrict__ dp, const float* __restric
       for (int v = 0; v < VPL; ++v) st_stream_f4(dh + i * VEC + v * LANES + sub, acc[v]);
     }
   }
+  rg::pdl_trigger();
 }
 
 // E1 + R1: the reference's sampled-candidate evaluation (get_scores + double argsort), fused.
@@ -532,6 +542,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
 candidate_rank_kernel(const float4* __restrict__ u, const float4* __restrict__ weight,
                       const int64_t* __restrict__ target, const int64_t* __restrict__ cand, int C,
                       float* __restrict__ scores, int64_t* __restrict__ rank) {
+  rg::pdl_wait();
   constexpr int LANES = VEC < 32 ? VEC : 32;
   constexpr int G = 32 / LANES;
   constexpr int VPL = VEC / LANES;
@@ -603,6 +614,7 @@ candidate_rank_kernel(const float4* __restrict__ u, const float4* __restrict__ w
     for (int w2 = 0; w2 < kScoreWarps; ++w2) t += s_cnt[w2];
     rank[b] = t;
   }
+  rg::pdl_trigger();
 }
 
 static int check_common(const char* who, int64_t V1, int64_t d, int64_t n_pos, int64_t K) {
@@ -668,11 +680,11 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);           \
         attr_set = true;                                                                         \
       }                                                                                          \
-      sampled_score_fwd_sparse_kernel<V><<<static_cast<unsigned>(blocks), kSparseThreads, sparse_smem, st>>>( \
+      rg::launch_pdl((sampled_score_fwd_sparse_kernel<V>), static_cast<unsigned>(blocks), kSparseThreads, sparse_smem, st,  \
           h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
           chunk, pos_per_cta);                                                                   \
     } else {                                                                                     \
-      sampled_score_fwd_kernel<V><<<static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st>>>(   \
+      rg::launch_pdl((sampled_score_fwd_kernel<V>), static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st,    \
           h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part);    \
     }                                                                                            \
   } while (0)
@@ -685,7 +697,7 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
 #undef RG_LAUNCH_SCORE
   RG_CHECK_LAUNCH("sampled_score_fwd");
   if (kind >= 0) {
-    loss_finalize_kernel<<<1, 256, 0, st>>>(part, blocks, loss_out);
+    rg::launch_pdl((loss_finalize_kernel), 1, 256, 0, st, part, blocks, loss_out);
     RG_CHECK_LAUNCH("loss_finalize");
   }
   return RECGURU_OK;
@@ -707,10 +719,10 @@ extern "C" int recguru_sampled_loss_fwd(const float* p, const float* n, int64_t 
              (long long)(blocks * 8));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float2* part = static_cast<float2*>(workspace);
-  sampled_loss_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+  rg::launch_pdl((sampled_loss_kernel), static_cast<unsigned>(blocks), 256, 0, st, 
       p, n, n_pos, static_cast<int>(K), mask, kind, dp_unit, dn_unit, part);
   RG_CHECK_LAUNCH("sampled_loss");
-  loss_finalize_kernel<<<1, 256, 0, st>>>(part, blocks, loss_out);
+  rg::launch_pdl((loss_finalize_kernel), 1, 256, 0, st, part, blocks, loss_out);
   RG_CHECK_LAUNCH("loss_finalize");
   return RECGURU_OK;
 }
@@ -733,7 +745,7 @@ extern "C" int recguru_sampled_score_bwd_dh(const float* dp, const float* dn, co
   const float4* w4 = reinterpret_cast<const float4*>(weight);
   float4* dh4 = reinterpret_cast<float4*>(dh);
 #define RG_LAUNCH_DH(V)                                                                        \
-  sampled_score_bwd_dh_kernel<V><<<static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st>>>(  \
+  rg::launch_pdl((sampled_score_bwd_dh_kernel<V>), static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st,   \
       dp, dn, scale, scale2, w4, pos, neg, n_pos, static_cast<int>(K), dh4)
   switch (d / 4) {
     case 8: RG_LAUNCH_DH(8); break;
@@ -763,7 +775,7 @@ extern "C" int recguru_candidate_scores_rank(const float* u, const float* weight
   const float4* u4 = reinterpret_cast<const float4*>(u);
   const float4* w4 = reinterpret_cast<const float4*>(weight);
 #define RG_LAUNCH_CAND(V)                                                                         \
-  candidate_rank_kernel<V><<<static_cast<unsigned>(B), kScoreWarps * 32, 0, st>>>(                \
+  rg::launch_pdl((candidate_rank_kernel<V>), static_cast<unsigned>(B), kScoreWarps * 32, 0, st,                 \
       u4, w4, target, cand, static_cast<int>(C), scores, rank)
   switch (d / 4) {
     case 8: RG_LAUNCH_CAND(8); break;
