@@ -72,6 +72,10 @@ int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d,
 /* PositionalEncoding.forward(x, mask) before dropout (Transformer/transformer.py:104-106;
  * learned variant :337-342 by passing the learned table as pe):
  *   out[t,:] = (x[t,:] + pe[t % L,:]) * mask[t]                                        */
+/* M1 alone: mask[i] = ids[i] != pad_index ? 1 : 0   (AutoEnc4Rec.py:71,:89; lets the plan of the
+ * table backward start before the gather)                                                  */
+int recguru_pad_mask(const int64_t* ids, int64_t n, int64_t pad_index, float* mask_out,
+                     recguru_stream_t stream);
 int recguru_pe_mask(const float* x, const float* pe, const float* mask, int64_t n_tokens,
                     int64_t L, int64_t d, float* out, recguru_stream_t stream);
 

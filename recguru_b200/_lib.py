@@ -35,6 +35,7 @@ SIGNATURES = {
     "recguru_launch_count": (c_i64, []),
     "recguru_gather_pe_mask": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr,
                                          c_i64, c_ptr, c_ptr, c_ptr]),
+    "recguru_pad_mask": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "recguru_pe_mask": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
     "recguru_embedding_bwd_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "recguru_embedding_bwd": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_i64, c_ptr,

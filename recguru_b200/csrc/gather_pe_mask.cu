@@ -114,6 +114,30 @@ pe_mask_kernel(const float4* __restrict__ x, const float4* __restrict__ pe,
 
 }  // namespace rg
 
+namespace rg {
+// mask[i] = ids[i] != pad_index (M1 on its own: lets the table-backward plan start before K1)
+__global__ void __launch_bounds__(256)
+pad_mask_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t pad_index, float* __restrict__ mask) {
+  rg::pdl_wait();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    mask[i] = ids[i] != pad_index ? 1.f : 0.f;
+  rg::pdl_trigger();
+}
+}  // namespace rg
+
+extern "C" int recguru_pad_mask(const int64_t* ids, int64_t n, int64_t pad_index, float* mask_out,
+                                recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(n >= 0 && (n == 0 || (ids && mask_out)), RECGURU_E_SHAPE, "pad_mask: null pointer");
+  if (n == 0) return RECGURU_OK;
+  const int64_t blocks = rg::min64(ceil_div(n, 256 * 4), kNumSMs * 8);
+  rg::launch_pdl((pad_mask_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), ids, n,
+                 pad_index, mask_out);
+  RG_CHECK_LAUNCH("pad_mask");
+  return RECGURU_OK;
+}
+
 extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d,
                                       const int64_t* ids, int64_t n_tokens, int64_t L,
                                       const float* pe, const float* mask_in, int64_t pad_index,

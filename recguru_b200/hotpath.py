@@ -56,10 +56,12 @@ class TrainHotPath:
         self.one = torch.ones(1, **f32)
         # side stream for the part of the table backward that does not depend on activations
         self.overlap_plan = overlap_plan
-        self._side = torch.cuda.Stream(device=dev)
+        # high priority: its short kernels slip in between the waves of the bandwidth-bound kernels
+        self._side = torch.cuda.Stream(device=dev, priority=-1)
         self._fork = torch.cuda.Event()
         self._join = torch.cuda.Event()
         self._planned = False
+        self._side_mask = torch.empty(B, L, **f32)
 
     # -- edge 1: ids -> activations ------------------------------------------------------
     def forward_in(self, dec_in: Tensor) -> Tensor:
@@ -81,11 +83,16 @@ class TrainHotPath:
         runs UNDER the forward pass (in a full model: under the whole transformer forward/backward)
         instead of on the critical path; :meth:`backward` joins it."""
         n = self.B * self.L
-        m = (self.mask if mask is None else mask).view(n)
         cur = torch.cuda.current_stream()
         self._fork.record(cur)
         self._side.wait_event(self._fork)
         with torch.cuda.stream(self._side):
+            if mask is None:
+                # the side stream derives the pad mask itself (a 2 us kernel), so the plan does not
+                # have to wait for K1 and can be issued at the very start of the step
+                m = ops.raw_pad_mask(dec_in, self.pad_index, out=self._side_mask).view(n)
+            else:
+                m = mask.view(n)
             ops.raw_fill_zero(self.dW)
             sites = [Site(dec_in, None, live=m), Site(dec_out, None, live=m),
                      Site(n_items, None, group=self.K, live=m)]
@@ -120,9 +127,9 @@ class TrainHotPath:
 
     def step(self, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, h: Tensor, g_x0: Tensor):
         """All edges of one step with the transformer replaced by given (h, g_x0)."""
-        self.forward_in(dec_in)
         if self.overlap_plan:
-            self.plan_backward(dec_in, dec_out, n_items)
+            self.plan_backward(dec_in, dec_out, n_items)      # needs the ids only: forked first
+        self.forward_in(dec_in)
         loss = self.forward_loss(h, dec_out, n_items)
         dh, dW = self.backward(h, dec_in, dec_out, n_items, g_x0)
         return loss, dh, dW

@@ -202,6 +202,15 @@ def raw_embedding_bwd_apply(sites: Sequence[Site], V1: int, d: int, out: Tensor,
     return out
 
 
+def raw_pad_mask(ids: Tensor, pad_index: int, out: Optional[Tensor] = None) -> Tensor:
+    """mask = (ids != pad_index) as fp32 (AutoEnc4Rec.py:71)."""
+    ids = _need(ids, torch.int64, "ids")
+    if out is None:
+        out = torch.empty(ids.shape, dtype=torch.float32, device=ids.device)
+    check(_lib.load().recguru_pad_mask(_ptr(ids), ids.numel(), int(pad_index), _ptr(out), _stream()), "pad_mask")
+    return out
+
+
 def raw_fill_zero(x: Tensor) -> Tensor:
     x = _need(x, torch.float32, "x")
     check(_lib.load().recguru_fill_zero(_ptr(x), x.numel(), _stream()), "fill_zero")
