@@ -73,7 +73,7 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // error picked up by RG_CHECK_LAUNCH
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 #endif
 
 // ---- device helpers --------------------------------------------------------------
