@@ -30,3 +30,27 @@ for name, kw in (("plan on side stream (default)", dict(overlap_plan=True)), ("e
     hp = TrainHotPath(W, pe, B, L, K, "bpr_sas", **kw)
     graphs = [hp.capture_step(tb.dec_in, tb.dec_out, tb.n_items, h, g) for tb, h, g in batches]
     print(f"{name:36s} {timeit(graphs):8.1f} us", flush=True)
+
+
+# lower bound of the overlapped schedule: the plan is not launched at all (apply re-uses the plan a
+# previous step left in the workspace: timing only)
+class NoPlan(TrainHotPath):
+    def plan_backward(self, dec_in, dec_out, n_items, mask=None):
+        cur = torch.cuda.current_stream()
+        self._fork.record(cur)
+        self._side.wait_event(self._fork)
+        with torch.cuda.stream(self._side):
+            self._join.record(self._side)
+        self._side2.wait_event(self._fork)
+        with torch.cuda.stream(self._side2):
+            ops.raw_fill_zero(self.dW)
+            self._join2.record(self._side2)
+        self._planned = True
+
+
+hp = NoPlan(W, pe, B, L, K, "bpr_sas")
+TrainHotPath.step(hp, batches[0][0].dec_in, batches[0][0].dec_out, batches[0][0].n_items, batches[0][1], batches[0][2])
+tb, h, g = batches[0]
+TrainHotPath.plan_backward(hp, tb.dec_in, tb.dec_out, tb.n_items); torch.cuda.synchronize()
+graphs = [hp.capture_step(tb.dec_in, tb.dec_out, tb.n_items, h, g) for _ in range(4)]
+print(f"{'no plan launched (lower bound)':36s} {timeit(graphs):8.1f} us", flush=True)
