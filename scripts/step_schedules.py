@@ -40,11 +40,8 @@ class NoPlan(TrainHotPath):
         self._fork.record(cur)
         self._side.wait_event(self._fork)
         with torch.cuda.stream(self._side):
-            self._join.record(self._side)
-        self._side2.wait_event(self._fork)
-        with torch.cuda.stream(self._side2):
             ops.raw_fill_zero(self.dW)
-            self._join2.record(self._side2)
+            self._join.record(self._side)
         self._planned = True
 
 
