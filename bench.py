@@ -406,6 +406,47 @@ def bench_train(D: Dist, args, peaks):
                                       batches[b]["h"], batches[b]["g"]) for b in range(n_batches)]
         ms_e2e_graph = timed_loop(D, e2e_step, K, Wm)
     ms_e2e = ms_e2e_eager if ms_e2e_graph is None else min(ms_e2e_eager, ms_e2e_graph)
+
+    # next row: negatives drawn on the device by recguru_sample_negatives instead of
+    # arriving over PCIe -- only dec_in/dec_out cross the link.  Reported beside the e2e number,
+    # not instead of it (the reference's loader samples on the host).
+    from recguru_b200.sampler import NegativeSampler
+    smp = NegativeSampler(cfg["n_items"] + 1, cfg["L"] * cfg["K"], seed=1)
+    e2e_graphs = None
+    state["primed"] = -1
+    torch.cuda.synchronize()
+    for ev in consumed:
+        ev.record()
+
+    def enqueue_copy_ids(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for k in ("dec_in", "dec_out"):
+                d_in[slot][k].copy_(pin[i % n_batches][k], non_blocking=True)
+            copied[slot].record(copy_stream)
+
+    def e2e_sampler_step(i):
+        if state["primed"] < i:
+            enqueue_copy_ids(i)
+        slot = i % 2
+        b = batches[i % n_batches]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copied[slot])
+        enqueue_copy_ids(i + 1)
+        state["primed"] = i + 1
+        smp.sample(d_in[slot]["dec_in"], out=d_in[slot]["n_items"].view(cfg["B"], -1))
+        hp.step(d_in[slot]["dec_in"], d_in[slot]["dec_out"], d_in[slot]["n_items"], b["h"], b["g"])
+        consumed[slot].record(cur)
+        loss_host.copy_(hp.sbuf["aux"][0:1], non_blocking=True)
+        cur.synchronize()
+
+    ms_e2e_smp = timed_loop(D, e2e_sampler_step, K, Wm)
+    e2e_sampler = {"value": cfg["B"] * D.world * K / (ms_e2e_smp / 1e3), "unit": "seqs/s",
+                   "ms_per_step": ms_e2e_smp / K,
+                   "h2d_bytes_per_step": sum(pin[0][k].numel() * 8 for k in ("dec_in", "dec_out")),
+                   "note": "negatives sampled on the device (recguru_sample_negatives, same law as "
+                           "data_loader.py:289-314); eager launches"}
     e2e_mode = "eager (TrainHotPath.step)" if ms_e2e == ms_e2e_eager else "cuda_graph (TrainHotPath.capture_step)"
     h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
     seqs = cfg["B"] * D.world
@@ -420,7 +461,7 @@ def bench_train(D: Dist, args, peaks):
                         "and are device resident"},
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
         "launch_mode": "eager" if args.no_graph else "cuda_graph (one graph per rotating batch)",
-        "table_adam": table_adam,
+        "table_adam": table_adam, "e2e_device_negatives": e2e_sampler,
         "ms_per_step_eager": ms_eager / K, "ms_per_step_serialised_stages": ms_serial / K,
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
         "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,
@@ -716,7 +757,7 @@ def main():
                     "table_backward": train["table_backward"], "launch_mode": train["launch_mode"],
                     "ms_per_step_eager": train["ms_per_step_eager"],
                     "ms_per_step_serialised_stages": train["ms_per_step_serialised_stages"],
-                    "table_adam": train["table_adam"]}
+                    "table_adam": train["table_adam"], "e2e_device_negatives": train["e2e_device_negatives"]}
             if gather is not None:
                 line["gather"] = gather
             line["catalog"] = cat

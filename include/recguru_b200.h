@@ -242,6 +242,20 @@ int recguru_table_adam(float* weight, float* exp_avg, float* exp_avg_sq, const f
                        int64_t n_floats, double lr, double beta1, double beta2, double eps,
                        int64_t step, recguru_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * SURVEY 8f rank 3 -- negative sampler of the training loader (data/data_loader.py:289-314):
+ *   n_items_out[b, :] ~ multinomial(weights_b, num_n, replacement=True), where weights_b is the
+ *   base weight vector over ids [0, v_size) -- uniform (alias_* NULL) or any non-negative weights
+ *   given as a Walker alias table over v_size entries (item_freq^0.75, :251-254) -- with id 0,
+ *   every id of history[b, :] (entries == pad_index ignored), val[b] and test[b] zeroed.
+ *   Deterministic in (seed, step): counter-based Philox, independent of launch geometry.
+ * ---------------------------------------------------------------------------------- */
+int recguru_sample_negatives(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
+                             const int64_t* val, const int64_t* test, int64_t v_size,
+                             const float* alias_prob, const int32_t* alias_idx, int64_t num_n,
+                             uint64_t seed, uint64_t step, int64_t* n_items_out,
+                             recguru_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ SIGNATURES = {
     "recguru_topk_merge": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
                                      c_ptr]),
     "recguru_rank_histogram": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, C.c_int, c_ptr]),
+    "recguru_sample_negatives": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
+                                           C.c_uint64, C.c_uint64, c_ptr, c_ptr]),
     "recguru_table_adam": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, C.c_double, C.c_double, C.c_double,
                                      C.c_double, c_i64, c_ptr]),
 }

@@ -1,0 +1,82 @@
+"""On-GPU negative sampler.
+
+The reference draws the L*K negatives of every training sample on the CPU inside
+``pickle_loader.__getitem__`` (data/data_loader.py:289-314): a ``np.ones(v_size)`` (or
+``item_freq ** 0.75``, :251-254) weight vector per sample, the user's sequence / val / test item
+zeroed, then ``torch.multinomial(weights, enc_maxlen * num_n, replacement=True)`` -- O(v_size)
+host work per sequence and 8 MB of H2D traffic per 1024-sequence batch at cfg2.
+:class:`NegativeSampler` draws from the same distribution on the device (rejection sampling,
+counter-based Philox: reproducible from ``(seed, step)``); only the id sequences cross PCIe.
+
+The random stream differs from ``torch.multinomial``'s, the distribution does not
+(``tests/test_gpu_sampler.py``: exclusions never drawn, chi-square against the reference weights).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _need, _ptr, _stream, check
+
+Tensor = torch.Tensor
+
+
+def build_alias(weights: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Walker/Vose alias table of a non-negative weight vector: (prob float32[n], alias int32[n])."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = w.size
+    if n == 0 or w.min() < 0 or w.sum() <= 0:
+        raise ValueError("weights must be non-negative with a positive sum")
+    p = w * (n / w.sum())
+    prob = np.ones(n, dtype=np.float64)
+    alias = np.arange(n, dtype=np.int64)
+    small = [i for i in range(n) if p[i] < 1.0]
+    large = [i for i in range(n) if p[i] >= 1.0]
+    while small and large:
+        s, l = small.pop(), large.pop()
+        prob[s], alias[s] = p[s], l
+        p[l] = p[l] + p[s] - 1.0
+        (small if p[l] < 1.0 else large).append(l)
+    return prob.astype(np.float32), alias.astype(np.int32)
+
+
+class NegativeSampler:
+    """``sample(history, val, test)`` -> ``n_items [B, num_n]`` int64 on the device.
+
+    ``v_size``: the loader's ``vocab_size_a/_b`` (ids ``1 .. v_size-1`` are candidates; 0 is the pad
+    id, ``v_size`` the EOS id).  ``item_freq``: the ``wf`` vector of the reference (raised to 0.75
+    here, data_loader.py:251-254); ``None`` = uniform."""
+
+    def __init__(self, v_size: int, num_n: int, seed: int = 0, item_freq: Optional[np.ndarray] = None,
+                 device="cuda"):
+        self.v_size, self.num_n, self.seed, self.step = int(v_size), int(num_n), int(seed), 0
+        self.device = torch.device(device)
+        self.alias_prob = self.alias_idx = None
+        if item_freq is not None:
+            w = np.power(np.asarray(item_freq, dtype=np.float64)[:self.v_size], 0.75)
+            w[0] = 0.0
+            prob, alias = build_alias(w)
+            self.alias_prob = torch.from_numpy(prob).to(self.device)
+            self.alias_idx = torch.from_numpy(alias).to(self.device)
+
+    def sample(self, history: Tensor, val: Optional[Tensor] = None, test: Optional[Tensor] = None,
+               pad_index: int = 0, step: Optional[int] = None, out: Optional[Tensor] = None) -> Tensor:
+        """``history [B, H]``: the ids to exclude per sequence (the padded sequence / ``enc_in``;
+        entries equal to ``pad_index`` or outside ``[1, v_size)`` -- the EOS id -- are ignored)."""
+        history = _need(history, torch.int64, "history")
+        B, H = history.shape
+        val = None if val is None else _need(val.view(-1), torch.int64, "val")
+        test = None if test is None else _need(test.view(-1), torch.int64, "test")
+        if out is None:
+            out = torch.empty(B, self.num_n, dtype=torch.int64, device=history.device)
+        if step is None:
+            step = self.step
+            self.step += 1
+        check(_lib.load().recguru_sample_negatives(_ptr(history), B, H, int(pad_index), _ptr(val), _ptr(test),
+                                                   self.v_size, _ptr(self.alias_prob), _ptr(self.alias_idx),
+                                                   self.num_n, self.seed, int(step), _ptr(out), _stream()),
+              "sample_negatives")
+        return out

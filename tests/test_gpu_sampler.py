@@ -1,0 +1,71 @@
+"""GPU negative sampler vs the reference's sampling law (data/data_loader.py:289-314): the weights
+vector with id 0, the sequence, val and test zeroed, multinomial with replacement.  The random
+stream is ours (Philox), so parity is distributional: exclusions are never drawn, every draw is in
+range, and the empirical frequencies match the reference weights (chi-square, 5-sigma bound)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_weights(v_size, seq, val, test, item_freq=None):
+    """The weight vector the reference hands to torch.multinomial."""
+    w = np.ones(v_size) if item_freq is None else np.power(item_freq[:v_size].astype(np.float64), 0.75)
+    w[0] = 0
+    w[np.asarray(seq)] = 0
+    w[val] = 0
+    w[test] = 0
+    return w / w.sum()
+
+
+def make_batch(B, H, v_size, seed):
+    g = np.random.default_rng(seed)
+    hist = np.zeros((B, H), dtype=np.int64)
+    seqs = []
+    for b in range(B):
+        n = int(g.integers(1, H))
+        s = g.integers(1, v_size, n)
+        hist[b, H - n:] = s                      # left padded like seq_padding
+        seqs.append(s)
+    val = g.integers(1, v_size, B)
+    test = g.integers(1, v_size, B)
+    return hist, seqs, val, test
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_sampler_distribution_and_exclusions(built_lib, weighted):
+    from recguru_b200.sampler import NegativeSampler
+    B, H, v_size, num_n = 6, 12, 60, 200_000
+    hist, seqs, val, test = make_batch(B, H, v_size, 3)
+    freq = None
+    if weighted:
+        freq = np.random.default_rng(5).integers(1, 1000, v_size + 1).astype(np.float64)
+    smp = NegativeSampler(v_size, num_n, seed=1234, item_freq=freq)
+    out = smp.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(val).cuda(), torch.from_numpy(test).cuda()).cpu().numpy()
+    assert out.shape == (B, num_n) and out.min() >= 1 and out.max() < v_size
+    for b in range(B):
+        p = reference_weights(v_size, seqs[b], val[b], test[b], freq)
+        cnt = np.bincount(out[b], minlength=v_size).astype(np.float64)
+        assert cnt[p == 0].sum() == 0                                   # exclusions never drawn
+        exp = p * num_n
+        sigma = np.sqrt(num_n * p * (1 - p))
+        assert np.all(np.abs(cnt - exp)[p > 0] < 5.5 * sigma[p > 0] + 1)  # per-id 5.5 sigma
+        chi2 = (((cnt - exp) ** 2)[p > 0] / exp[p > 0]).sum()
+        dof = int((p > 0).sum()) - 1
+        assert chi2 < dof + 6 * np.sqrt(2 * dof)                         # chi-square within 6 sigma
+
+
+def test_sampler_is_deterministic_in_seed_and_step(built_lib):
+    from recguru_b200.sampler import NegativeSampler
+    B, H, v_size, num_n = 33, 50, 5000, 1000
+    hist, seqs, val, test = make_batch(B, H, v_size, 9)
+    h, v, t = (torch.from_numpy(x).cuda() for x in (hist, val, test))
+    a = NegativeSampler(v_size, num_n, seed=7).sample(h, v, t, step=3)
+    b = NegativeSampler(v_size, num_n, seed=7).sample(h, v, t, step=3)
+    c = NegativeSampler(v_size, num_n, seed=7).sample(h, v, t, step=4)
+    d = NegativeSampler(v_size, num_n, seed=8).sample(h, v, t, step=3)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    for bi in range(B):                                                   # exclusions at a realistic size
+        bad = set(seqs[bi].tolist()) | {int(val[bi]), int(test[bi]), 0}
+        assert not (set(a[bi].cpu().tolist()) & bad)

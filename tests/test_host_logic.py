@@ -124,3 +124,23 @@ def test_product_never_imports_oracle():
     root = Path(__file__).resolve().parent.parent / "recguru_b200"
     for f in root.rglob("*.py"):
         assert not re.search(r"^\s*(from|import)\s+oracle", f.read_text(), flags=re.M), f
+
+
+def test_alias_table_reproduces_weights():
+    """Walker alias table of the negative sampler (recguru_b200/sampler.py): marginal == weights."""
+    import numpy as np
+    from recguru_b200.sampler import build_alias
+    w = np.array([0, 3, 1, 0, 6, 2.5, 0.5], dtype=np.float64)
+    prob, alias = build_alias(w)
+    n = len(w)
+    p = np.zeros(n)
+    for i in range(n):
+        p[i] += prob[i] / n
+        p[alias[i]] += (1 - prob[i]) / n
+    assert np.allclose(p, w / w.sum(), atol=1e-6)
+    g = np.random.default_rng(0).random(1000)
+    prob, alias = build_alias(g)
+    p = np.zeros(1000)
+    np.add.at(p, np.arange(1000), prob / 1000)
+    np.add.at(p, alias, (1 - prob) / 1000)
+    assert np.allclose(p, g / g.sum(), atol=1e-7)
