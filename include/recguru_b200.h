@@ -122,7 +122,8 @@ int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites, 
  * forward pass (it depends on the ids and the pad mask only, not on any activation):
  *   plan  : stable compaction of the live (id, occurrence) pairs + LSD radix sort -> workspace.
  *           Reads site.ids and site.live (else site.coef); X/scale may still be unset.
- *   apply : segmented reduce of coef * X rows over the plan, for the SAME ids/counts/groups.
+ *   apply : segmented reduce of coef * X rows over the plan, for the SAME ids/counts/groups and the
+ *           same `live` configuration (all sites sharing one mask selects compaction by row in both).
  * recguru_embedding_bwd == plan followed by apply on one stream.                              */
 int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_host, int n_sites, int64_t V1,
                                int64_t padding_idx, void* workspace, int64_t workspace_bytes,

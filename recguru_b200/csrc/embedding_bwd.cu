@@ -36,6 +36,15 @@ constexpr int kMaxBins = 1 << kMaxRadixBits;
 constexpr int kChunk = 64;                               // sorted occurrences per warp
 constexpr int kReduceWarps = 8;
 
+inline bool env_row_mode_off() {   // RECGURU_BWD_ROWMODE=0: always compact by gathered index
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RECGURU_BWD_ROWMODE");
+    v = (e && e[0] == '0') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 struct SiteTable {
   const int64_t* ids[RECGURU_MAX_SITES];
   const float* X[RECGURU_MAX_SITES];
@@ -191,6 +200,97 @@ compact_scatter_kernel(SiteTable st, int64_t total, int64_t padding_idx,
     if (rank[j] != 0xffffffffu) {
       keys[base + rank[j]] = key[j];
       vals[base + rank[j]] = static_cast<uint32_t>(warp0 + j * 32 + lane);
+    }
+  }
+  rg::pdl_trigger();
+}
+
+// ---- 1b. compaction by ROW when every site shares one liveness mask -----------------------
+// A training step's lookup sites all hang off the same positions (input id, positive, K negatives
+// of position r), and the pad mask says per position whether any of them carries gradient.  The
+// plan then compacts the 0.2 M positions instead of the 1.4 M gathered indices: 7x less to read
+// and scan, and the ids are only read for live positions.  Output order is the same as in the
+// generic path -- site-major, then position, then k == ascending occurrence index -- so the sums
+// are bit-identical.  An occurrence whose id is padding_idx at a live position (dropped by the
+// generic path) gets the key `sentinel` (= V1, sorts last) and is skipped by the reduce kernels.
+__global__ void __launch_bounds__(kSortThreads)
+row_count_kernel(const float* __restrict__ live, int64_t n_rows, uint32_t* __restrict__ tile_count) {
+  rg::pdl_wait();
+  __shared__ uint32_t s_w[kSortThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    c += (i < n_rows && live[i] != 0.f) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) s_w[warp] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) t += s_w[w];
+    tile_count[blockIdx.x] = t;
+  }
+  rg::pdl_trigger();
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kSortThreads)
+row_scatter_kernel(SiteTable st, const float* __restrict__ live, int64_t n_rows, int64_t padding_idx,
+                   uint32_t sentinel, const uint32_t* __restrict__ tile_offset,
+                   const uint32_t* __restrict__ n_live_rows, uint32_t* __restrict__ n_live_occ,
+                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  rg::pdl_wait();
+  __shared__ uint32_t s_w[kSortThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t rank[kCompactItems];   // 0xffffffff = dead
+  uint32_t run = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    const bool lv = i < n_rows && live[i] != 0.f;
+    const uint32_t b = __ballot_sync(0xffffffffu, lv);
+    rank[j] = lv ? run + __popc(b & lt_mask) : 0xffffffffu;
+    run += __popc(b);
+  }
+  if (lane == 0) s_w[warp] = run;
+  __syncthreads();
+  uint32_t base = tile_offset[blockIdx.x];
+#pragma unroll
+  for (int w = 0; w < kSortThreads / 32; ++w)
+    if (w < warp) base += s_w[w];
+  const uint32_t p_live = *n_live_rows;
+  uint32_t g_total = 0;
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2)
+    if (s2 < st.n_sites) g_total += static_cast<uint32_t>(st.group[s2]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_live_occ = p_live * g_total;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    if (rank[j] == 0xffffffffu) continue;
+    const int64_t row = warp0 + j * 32 + lane;
+    const uint32_t r = base + rank[j];
+    uint32_t gpre = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) {
+      if (s2 < st.n_sites) {
+        const uint32_t G = static_cast<uint32_t>(st.group[s2]);
+        const int64_t* ids = st.ids[s2] + row * G;
+        const uint32_t out0 = p_live * gpre + r * G;
+        const uint32_t occ0 = static_cast<uint32_t>(st.offset[s2] + row * G);
+        for (uint32_t k = 0; k < G; ++k) {
+          const int64_t id = ids[k];
+          keys[out0 + k] = id == padding_idx ? sentinel : static_cast<uint32_t>(id);
+          vals[out0 + k] = occ0 + k;
+        }
+        gpre += G;
+      }
     }
   }
   rg::pdl_trigger();
@@ -734,6 +834,20 @@ static int build_site_table(const char* who, const recguru_lookup_site_t* sites_
 }
 }  // namespace rg
 
+namespace rg {
+// All sites carry the same liveness mask over the same number of rows => compaction by row.
+static bool row_mode(const recguru_lookup_site_t* sites, int n_sites, int64_t* n_rows) {
+  if (env_row_mode_off()) return false;
+  const float* lv = sites[0].live;
+  if (lv == nullptr || sites[0].group < 1) return false;
+  const int64_t rows = sites[0].count / sites[0].group;
+  for (int s = 0; s < n_sites; ++s)
+    if (sites[s].live != lv || sites[s].group < 1 || sites[s].count != rows * sites[s].group) return false;
+  *n_rows = rows;
+  return rows > 0;
+}
+}  // namespace rg
+
 extern "C" int recguru_fill_zero(float* p, int64_t n_floats, recguru_stream_t stream) {
   using namespace rg;
   RG_REQUIRE(n_floats >= 0 && n_floats % 4 == 0 && (n_floats == 0 || (p && aligned16(p))), RECGURU_E_SHAPE,
@@ -760,15 +874,33 @@ extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_hos
   if (rc) return rc;
   if (total == 0) return RECGURU_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const SortPlan p = make_sort_plan(total, V1);
+  int64_t n_rows = 0;
+  const bool by_row = row_mode(sites_host, n_sites, &n_rows);
+  // by_row: one more key value (the sentinel V1) must sort correctly
+  const SortPlan p = make_sort_plan(total, by_row ? V1 + 1 : V1);
   RG_REQUIRE(workspace && workspace_bytes >= p.end, RECGURU_E_WORKSPACE,
              "embedding_bwd_plan: workspace %lld < %lld", (long long)workspace_bytes, (long long)p.end);
   char* ws = static_cast<char*>(workspace);
   uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(ws + p.off_tilecnt);
   uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
-  const unsigned tiles = static_cast<unsigned>(ceil_div(total, kCompactTile));
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + p.off_keys_a);
   uint32_t* va = reinterpret_cast<uint32_t*>(ws + p.off_vals_a);
+  if (by_row) {
+    const unsigned rtiles = static_cast<unsigned>(ceil_div(n_rows, kCompactTile));
+    const float* lv = sites_host[0].live;
+    rg::launch_pdl((row_count_kernel), rtiles, kSortThreads, 0, st, lv, n_rows, tile_cnt);
+    RG_CHECK_LAUNCH("row_count");
+    rg::launch_pdl((compact_scan_kernel), 1, 1024, 0, st, tile_cnt, static_cast<int>(rtiles), n_live + 1);
+    RG_CHECK_LAUNCH("compact_scan");
+    const uint32_t sentinel = static_cast<uint32_t>(V1);
+    if (n_sites <= 1) rg::launch_pdl((row_scatter_kernel<1>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va);
+    else if (n_sites <= 3) rg::launch_pdl((row_scatter_kernel<3>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va);
+    else rg::launch_pdl((row_scatter_kernel<RECGURU_MAX_SITES>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va);
+    RG_CHECK_LAUNCH("row_scatter");
+    uint32_t *sk2, *sv2;
+    return run_radix_sort(p, ws, total, n_live, false, st, &sk2, &sv2, nullptr, nullptr);
+  }
+  const unsigned tiles = static_cast<unsigned>(ceil_div(total, kCompactTile));
   if (n_sites <= 1) rg::launch_pdl((compact_count_kernel<1>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt);
   else if (n_sites <= 3) rg::launch_pdl((compact_count_kernel<3>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt);
   else rg::launch_pdl((compact_count_kernel<RECGURU_MAX_SITES>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt);
@@ -807,7 +939,10 @@ extern "C" int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_ho
     if (rc) return rc;
   }
   if (total == 0) return RECGURU_OK;
-  const SortPlan p = make_sort_plan(total, V1);
+  int64_t n_rows = 0;
+  const bool by_row = row_mode(sites_host, n_sites, &n_rows);   // the same decision the plan took
+  const int64_t pad_key = by_row ? V1 : -1;                       // sentinel key of dropped occurrences
+  const SortPlan p = make_sort_plan(total, by_row ? V1 + 1 : V1);
   const int64_t n_chunks = ceil_div(total, kChunk);
   const int64_t need = p.end + align_up(n_chunks * 2 * d * 4, 256);
   RG_REQUIRE(workspace && workspace_bytes >= need, RECGURU_E_WORKSPACE,
@@ -826,19 +961,19 @@ extern "C" int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_ho
 #define RG_LAUNCH_REDUCE(V)                                                                   \
   do {                                                                                        \
     if (n_sites <= 1)                                                                         \
-      rg::launch_pdl((chunk_reduce_kernel<V, 1>), grid, kReduceWarps * 32, 0, st, tab, sk, sv, n_live, vec, -1, \
+      rg::launch_pdl((chunk_reduce_kernel<V, 1>), grid, kReduceWarps * 32, 0, st, tab, sk, sv, n_live, vec, pad_key, \
                                                                     accumulate, dW4, partial);    \
     else if (n_sites <= 3)                                                                    \
-      rg::launch_pdl((chunk_reduce_kernel<V, 3>), grid, kReduceWarps * 32, 0, st, tab, sk, sv, n_live, vec, -1, \
+      rg::launch_pdl((chunk_reduce_kernel<V, 3>), grid, kReduceWarps * 32, 0, st, tab, sk, sv, n_live, vec, pad_key, \
                                                                     accumulate, dW4, partial);    \
     else                                                                                      \
       rg::launch_pdl((chunk_reduce_kernel<V, RECGURU_MAX_SITES>), grid, kReduceWarps * 32, 0, st,           \
-          tab, sk, sv, n_live, vec, -1, accumulate, dW4, partial);                            \
+          tab, sk, sv, n_live, vec, pad_key, accumulate, dW4, partial);                            \
     RG_CHECK_LAUNCH("chunk_reduce");                                                          \
     if (n_chunks > 1) {                                                                       \
       const unsigned g2 = static_cast<unsigned>(ceil_div(n_chunks - 1, kReduceWarps));        \
       rg::launch_pdl((span_fixup_kernel<V>), g2, kReduceWarps * 32, 0, st, sk, n_live, vec,                 \
-                                                             -1, accumulate, dW4,             \
+                                                             pad_key, accumulate, dW4,        \
                                                              partial);                        \
       RG_CHECK_LAUNCH("span_fixup");                                                          \
     }                                                                                         \

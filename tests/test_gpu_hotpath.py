@@ -99,6 +99,16 @@ def test_plan_apply_equals_fused(hp_mod):
     ops.raw_embedding_bwd_apply([ops.Site(ids_a, Xa, ca, live=live), ops.Site(ids_b, Xb, cb, group=K, live=live)],
                                 V1, d, out, ws, mode=ops.DW_PREZEROED)
     assert torch.equal(out, fused)
+    # the same plan by gathered index (distinct mask buffers => no shared-mask fast path) must give
+    # the same bits as the plan by row (one shared mask)
+    ws2 = torch.empty_like(ws)
+    live_b = live.clone()
+    ops.raw_embedding_bwd_plan([ops.Site(ids_a, None, live=live), ops.Site(ids_b, None, group=K, live=live_b)],
+                               V1, 0, ws2)
+    out_idx = torch.zeros(V1, d, device="cuda")
+    ops.raw_embedding_bwd_apply([ops.Site(ids_a, Xa, ca, live=live), ops.Site(ids_b, Xb, cb, group=K, live=live_b)],
+                                V1, d, out_idx, ws2, mode=ops.DW_PREZEROED)
+    assert torch.equal(out_idx, fused)
     # accumulate mode on top of an existing gradient
     out2 = fused.clone()
     ops.raw_embedding_bwd_apply([ops.Site(ids_a, Xa, ca, live=live), ops.Site(ids_b, Xb, cb, group=K, live=live)],
