@@ -461,6 +461,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         }
       }
     };
+    const uint32_t acc_full_addr = ptx::smem_u32(bar_acc_full);     // + 8 * slot
+    const uint32_t acc_empty_addr = ptx::smem_u32(bar_acc_empty);
+    const int n_items32 = static_cast<int>(p.n_items);               // < 2^31 (checked on the host)
     uint32_t vrA[PIPE ? 64 : 1], vrB[PIPE ? 64 : 1];   // PIPE: the two halves of a tile's accumulator row
     bool a_inflight = false;                            // PIPE: this tile's first half was requested last iteration
     for (int j = e; j < n_tiles; j += NSETS) {
@@ -469,11 +472,14 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       const uint32_t aph = (j / NACC) & 1;
       const int tile = tile_begin + j;
       const int n0 = tile * BN;                                   // slice-local item index
-      const int valid = static_cast<int>(rg::min64(BN, p.n_items - n0));
+      const int valid = min(BN, n_items32 - n0);
       const bool free_run = (dflags & 32768u) != 0;   // debug: epilogue ignores the accumulator barriers
       if ((dflags & 64u) && !free_run) break;  // debug: no accumulator handshake at all
       const long long te0 = prof ? clock64() : 0;
-      if (!free_run && !a_inflight) ptx::mbar_wait_warp(&bar_acc_full[a], aph, spin);
+      if (!free_run && !a_inflight) {
+        if (DBG && spin) ptx::mbar_wait_warp(&bar_acc_full[a], aph, true);
+        else ptx::mbar_wait_warp_addr(acc_full_addr + a * 8, aph);
+      }
       const long long te1 = (prof || trace) ? clock64() : 0;
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + a * BN;
@@ -535,7 +541,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         ptx::tmem_ld_wait_regs(vrB);
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+        if (lane == 0) ptx::mbar_arrive_addr(acc_empty_addr + a * 8);
         released = true;
         a_inflight = false;
         const int jn = j + NSETS;
@@ -585,7 +591,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           if (c0 + CH == BN) {
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+            if (lane == 0) ptx::mbar_arrive_addr(acc_empty_addr + a * 8);
             released = true;
           }
           if (dflags & 1u) {
@@ -679,7 +685,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       if (!released) {
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[a]);
+        if (lane == 0) ptx::mbar_arrive_addr(acc_empty_addr + a * 8);
       }
       if (trace && lane == 0 && quarter == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) {
         g_trace[j - kTraceFirst][3] = te1; g_trace[j - kTraceFirst][4] = clock64();

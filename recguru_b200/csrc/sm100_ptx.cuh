@@ -65,6 +65,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity), "r"(0x989680u)
       : "memory");
 }
+// Address-based variants: the 32-bit shared address is formed once outside the hot loop (the
+// generic -> shared conversion of a dynamic-smem pointer otherwise gets re-materialised per tile).
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP_A:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra WAIT_DONE_A;\n\t"
+      "bra WAIT_LOOP_A;\n\t"
+      "WAIT_DONE_A:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_warp_addr(uint32_t addr, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_addr(addr, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 // Whole-warp wait with a single polling lane: 32 lanes spinning on the same barrier word only
 // add shared-memory traffic; the others park at the warp barrier.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool spin = false) {

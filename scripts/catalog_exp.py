@@ -39,8 +39,6 @@ def run(n_items, label, k=k, **env):
 
 
 n_items = 1_000_000
-import os as _os
-_v = _os.environ.get("VARIANT", "default")
-run(n_items, _v + " top-10 1M")
-run(n_items, _v + " rank-only 1M", k=0)
-run(10_000_000, _v + " top-10 10M")
+run(n_items, "top-10 + rank (default)")
+run(n_items, "rank only (k = 0)", k=0)
+run(10_000_000, "top-10 + rank, 10M items")
