@@ -229,6 +229,9 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, BN);
     const uint32_t a_addr = ptx::smem_u32(smem + L::kOffA);
     const int reps = (dflags & 16u) ? 0 : ((dflags & 8u) ? 2 : 1);  // debug knobs
+    const uint32_t mma_acc_empty_addr = ptx::smem_u32(bar_acc_empty);
+    const uint32_t mma_acc_full_addr = ptx::smem_u32(bar_acc_full);
+    const uint32_t mma_full_addr = ptx::smem_u32(bar_full);
     ptx::mbar_wait_warp(bar_a, 0);
     ptx::tc_fence_after();
     for (int j = warp - 1; j < n_tiles; j += 2) {
@@ -237,9 +240,11 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       const int a = j % NACC;
       const uint32_t aph = (j / NACC) & 1;
       const long long tm0 = prof ? clock64() : 0;
-      if (!(dflags & 64u)) ptx::mbar_wait_warp(&bar_acc_empty[a], aph ^ 1, spin);
+      if (!DBG) ptx::mbar_wait_warp_addr(mma_acc_empty_addr + a * 8, aph ^ 1);
+      else if (!(dflags & 64u)) ptx::mbar_wait_warp(&bar_acc_empty[a], aph ^ 1, spin);
       const long long tm1 = (prof || trace) ? clock64() : 0;
-      if (!(dflags & 32u)) ptx::mbar_wait_warp(&bar_full[s], ph, spin);
+      if (!DBG) ptx::mbar_wait_warp_addr(mma_full_addr + s * 8, ph);
+      else if (!(dflags & 32u)) ptx::mbar_wait_warp(&bar_full[s], ph, spin);
       const long long tm2 = (prof || trace) ? clock64() : 0;
       ptx::tc_fence_after();
       if (leader) {
@@ -266,6 +271,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
           else if (!kCoupled) ptx::umma_commit(&bar_empty[s]);
         }
         if (dflags & 128u) ptx::mbar_arrive(&bar_acc_full[a]);     // debug: plain arrive instead of commit
+        else if (!DBG) ptx::umma_commit_addr(mma_acc_full_addr + a * 8);
         else ptx::umma_commit(&bar_acc_full[a]);  // accumulator ready for the epilogue (and stage free)
       }
       __syncwarp();

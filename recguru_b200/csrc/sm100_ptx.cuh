@@ -87,6 +87,10 @@ __device__ __forceinline__ void mbar_wait_warp_addr(uint32_t addr, uint32_t pari
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr)
+               : "memory");
+}
 // Whole-warp wait with a single polling lane: 32 lanes spinning on the same barrier word only
 // add shared-memory traffic; the others park at the warp barrier.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool spin = false) {
