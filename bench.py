@@ -345,6 +345,25 @@ def bench_train(D: Dist, args, peaks):
                   "gbs": round(adam_mb / ms_adam, 1), "frac_of_hbm_peak": round(adam_mb / ms_adam / peaks["hbm"], 3),
                   "note": "torch.optim.Adam arithmetic for the [V1,d] table in one kernel (read W,m,v,g; write W,m,v); "
                           "not included in the timed step"}
+    # sparse-gradient form: dW as a row store (no zero fill), rows stamped by mark_rows, g = 0 elsewhere
+    tb0 = batches[0]["tb"]
+    m0 = hp.mask.view(n)
+    hp.forward_in(tb0.dec_in)
+    plan_sites = [ops.Site(tb0.dec_in, None, live=m0), ops.Site(tb0.dec_out, None, live=m0),
+                  ops.Site(tb0.n_items, None, group=cfg["K"], live=m0)]
+    ops.raw_embedding_bwd_plan(plan_sites, hp.V1, 0, hp.ws_bwd)
+    row_epoch = torch.zeros(hp.V1, dtype=torch.int32, device=dev)
+    ms_mark = timed_loop(D, lambda i: ops.raw_embedding_bwd_mark_rows(plan_sites, hp.V1, hp.ws_bwd, row_epoch, 1),
+                         max(K, 10), Wm) / max(K, 10)
+    rows_live = int((row_epoch == 1).sum().item())
+    ms_adam_rows = timed_loop(D, lambda i: opt.step_rows(hp.dW, row_epoch, 1), max(K, 10), Wm) / max(K, 10)
+    rows_mb = (6 * W.numel() * 4 + rows_live * cfg["d"] * 4 + hp.V1 * 4) / 1e6
+    table_adam["row_store"] = {
+        "ms": round(ms_adam_rows, 4), "mark_rows_ms": round(ms_mark, 4), "rows_with_gradient": rows_live,
+        "algorithmic_mb": round(rows_mb, 1), "gbs": round(rows_mb / ms_adam_rows, 1),
+        "frac_of_hbm_peak": round(rows_mb / ms_adam_rows / peaks["hbm"], 3),
+        "note": "recguru_table_adam_rows: same arithmetic, gradient rows read only where the table backward "
+                "wrote them (TrainHotPath(dense_grad=False)); also removes the 4*V1*d zero fill of dW from the step"}
     del w_adam, opt
 
     # ---- end to end through the public API with host buffers ----
@@ -447,6 +466,41 @@ def bench_train(D: Dist, args, peaks):
                    "h2d_bytes_per_step": sum(pin[0][k].numel() * 8 for k in ("dec_in", "dec_out")),
                    "note": "negatives sampled on the device (recguru_sample_negatives, same law as "
                            "data_loader.py:289-314); eager launches"}
+    # next row (second half): the dataset resident in HBM in ragged form
+    # (recguru_b200.loader.SequenceStore), rows built by recguru_build_batches, negatives by the
+    # device sampler -- the only per-step host input left is the batch's user indices (8 B each).
+    from recguru_b200.loader import SequenceStore
+    eos = cfg["n_items"] + 1
+    ragged = []
+    for t in host:                                      # histories back from the padded rows
+        for row in t.enc_in.numpy():
+            ragged.append(row[(row != 0) & (row != eos)])
+    store = SequenceStore(ragged, None, None, eos, cfg["L"])
+    idx_pin = [torch.arange(b * cfg["B"], (b + 1) * cfg["B"], dtype=torch.int64).pin_memory()
+               for b in range(n_batches)]
+    idx_dev = [torch.empty(cfg["B"], dtype=torch.int64, device=dev) for _ in range(2)]
+    rows = [store.train_batch(idx_dev[s].copy_(idx_pin[s])) for s in range(2)]
+    for s in range(2):                                   # the builder reproduces the host-built rows
+        assert torch.equal(rows[s].dec_in, batches[s]["tb"].dec_in) and \
+            torch.equal(rows[s].dec_out, batches[s]["tb"].dec_out), "device-built rows differ from the host rows"
+
+    def e2e_builder_step(i):
+        slot = i % 2
+        b = batches[i % n_batches]
+        idx_dev[slot].copy_(idx_pin[i % n_batches], non_blocking=True)
+        r = store.train_batch(idx_dev[slot], out=rows[slot])
+        smp.sample(r.enc_in, out=d_in[slot]["n_items"].view(cfg["B"], -1))
+        hp.step(r.dec_in, r.dec_out, d_in[slot]["n_items"], b["h"], b["g"])
+        loss_host.copy_(hp.sbuf["aux"][0:1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e_bld = timed_loop(D, e2e_builder_step, K, Wm)
+    e2e_builder = {"value": cfg["B"] * D.world * K / (ms_e2e_bld / 1e3), "unit": "seqs/s",
+                   "ms_per_step": ms_e2e_bld / K, "h2d_bytes_per_step": cfg["B"] * 8, "d2h_bytes_per_step": 4,
+                   "resident_dataset_bytes": int(store.items.numel() * 8 + store.offsets.numel() * 8),
+                   "note": "ragged histories resident in HBM (SequenceStore), rows built on the device "
+                           "(recguru_build_batches = seq_padding, data_loader.py:25-36), negatives sampled on the "
+                           "device; only the batch's user indices cross PCIe; eager launches"}
     e2e_mode = "eager (TrainHotPath.step)" if ms_e2e == ms_e2e_eager else "cuda_graph (TrainHotPath.capture_step)"
     h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
     seqs = cfg["B"] * D.world
@@ -461,7 +515,7 @@ def bench_train(D: Dist, args, peaks):
                         "and are device resident"},
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
         "launch_mode": "eager" if args.no_graph else "cuda_graph (one graph per rotating batch)",
-        "table_adam": table_adam, "e2e_device_negatives": e2e_sampler,
+        "table_adam": table_adam, "e2e_device_negatives": e2e_sampler, "e2e_device_batches": e2e_builder,
         "ms_per_step_eager": ms_eager / K, "ms_per_step_serialised_stages": ms_serial / K,
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
         "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,

@@ -243,6 +243,24 @@ int recguru_table_adam(float* weight, float* exp_avg, float* exp_avg_sq, const f
                        int64_t n_floats, double lr, double beta1, double beta2, double eps,
                        int64_t step, recguru_stream_t stream);
 
+/* Sparse-gradient form of the two calls above ("directly from K2's segmented
+ * output without materialising a dense grad"): run recguru_embedding_bwd_apply with
+ * RECGURU_DW_PREZEROED on a dW buffer that is NOT zeroed (a row store: only the rows of this
+ * step's lookups are written), then
+ *   recguru_embedding_bwd_mark_rows: row_epoch[row] = epoch for every row the apply stage wrote
+ *     (same sites / workspace as the plan; row_epoch uint32 [V1], zeroed once at allocation,
+ *      epochs count from 1 so it never needs clearing);
+ *   recguru_table_adam_rows: the Adam arithmetic of recguru_table_adam with
+ *     g = row_epoch[row] == epoch ? grad_rows[row, :] : 0 -- bit-identical to the dense call on
+ *     a zero-filled gradient, minus the 4*V1*d zero fill and the reads of untouched rows. */
+int recguru_embedding_bwd_mark_rows(const recguru_lookup_site_t* sites, int n_sites, int64_t V1,
+                                    const void* workspace, int64_t workspace_bytes,
+                                    uint32_t* row_epoch, uint32_t epoch, recguru_stream_t stream);
+int recguru_table_adam_rows(float* weight, float* exp_avg, float* exp_avg_sq, const float* grad_rows,
+                            const uint32_t* row_epoch, uint32_t epoch, int64_t V1, int64_t d,
+                            double lr, double beta1, double beta2, double eps, int64_t step,
+                            recguru_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * SURVEY 8f rank 3 -- negative sampler of the training loader (data/data_loader.py:289-314):
  *   n_items_out[b, :] ~ multinomial(weights_b, num_n, replacement=True), where weights_b is the
@@ -256,6 +274,26 @@ int recguru_sample_negatives(const int64_t* history, int64_t B, int64_t H, int64
                              const float* alias_prob, const int32_t* alias_idx, int64_t num_n,
                              uint64_t seed, uint64_t step, int64_t* n_items_out,
                              recguru_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * SURVEY 8f rank 3 (second half) -- batch builder of the loaders:
+ *   seq_padding  (data/data_loader.py:25-36)  mode RECGURU_BATCH_TRAIN -> enc_in, dec_in, dec_out
+ *   test_seq_gen (data/data_loader.py:39-55)  mode RECGURU_BATCH_EVAL  -> enc_in, dec_in
+ *       (call once with append = NULL for (eval_enc_in, dec_in) and once with append = val for
+ *        (test_enc_in, t_dec_in): the appended item is the per-user array indexed like val/test)
+ *   The dataset is resident in ragged form: items[] (all histories back to back, the "seq" lists
+ *   of the pickles) and offsets[n_users + 1]; user_idx[B] selects the batch (NULL = users 0..B-1).
+ *   enc_in [B, enc_len], dec_in / dec_out [B, dec_len] int64, any of them may be NULL;
+ *   requires 2 <= enc_len, 1 <= dec_len <= enc_len.  val_out / test_out [B] (optional) receive
+ *   val[user_idx[b]] / test[user_idx[b]] (the targets the loaders return beside the rows).
+ * ---------------------------------------------------------------------------------- */
+#define RECGURU_BATCH_TRAIN 0
+#define RECGURU_BATCH_EVAL 1
+int recguru_build_batches(const int64_t* items, const int64_t* offsets, const int64_t* user_idx,
+                          const int64_t* append, int64_t B, int64_t enc_len, int64_t dec_len,
+                          int64_t eos, int mode, int64_t* enc_in, int64_t* dec_in, int64_t* dec_out,
+                          const int64_t* val, const int64_t* test, int64_t* val_out,
+                          int64_t* test_out, recguru_stream_t stream);
 
 #ifdef __cplusplus
 }

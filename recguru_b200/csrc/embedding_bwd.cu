@@ -991,6 +991,51 @@ extern "C" int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_ho
   return RECGURU_OK;
 }
 
+// Row liveness for the sparse-gradient consumers (recguru_table_adam_rows): every table row that
+// owns a run of the sorted plan -- exactly the rows chunk_reduce / span_fixup write -- gets
+// row_epoch[row] = epoch.  One thread per sorted occurrence; run starts only.
+namespace rg {
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ n_live, uint32_t key_limit,
+                 uint32_t epoch, uint32_t* __restrict__ row_epoch) {
+  rg::pdl_wait();
+  const int64_t total = *n_live;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const uint32_t k = skeys[i];
+    if (k < key_limit && (i == 0 || skeys[i - 1] != k)) row_epoch[k] = epoch;
+  }
+  rg::pdl_trigger();
+}
+}  // namespace rg
+
+extern "C" int recguru_embedding_bwd_mark_rows(const recguru_lookup_site_t* sites_host, int n_sites, int64_t V1,
+                                               const void* workspace, int64_t workspace_bytes,
+                                               uint32_t* row_epoch, uint32_t epoch, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "embedding_bwd_mark_rows: bad V1");
+  RG_REQUIRE(row_epoch != nullptr, RECGURU_E_SHAPE, "embedding_bwd_mark_rows: null row_epoch");
+  SiteTable tab;
+  int64_t total = 0;
+  int rc = build_site_table("embedding_bwd_mark_rows", sites_host, n_sites, false, &tab, &total);
+  if (rc) return rc;
+  if (total == 0) return RECGURU_OK;
+  int64_t n_rows = 0;
+  const bool by_row = row_mode(sites_host, n_sites, &n_rows);   // the same decision the plan took
+  const SortPlan p = make_sort_plan(total, by_row ? V1 + 1 : V1);
+  RG_REQUIRE(workspace && workspace_bytes >= p.end, RECGURU_E_WORKSPACE,
+             "embedding_bwd_mark_rows: workspace %lld < %lld", (long long)workspace_bytes, (long long)p.end);
+  const char* ws = static_cast<const char*>(workspace);
+  const uint32_t* n_live = reinterpret_cast<const uint32_t*>(ws + p.off_nlive);
+  const uint32_t* sk = reinterpret_cast<const uint32_t*>(ws + ((p.passes & 1) ? p.off_keys_b : p.off_keys_a));
+  const unsigned blocks = static_cast<unsigned>(rg::min64(ceil_div(total, 256), kNumSMs * 8));
+  // keys >= V1 are the by-row sentinel of dropped occurrences (padding ids at live rows)
+  rg::launch_pdl((mark_rows_kernel), blocks, 256, 0, static_cast<cudaStream_t>(stream), sk, n_live,
+                 static_cast<uint32_t>(V1), epoch, row_epoch);
+  RG_CHECK_LAUNCH("mark_rows");
+  return RECGURU_OK;
+}
+
 extern "C" int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites,
                                      int64_t d, int64_t V1, int64_t padding_idx, float* dW,
                                      int zero_fill, void* workspace, int64_t workspace_bytes,

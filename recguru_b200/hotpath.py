@@ -28,7 +28,7 @@ class TrainHotPath:
 
     def __init__(self, weight: Tensor, pe: Tensor, B: int, L: int, K: int, kind: str = "bpr_sas",
                  pad_index: int = 0, padding_idx: Optional[int] = 0, skip_masked: bool = True,
-                 overlap_plan: bool = True):
+                 overlap_plan: bool = True, dense_grad: bool = True):
         assert weight.is_cuda and weight.dtype == torch.float32
         self.weight = weight
         self.pe = pe[0] if pe.dim() == 3 else pe
@@ -51,6 +51,12 @@ class TrainHotPath:
         }
         self.dh = torch.empty(B, L, d, **f32)
         self.dW = torch.empty(V1, d, **f32)
+        # dense_grad=False: dW is a row store -- no zero fill, only the rows of this
+        # step's lookups are written and stamped row_epoch[row] = epoch; consumed by
+        # FusedTableAdam.step_rows.  dense_grad=True keeps the reference's dense-gradient contract.
+        self.dense_grad = dense_grad
+        self.row_epoch = None if dense_grad else torch.zeros(V1, dtype=torch.int32, device=dev)
+        self.epoch = 0
         total = n * (2 + K)
         self.ws_bwd = torch.empty(ops.embedding_bwd_workspace_bytes(total, V1, d), dtype=torch.uint8, device=dev)
         self.one = torch.ones(1, **f32)
@@ -93,10 +99,14 @@ class TrainHotPath:
                 m = ops.raw_pad_mask(dec_in, self.pad_index, out=self._side_mask).view(n)
             else:
                 m = mask.view(n)
-            ops.raw_fill_zero(self.dW)
+            if self.dense_grad:
+                ops.raw_fill_zero(self.dW)
             sites = [Site(dec_in, None, live=m), Site(dec_out, None, live=m),
                      Site(n_items, None, group=self.K, live=m)]
             ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
+            if not self.dense_grad:
+                self.epoch += 1
+                ops.raw_embedding_bwd_mark_rows(sites, self.V1, self.ws_bwd, self.row_epoch, self.epoch)
             self._join.record(self._side)
         self._planned = True
 
@@ -120,9 +130,14 @@ class TrainHotPath:
             torch.cuda.current_stream().wait_event(self._join)
             ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
             self._planned = False
-        else:
+        elif self.dense_grad:
             ops.raw_embedding_bwd(sites, self.V1, self.d, self.padding_idx, out=self.dW, zero_fill=True,
                                   workspace=self.ws_bwd)
+        else:
+            ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
+            ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
+            self.epoch += 1
+            ops.raw_embedding_bwd_mark_rows(sites, self.V1, self.ws_bwd, self.row_epoch, self.epoch)
         return self.dh, self.dW
 
     def step(self, dec_in: Tensor, dec_out: Tensor, n_items: Tensor, h: Tensor, g_x0: Tensor):
@@ -142,6 +157,10 @@ class TrainHotPath:
         allocation, no synchronisation, the live-index count of the table backward stays on the
         device.  Refill the input buffers in place, then ``graph.replay()``; results land in
         ``sbuf['aux'][0]`` (loss), ``dh`` and ``dW``."""
+        if not self.dense_grad:
+            # the row-store epoch is a host-side counter passed by value: a replayed graph would stamp
+            # every step with the captured epoch and stale rows of earlier replays would look live
+            raise RuntimeError("recguru: capture_step needs dense_grad=True (the row-store epoch is a launch argument)")
         warm = torch.cuda.Stream()
         warm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(warm):

@@ -202,6 +202,22 @@ def raw_embedding_bwd_apply(sites: Sequence[Site], V1: int, d: int, out: Tensor,
     return out
 
 
+def raw_embedding_bwd_mark_rows(sites: Sequence[Site], V1: int, workspace: Tensor, row_epoch: Tensor,
+                                epoch: int) -> Tensor:
+    """``row_epoch[row] = epoch`` for every table row the apply stage writes for the plan left in
+    ``workspace`` (same sites as the plan).  ``row_epoch``: int32/uint32-sized ``[V1]`` tensor, zeroed
+    once; epochs count from 1.  Feeds :func:`raw_table_adam_rows`."""
+    arr, keep, total = _marshal_sites(sites, None)
+    workspace = _need(workspace, torch.uint8, "workspace")
+    row_epoch = _need(row_epoch, torch.int32, "row_epoch")
+    if row_epoch.numel() != V1 or not row_epoch.is_contiguous():
+        raise RuntimeError("recguru: row_epoch must be a contiguous int32 [V1] tensor")
+    check(_lib.load().recguru_embedding_bwd_mark_rows(arr, len(sites), V1, _ptr(workspace), workspace.numel(),
+                                                      _ptr(row_epoch), int(epoch) & 0xFFFFFFFF, _stream()),
+          "embedding_bwd_mark_rows")
+    return row_epoch
+
+
 def raw_pad_mask(ids: Tensor, pad_index: int, out: Optional[Tensor] = None) -> Tensor:
     """mask = (ids != pad_index) as fp32 (AutoEnc4Rec.py:71)."""
     ids = _need(ids, torch.int64, "ids")
@@ -453,6 +469,28 @@ def raw_table_adam(weight: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, grad: Te
     check(lib.recguru_table_adam(_ptr(weight), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(bufs[3]), weight.numel(),
                                  float(lr), float(beta1), float(beta2), float(eps), int(step), _stream()),
           "table_adam")
+
+
+def raw_table_adam_rows(weight: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, grad_rows: Tensor,
+                        row_epoch: Tensor, epoch: int, lr: float, beta1: float, beta2: float, eps: float,
+                        step: int) -> None:
+    """:func:`raw_table_adam` with the gradient given as a row store: rows whose ``row_epoch`` differs
+    from ``epoch`` take g = 0 and are not read (bit-identical to the dense call on a zero-filled
+    gradient)."""
+    lib = _lib.load()
+    bufs = [_need(t, torch.float32, n) for t, n in ((weight, "weight"), (exp_avg, "exp_avg"),
+                                                    (exp_avg_sq, "exp_avg_sq"), (grad_rows, "grad_rows"))]
+    if any(not t.is_contiguous() for t in (weight, exp_avg, exp_avg_sq, grad_rows)):
+        raise RuntimeError("recguru: table_adam_rows: weight, moments and the row store must be contiguous")
+    if weight.dim() != 2 or len({tuple(t.shape) for t in bufs}) != 1:
+        raise RuntimeError("recguru: table_adam_rows: weight, moments and grad_rows must all be [V1, d]")
+    V1, d = weight.shape
+    row_epoch = _need(row_epoch, torch.int32, "row_epoch")
+    if row_epoch.numel() != V1 or not row_epoch.is_contiguous():
+        raise RuntimeError("recguru: row_epoch must be a contiguous int32 [V1] tensor")
+    check(lib.recguru_table_adam_rows(_ptr(weight), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(grad_rows),
+                                      _ptr(row_epoch), int(epoch) & 0xFFFFFFFF, V1, d, float(lr), float(beta1),
+                                      float(beta2), float(eps), int(step), _stream()), "table_adam_rows")
 
 
 # --------------------------------------------------------------------------------------

@@ -14,6 +14,12 @@ Usage next to the reference's optimizer::
     ...
     opt_rest.step(); opt_table.step()                  # uses table.grad, or pass grad=hp.dW
 
+Sparse-gradient form ("without materialising a dense grad"): with
+``TrainHotPath(..., dense_grad=False)`` the table backward writes only the rows of the step's
+lookups into ``hp.dW`` (no zero fill) and stamps them in ``hp.row_epoch``;
+``opt_table.step_rows(hp.dW, hp.row_epoch, hp.epoch)`` then applies dense-equivalent Adam
+(untouched rows: g = 0) bit-identically to the dense call.
+
 ``param_groups`` mirrors torch's layout far enough for ``ScheduledOptim`` to set ``['lr']``.
 """
 from __future__ import annotations
@@ -45,6 +51,18 @@ class FusedTableAdam:
         w = self.weight.data if isinstance(self.weight, torch.nn.Parameter) else self.weight
         ops.raw_table_adam(w, self.state["exp_avg"], self.state["exp_avg_sq"], g.contiguous(), grp["lr"],
                            grp["betas"][0], grp["betas"][1], grp["eps"], self.state["step"])
+
+    @torch.no_grad()
+    def step_rows(self, grad_rows: Tensor, row_epoch: Tensor, epoch: int) -> None:
+        """The same update from a ROW STORE instead of a dense gradient: ``grad_rows [V1, d]`` is valid
+        only where ``row_epoch[row] == epoch`` (``TrainHotPath(dense_grad=False)`` produces the pair);
+        all other rows take g = 0 without being read.  Bit-identical to :meth:`step` on the
+        zero-filled gradient; saves the dense zero fill and the reads of untouched rows."""
+        grp = self.param_groups[0]
+        self.state["step"] += 1
+        w = self.weight.data if isinstance(self.weight, torch.nn.Parameter) else self.weight
+        ops.raw_table_adam_rows(w, self.state["exp_avg"], self.state["exp_avg_sq"], grad_rows, row_epoch, epoch,
+                                grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"], self.state["step"])
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         if isinstance(self.weight, torch.nn.Parameter) and self.weight.grad is not None:

@@ -165,3 +165,58 @@ def test_seq_padding_kats():
     # longer than the window: keeps the most recent items
     e, di, do = O.seq_padding(list(range(1, 11)), 6, 6, 99)
     assert e.tolist() == [6, 7, 8, 9, 10, 99]
+
+
+def _batch_cases():
+    g = load_golden("batch_layouts.npz")
+    for c in range(int(g["n_cases"])):
+        yield {k[len(f"c{c}_"):]: v for k, v in g.items() if k.startswith(f"c{c}_")}
+
+
+def test_batch_layouts_golden():
+    """oracle seq_padding / test_seq_gen against rows built by the reference's own functions
+    (oracle/make_golden_batches.py): empty, short, window-sized and over-long histories, decoder
+    window shorter than the encoder window, val pushing a history over the window."""
+    n = 0
+    for c in _batch_cases():
+        Le, Ld, eos = (int(x) for x in c["dims"])
+        off = c["offsets"]
+        for b in range(len(off) - 1):
+            seq = c["items"][off[b]:off[b + 1]].tolist()
+            e, di, do = O.seq_padding(seq, Le, Ld, eos)
+            assert e.tolist() == c["enc_in"][b].tolist()
+            assert di.tolist() == c["dec_in"][b].tolist() and do.tolist() == c["dec_out"][b].tolist()
+            ee, edi, te, tdi = O.test_seq_gen(seq, Le, Ld, eos, int(c["val"][b]))
+            assert ee.tolist() == c["eval_enc_in"][b].tolist() and edi.tolist() == c["eval_dec_in"][b].tolist()
+            assert te.tolist() == c["test_enc_in"][b].tolist() and tdi.tolist() == c["t_dec_in"][b].tolist()
+            n += 1
+    assert n >= 200
+
+
+def test_batch_layout_closed_form_matches_golden():
+    """The closed form recguru_build_batches evaluates per output element (csrc/batch_builder.cu
+    header), restated in numpy, against the reference-built rows: host-side check of the index
+    algebra that runs without a GPU."""
+    def rows(items, off, extra, Le, Ld, eos, shift_in, first_zero):
+        B = len(off) - 1
+        enc = np.zeros((B, Le), dtype=np.int64)
+        dec = np.zeros((B, Ld), dtype=np.int64)
+        for b in range(B):
+            seq = items[off[b]:off[b + 1]].tolist() + ([] if extra is None else [int(extra[b])])
+            n = len(seq)
+            E = lambda j: eos if j == Le - 1 else (seq[j - (Le - 1 - n)] if j - (Le - 1 - n) >= 0 else 0)
+            enc[b] = [E(j) for j in range(Le)]
+            for jd in range(Ld):
+                J = Le - Ld + jd
+                dec[b, jd] = 0 if J < first_zero else E(J - shift_in)
+        return enc, dec
+    for c in _batch_cases():
+        Le, Ld, eos = (int(x) for x in c["dims"])
+        enc, dec_in = rows(c["items"], c["offsets"], None, Le, Ld, eos, 2, 2)
+        _, dec_out = rows(c["items"], c["offsets"], None, Le, Ld, eos, 1, 2)
+        assert np.array_equal(enc, c["enc_in"]) and np.array_equal(dec_in, c["dec_in"])
+        assert np.array_equal(dec_out, c["dec_out"])
+        enc, dec = rows(c["items"], c["offsets"], None, Le, Ld, eos, 1, 1)
+        assert np.array_equal(enc, c["eval_enc_in"]) and np.array_equal(dec, c["eval_dec_in"])
+        enc, dec = rows(c["items"], c["offsets"], c["val"], Le, Ld, eos, 1, 1)
+        assert np.array_equal(enc, c["test_enc_in"]) and np.array_equal(dec, c["t_dec_in"])
