@@ -494,13 +494,53 @@ def bench_train(D: Dist, args, peaks):
         loss_host.copy_(hp.sbuf["aux"][0:1], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    ms_e2e_bld = timed_loop(D, e2e_builder_step, K, Wm)
+    bld_graphs = None
+    ms_e2e_bld_eager = timed_loop(D, e2e_builder_step, K, Wm)
+    ms_e2e_bld_graph = None
+    if not args.no_graph:
+        # the same chain as ONE CUDA graph per rotating batch: rows, negatives (the sampler reads its
+        # step from a device counter that the graph itself advances, so every replay draws fresh
+        # negatives), then the step's kernels; the index copy and the loss read-back stay outside
+        step_dev = torch.full((1,), 1 << 20, dtype=torch.int64, device=dev)
+
+        def chain(bi):
+            slot = bi % 2
+            r = store.train_batch(idx_dev[slot], out=rows[slot])
+            smp.sample(r.enc_in, out=d_in[slot]["n_items"].view(cfg["B"], -1), step_dev=step_dev)
+            smp.advance(step_dev)
+            hp.step(r.dec_in, r.dec_out, d_in[slot]["n_items"], batches[bi]["h"], batches[bi]["g"])
+
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            for bi in range(n_batches):
+                chain(bi)
+        torch.cuda.current_stream().wait_stream(warm)
+        bld_graphs = []
+        for bi in range(n_batches):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                chain(bi)
+            bld_graphs.append(gph)
+
+        def e2e_builder_graph_step(i):
+            bi = i % n_batches
+            idx_dev[bi % 2].copy_(idx_pin[bi], non_blocking=True)
+            bld_graphs[bi].replay()
+            loss_host.copy_(hp.sbuf["aux"][0:1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        ms_e2e_bld_graph = timed_loop(D, e2e_builder_graph_step, K, Wm)
+    ms_e2e_bld = ms_e2e_bld_eager if ms_e2e_bld_graph is None else min(ms_e2e_bld_eager, ms_e2e_bld_graph)
     e2e_builder = {"value": cfg["B"] * D.world * K / (ms_e2e_bld / 1e3), "unit": "seqs/s",
                    "ms_per_step": ms_e2e_bld / K, "h2d_bytes_per_step": cfg["B"] * 8, "d2h_bytes_per_step": 4,
+                   "ms_per_step_eager": ms_e2e_bld_eager / K,
+                   "ms_per_step_graph": None if ms_e2e_bld_graph is None else ms_e2e_bld_graph / K,
                    "resident_dataset_bytes": int(store.items.numel() * 8 + store.offsets.numel() * 8),
                    "note": "ragged histories resident in HBM (SequenceStore), rows built on the device "
                            "(recguru_build_batches = seq_padding, data_loader.py:25-36), negatives sampled on the "
-                           "device; only the batch's user indices cross PCIe; eager launches"}
+                           "device; only the batch's user indices cross PCIe; value = the faster of eager launches and one "
+                           "CUDA graph per batch (sampler step read from a device counter the graph advances)"}
     e2e_mode = "eager (TrainHotPath.step)" if ms_e2e == ms_e2e_eager else "cuda_graph (TrainHotPath.capture_step)"
     h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
     seqs = cfg["B"] * D.world
@@ -811,7 +851,8 @@ def main():
                     "table_backward": train["table_backward"], "launch_mode": train["launch_mode"],
                     "ms_per_step_eager": train["ms_per_step_eager"],
                     "ms_per_step_serialised_stages": train["ms_per_step_serialised_stages"],
-                    "table_adam": train["table_adam"], "e2e_device_negatives": train["e2e_device_negatives"]}
+                    "table_adam": train["table_adam"], "e2e_device_negatives": train["e2e_device_negatives"],
+                    "e2e_device_batches": train["e2e_device_batches"]}
             if gather is not None:
                 line["gather"] = gather
             line["catalog"] = cat

@@ -274,6 +274,17 @@ int recguru_sample_negatives(const int64_t* history, int64_t B, int64_t H, int64
                              const float* alias_prob, const int32_t* alias_idx, int64_t num_n,
                              uint64_t seed, uint64_t step, int64_t* n_items_out,
                              recguru_stream_t stream);
+/* Same, with the step read from device memory at kernel time (its low 32 bits are the Philox
+ * counter word, as above) so that the call can sit in a CUDA graph: replay, then
+ * recguru_counter_add(step_dev, 1) inside the same graph, and every replay draws fresh negatives
+ * identical to the immediate-step call with that step value. */
+int recguru_sample_negatives_devstep(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
+                                     const int64_t* val, const int64_t* test, int64_t v_size,
+                                     const float* alias_prob, const int32_t* alias_idx,
+                                     int64_t num_n, uint64_t seed, const uint64_t* step_dev,
+                                     int64_t* n_items_out, recguru_stream_t stream);
+/* *counter += inc on the stream (a one-thread kernel; graph-capturable step bookkeeping). */
+int recguru_counter_add(uint64_t* counter, uint64_t inc, recguru_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * SURVEY 8f rank 3 (second half) -- batch builder of the loaders:

@@ -69,6 +69,9 @@ SIGNATURES = {
     "recguru_rank_histogram": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, C.c_int, c_ptr]),
     "recguru_sample_negatives": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
                                            C.c_uint64, C.c_uint64, c_ptr, c_ptr]),
+    "recguru_sample_negatives_devstep": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
+                                                   c_i64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
+    "recguru_counter_add": (C.c_int, [c_ptr, C.c_uint64, c_ptr]),
     "recguru_embedding_bwd_mark_rows": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_ptr, c_i64, c_ptr, C.c_uint32, c_ptr]),
     "recguru_table_adam_rows": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_uint32, c_i64, c_i64, C.c_double,
                                           C.c_double, C.c_double, C.c_double, c_i64, c_ptr]),

@@ -42,8 +42,10 @@ sample_negatives_kernel(const int64_t* __restrict__ history, int H, int64_t pad_
                         const int64_t* __restrict__ val, const int64_t* __restrict__ test,
                         uint32_t v_size, const float* __restrict__ alias_prob,
                         const int32_t* __restrict__ alias_idx, int64_t num_n, uint32_t seed_lo,
-                        uint32_t seed_hi, uint32_t step, int64_t* __restrict__ out) {
+                        uint32_t seed_hi, uint32_t step, const uint64_t* __restrict__ step_dev,
+                        int64_t* __restrict__ out) {
   rg::pdl_wait();
+  if (step_dev != nullptr) step = static_cast<uint32_t>(*step_dev);   // device-side step counter (CUDA graphs)
   extern __shared__ int s_hist[];
   __shared__ int s_n;
   const int64_t b = blockIdx.x;
@@ -90,11 +92,53 @@ sample_negatives_kernel(const int64_t* __restrict__ history, int H, int64_t pad_
 
 }  // namespace rg
 
+namespace rg {
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) {
+  rg::pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += inc;
+  rg::pdl_trigger();
+}
+}  // namespace rg
+
+extern "C" int recguru_counter_add(uint64_t* counter, uint64_t inc, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(counter != nullptr, RECGURU_E_SHAPE, "counter_add: null counter");
+  rg::launch_pdl((counter_add_kernel), 1, 32, 0, static_cast<cudaStream_t>(stream), counter, inc);
+  RG_CHECK_LAUNCH("counter_add");
+  return RECGURU_OK;
+}
+
+static int sample_negatives_impl(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
+                                 const int64_t* val, const int64_t* test, int64_t v_size,
+                                 const float* alias_prob, const int32_t* alias_idx, int64_t num_n,
+                                 uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                 int64_t* n_items_out, recguru_stream_t stream);
+
 extern "C" int recguru_sample_negatives(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
                                         const int64_t* val, const int64_t* test, int64_t v_size,
                                         const float* alias_prob, const int32_t* alias_idx,
                                         int64_t num_n, uint64_t seed, uint64_t step,
                                         int64_t* n_items_out, recguru_stream_t stream) {
+  return sample_negatives_impl(history, B, H, pad_index, val, test, v_size, alias_prob, alias_idx, num_n, seed,
+                               step, nullptr, n_items_out, stream);
+}
+
+extern "C" int recguru_sample_negatives_devstep(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
+                                                const int64_t* val, const int64_t* test, int64_t v_size,
+                                                const float* alias_prob, const int32_t* alias_idx,
+                                                int64_t num_n, uint64_t seed, const uint64_t* step_dev,
+                                                int64_t* n_items_out, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(step_dev != nullptr, RECGURU_E_SHAPE, "sample_negatives_devstep: null step counter");
+  return sample_negatives_impl(history, B, H, pad_index, val, test, v_size, alias_prob, alias_idx, num_n, seed,
+                               0, step_dev, n_items_out, stream);
+}
+
+static int sample_negatives_impl(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
+                                 const int64_t* val, const int64_t* test, int64_t v_size,
+                                 const float* alias_prob, const int32_t* alias_idx, int64_t num_n,
+                                 uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                 int64_t* n_items_out, recguru_stream_t stream) {
   using namespace rg;
   RG_REQUIRE(B >= 0 && H >= 0 && num_n >= 0 && v_size >= 2 && v_size < (1ll << 31), RECGURU_E_SHAPE,
              "sample_negatives: bad sizes B=%lld H=%lld num_n=%lld v_size=%lld", (long long)B, (long long)H,
@@ -107,7 +151,7 @@ extern "C" int recguru_sample_negatives(const int64_t* history, int64_t B, int64
   rg::launch_pdl((sample_negatives_kernel), static_cast<unsigned>(B), kSamplerThreads, static_cast<size_t>(H) * 4 + 16,
                  static_cast<cudaStream_t>(stream), history, static_cast<int>(H), pad_index, val, test,
                  static_cast<uint32_t>(v_size), alias_prob, alias_idx, num_n, static_cast<uint32_t>(seed),
-                 static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(step), n_items_out);
+                 static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(step), step_dev, n_items_out);
   RG_CHECK_LAUNCH("sample_negatives");
   return RECGURU_OK;
 }

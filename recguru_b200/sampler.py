@@ -63,15 +63,25 @@ class NegativeSampler:
             self.alias_idx = torch.from_numpy(alias).to(self.device)
 
     def sample(self, history: Tensor, val: Optional[Tensor] = None, test: Optional[Tensor] = None,
-               pad_index: int = 0, step: Optional[int] = None, out: Optional[Tensor] = None) -> Tensor:
+               pad_index: int = 0, step: Optional[int] = None, out: Optional[Tensor] = None,
+               step_dev: Optional[Tensor] = None) -> Tensor:
         """``history [B, H]``: the ids to exclude per sequence (the padded sequence / ``enc_in``;
-        entries equal to ``pad_index`` or outside ``[1, v_size)`` -- the EOS id -- are ignored)."""
+        entries equal to ``pad_index`` or outside ``[1, v_size)`` -- the EOS id -- are ignored).
+        ``step_dev``: a device int64 ``[1]`` step counter read at kernel time instead of ``step``
+        (CUDA graphs: bump it inside the graph with :meth:`advance`)."""
         history = _need(history, torch.int64, "history")
         B, H = history.shape
         val = None if val is None else _need(val.view(-1), torch.int64, "val")
         test = None if test is None else _need(test.view(-1), torch.int64, "test")
         if out is None:
             out = torch.empty(B, self.num_n, dtype=torch.int64, device=history.device)
+        if step_dev is not None:
+            step_dev = _need(step_dev, torch.int64, "step_dev")
+            check(_lib.load().recguru_sample_negatives_devstep(
+                _ptr(history), B, H, int(pad_index), _ptr(val), _ptr(test), self.v_size, _ptr(self.alias_prob),
+                _ptr(self.alias_idx), self.num_n, self.seed, _ptr(step_dev), _ptr(out), _stream()),
+                "sample_negatives_devstep")
+            return out
         if step is None:
             step = self.step
             self.step += 1
@@ -80,3 +90,9 @@ class NegativeSampler:
                                                    self.num_n, self.seed, int(step), _ptr(out), _stream()),
               "sample_negatives")
         return out
+
+    @staticmethod
+    def advance(step_dev: Tensor, inc: int = 1) -> None:
+        """``step_dev += inc`` on the current stream (one-thread kernel; capturable)."""
+        step_dev = _need(step_dev, torch.int64, "step_dev")
+        check(_lib.load().recguru_counter_add(_ptr(step_dev), int(inc), _stream()), "counter_add")

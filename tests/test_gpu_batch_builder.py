@@ -86,9 +86,12 @@ def test_cfg2_sized_batch_vs_oracle(built_lib):
         a = O.test_seq_gen(seqs[u], L, L, eos, int(val[u]))
         assert np.array_equal(ee[b], a[0]) and np.array_equal(edi[b], a[1])
         assert np.array_equal(te[b], a[2]) and np.array_equal(tdi[b], a[3])
-    # size-independent property: dec_out is dec_in advanced by one item; the mask of the training
-    # step (dec_in != 0) marks exactly min(len, L-1) - 1 ... positions
-    assert np.array_equal(din[:, 1:], dout[:, :-1])
+    # size-independent properties: dec_out is dec_in advanced by one item -- except that the
+    # reference forces the first TWO decoder positions of both rows to 0 ([0, 0] + enc_in[1:-1]), so
+    # a full window loses enc_in[0] in dec_out; the mask of the training step (dec_in != 0) marks
+    # clip(len - 1, 0, L - 2) positions
+    assert np.array_equal(din[:, 2:], dout[:, 1:-1])
+    assert not din[:, :2].any() and not dout[:, :2].any()
     n_live = (din != 0).sum(1)
     assert np.array_equal(n_live, np.clip(lens[idx] - 1, 0, L - 2))
 

@@ -69,3 +69,32 @@ def test_sampler_is_deterministic_in_seed_and_step(built_lib):
     for bi in range(B):                                                   # exclusions at a realistic size
         bad = set(seqs[bi].tolist()) | {int(val[bi]), int(test[bi]), 0}
         assert not (set(a[bi].cpu().tolist()) & bad)
+
+
+def test_sampler_device_step_counter_matches_immediate_step(built_lib):
+    """recguru_sample_negatives_devstep reads the step from device memory (CUDA-graph use): same draws
+    as the immediate-step call, and a captured [sample, advance] graph draws fresh negatives on every
+    replay."""
+    from recguru_b200.sampler import NegativeSampler
+    hist, _, val, test = make_batch(8, 20, 500, seed=5)
+    h, v, t = (torch.from_numpy(x).cuda() for x in (hist, val, test))
+    smp = NegativeSampler(500, 64, seed=11)
+    step_dev = torch.tensor([7], dtype=torch.int64, device="cuda")
+    a = smp.sample(h, v, t, step_dev=step_dev)
+    assert torch.equal(a, smp.sample(h, v, t, step=7))
+    smp.advance(step_dev, 2)
+    assert int(step_dev.item()) == 9
+    out = torch.empty_like(a)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        smp.sample(h, v, t, step_dev=step_dev, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        smp.sample(h, v, t, step_dev=step_dev, out=out)
+        smp.advance(step_dev)
+    for s in (9, 10, 11):
+        g.replay()
+        assert torch.equal(out, smp.sample(h, v, t, step=s)), s
+    assert int(step_dev.item()) == 12
