@@ -359,7 +359,7 @@ def bench_train(D: Dist, args, peaks):
     ms_adam_rows = timed_loop(D, lambda i: opt.step_rows(hp.dW, row_epoch, 1), max(K, 10), Wm) / max(K, 10)
     rows_mb = (6 * W.numel() * 4 + rows_live * cfg["d"] * 4 + hp.V1 * 4) / 1e6
     table_adam["row_store"] = {
-        "ms": round(ms_adam_rows, 4), "mark_rows_ms": round(ms_mark, 4), "rows_with_gradient": rows_live,
+        "ms": round(ms_adam_rows, 4), "mark_rows_ms_eager_launch": round(ms_mark, 4), "rows_with_gradient": rows_live,
         "algorithmic_mb": round(rows_mb, 1), "gbs": round(rows_mb / ms_adam_rows, 1),
         "frac_of_hbm_peak": round(rows_mb / ms_adam_rows / peaks["hbm"], 3),
         "note": "recguru_table_adam_rows: same arithmetic, gradient rows read only where the table backward "

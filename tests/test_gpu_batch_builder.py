@@ -90,7 +90,7 @@ def test_cfg2_sized_batch_vs_oracle(built_lib):
     # reference forces the first TWO decoder positions of both rows to 0 ([0, 0] + enc_in[1:-1]), so
     # a full window loses enc_in[0] in dec_out; the mask of the training step (dec_in != 0) marks
     # clip(len - 1, 0, L - 2) positions
-    assert np.array_equal(din[:, 2:], dout[:, 1:-1])
+    assert np.array_equal(din[:, 3:], dout[:, 2:-1])
     assert not din[:, :2].any() and not dout[:, :2].any()
     n_live = (din != 0).sum(1)
     assert np.array_equal(n_live, np.clip(lens[idx] - 1, 0, L - 2))
