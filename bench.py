@@ -226,16 +226,25 @@ def bench_train(D: Dist, args, peaks):
         h2 = b["h"].view(n, cfg["d"])
 
         def f_gather():
-            hp.forward_in(tb.dec_in)
+            ops.raw_gather_pe_mask(hp.weight, tb.dec_in, hp.pe, hp.pad_index, out=hp.x0, mask_out=hp.mask)
 
         def f_fwd():
-            hp.forward_loss(b["h"], tb.dec_out, tb.n_items)
+            if hp.fuse_dh:       # forward + dh in one kernel; sum(mask) comes from the plan stage's pad-mask kernel
+                ops.raw_sampled_score_loss(b["h"], hp.weight, tb.dec_out, tb.n_items, hp.mask, hp.kind, bufs=hp.sbuf,
+                                           skip_masked=True, dh_out=hp.dh, live_count=hp._cnt)
+            else:
+                ops.raw_sampled_score_loss(b["h"], hp.weight, tb.dec_out, tb.n_items, hp.mask, hp.kind, bufs=hp.sbuf,
+                                           skip_masked=hp.skip_masked)
 
         def f_dh():
             ops.raw_sampled_score_bwd_dh(hp.sbuf["dp"], hp.sbuf["dn"], hp.weight, tb.dec_out, tb.n_items,
                                          scale=hp.one, scale2=hp.sbuf["aux"][1:2], out=hp.dh)
 
         def f_plan():
+            if hp.fuse_dh:
+                ops.raw_pad_mask_count(tb.dec_in, hp.pad_index, hp._side_mask, hp._cnt)
+            else:
+                ops.raw_pad_mask(tb.dec_in, hp.pad_index, out=hp._side_mask)
             ops.raw_fill_zero(hp.dW)
             ops.raw_embedding_bwd_plan([ops.Site(tb.dec_in, None, live=m), ops.Site(tb.dec_out, None, live=m),
                                         ops.Site(tb.n_items, None, group=cfg["K"], live=m)], hp.V1, 0, hp.ws_bwd)
@@ -246,16 +255,21 @@ def bench_train(D: Dist, args, peaks):
                      ops.Site(tb.n_items, h2, coef=hp.sbuf["dn"].view(-1), scale=hp.one,
                               scale2=hp.sbuf["aux"][1:2], group=cfg["K"], live=m)]
             ops.raw_embedding_bwd_apply(sites, hp.V1, hp.d, hp.dW, hp.ws_bwd, mode=ops.DW_PREZEROED)
-        return [f_gather, f_fwd, f_dh, f_plan, f_apply]
+        # plan first: it needs the ids only (in the timed step it is forked onto the side stream at
+        # the start) and its pad-mask kernel provides sum(mask) for the fused forward
+        return [f_plan, f_gather, f_fwd, f_dh, f_apply]
 
     fns = [stage_fns(b) for b in batches]
     # one eager pass counts the launches of a step; the timing itself replays one small CUDA graph
     # per stage, so that a slow host cannot stretch the gaps between the events
-    l0 = _lib.launch_count()
     for f in fns[0]:
         f()
     torch.cuda.synchronize()
-    launches_per_step = _lib.launch_count() - l0
+    l0 = _lib.launch_count()
+    hp.step(batches[0]["tb"].dec_in, batches[0]["tb"].dec_out, batches[0]["tb"].n_items, batches[0]["h"],
+            batches[0]["g"])
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - l0                  # kernels of one TrainHotPath.step
     stage_graphs = None
     if not args.no_graph:
         stage_graphs = []
@@ -298,8 +312,8 @@ def bench_train(D: Dist, args, peaks):
                   for b in batches]
         with ClockSampler(torch.cuda.current_device()) as cs:
             ms = timed_loop(D, lambda i: graphs[i % n_batches].replay(), K, Wm)
-    stage_names = ["gather_pe_mask", "sampled_score_loss_fwd", "sampled_score_bwd_dh", "embedding_bwd_plan",
-                   "embedding_bwd_apply"]
+    dh_name = "sampled_score_bwd_dh_standalone" if hp.fuse_dh else "sampled_score_bwd_dh"
+    stage_names = ["embedding_bwd_plan", "gather_pe_mask", "sampled_score_loss_fwd", dh_name, "embedding_bwd_apply"]
     stage_ms = {nme: sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)) / K
                 for j, nme in enumerate(stage_names)}
     # distinct touched rows (for the algorithmic bytes of the table backward)
@@ -315,13 +329,19 @@ def bench_train(D: Dist, args, peaks):
                     "gbs": round(abytes[nme] / 1e6 / stage_ms[nme], 1),
                     "frac_of_hbm_peak": round(abytes[nme] / 1e6 / stage_ms[nme] / peaks["hbm"], 3)}
               for nme in stage_names}
-    stages["embedding_bwd_plan"]["schedule"] = ("off the critical path: forked onto a side stream after "
-                                                "gather_pe_mask, runs under the two scoring kernels")
+    stages["embedding_bwd_plan"]["schedule"] = ("off the critical path: forked onto a high-priority side stream at "
+                                                "the start of the step (own pad-mask kernel), runs under the "
+                                                "gather and scoring kernels")
+    if hp.fuse_dh:
+        stages["sampled_score_loss_fwd"]["fused"] = ("forward + d loss/d h in one kernel "
+                                                      "(recguru_sampled_score_loss_fwd_dh)")
+        stages[dh_name]["schedule"] = "NOT launched by the timed step (dh is fused into the forward); timed for reference"
     # roofline: the longest stage ON the critical path of the timed schedule
-    critical = [s_ for s_ in stage_names if s_ != "embedding_bwd_plan"]
+    critical = [s_ for s_ in stage_names if s_ not in ("embedding_bwd_plan", "sampled_score_bwd_dh_standalone")]
     dom = max(critical, key=lambda s_: stage_ms[s_])
     stage_kernels = {"gather_pe_mask": ("gather_pe_mask_kernel",), "sampled_score_loss_fwd": ("sampled_score_fwd",),
                      "sampled_score_bwd_dh": ("sampled_score_bwd_dh",),
+                     "sampled_score_bwd_dh_standalone": ("sampled_score_bwd_dh",),
                      "embedding_bwd_apply": ("chunk_reduce_kernel", "span_fixup_kernel")}
     roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
             "frac": stages[dom]["frac_of_hbm_peak"], "traffic": ncu_traffic(*stage_kernels[dom]),

@@ -76,6 +76,11 @@ int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d,
  * table backward start before the gather)                                                  */
 int recguru_pad_mask(const int64_t* ids, int64_t n, int64_t pad_index, float* mask_out,
                      recguru_stream_t stream);
+/* M1 + its population count (the sum(mask) of the masked-mean losses, known before any activation
+ * exists): count3 = three uint32 words zeroed once by the caller; after the call count3[2] holds
+ * #{i : ids[i] != pad_index}; words 0-1 are scratch that the kernel leaves cleared.             */
+int recguru_pad_mask_count(const int64_t* ids, int64_t n, int64_t pad_index, float* mask_out,
+                           uint32_t* count3, recguru_stream_t stream);
 int recguru_pe_mask(const float* x, const float* pe, const float* mask, int64_t n_tokens,
                     int64_t L, int64_t d, float* out, recguru_stream_t stream);
 
@@ -162,6 +167,20 @@ int recguru_sampled_score_loss_fwd(const float* h, const float* weight, int64_t 
                                    float* n_out, float* loss_out, float* dp_unit,
                                    float* dn_unit, void* workspace, int64_t workspace_bytes,
                                    recguru_stream_t stream);
+/* Forward and d loss / d h in ONE kernel (training step: padding-aware kinds only, i.e. `kind` carries
+ * RECGURU_LOSS_SKIP_MASKED and mask != NULL):
+ *   dh[i,:] = grad_scale * (1 / *live_count) * (dp_unit[i] * W[pos[i],:] + sum_k dn_unit[i,k] * W[neg[i,k],:])
+ * -- bit-identical to recguru_sampled_score_bwd_dh(dp_unit, dn_unit, grad_scale, loss_out + 1, ...)
+ * run afterwards, without re-reading ids, derivatives and table rows.  It needs sum(mask) BEFORE the
+ * loss is reduced: live_count points at the count recguru_pad_mask_count produced for this mask
+ * (count3 + 2).  grad_scale: device scalar d(total)/d(loss), NULL = 1.                          */
+int recguru_sampled_score_loss_fwd_dh(const float* h, const float* weight, int64_t V1, int64_t d,
+                                      const int64_t* pos, const int64_t* neg, int64_t n_pos,
+                                      int64_t K, const float* mask, int kind, float* p_out,
+                                      float* n_out, float* loss_out, float* dp_unit,
+                                      float* dn_unit, void* workspace, int64_t workspace_bytes,
+                                      const float* grad_scale, const uint32_t* live_count,
+                                      float* dh, recguru_stream_t stream);
 /* Loss only, from logits (drop-in for loss_bpr(p,n,mask) / loss_s_ce(logits,...)). */
 int recguru_sampled_loss_fwd(const float* p, const float* n, int64_t n_pos, int64_t K,
                              const float* mask, int kind, float* loss_out, float* dp_unit,

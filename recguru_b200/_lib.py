@@ -69,6 +69,10 @@ SIGNATURES = {
     "recguru_rank_histogram": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, C.c_int, c_ptr]),
     "recguru_sample_negatives": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
                                            C.c_uint64, C.c_uint64, c_ptr, c_ptr]),
+    "recguru_pad_mask_count": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
+    "recguru_sampled_score_loss_fwd_dh": (C.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr,
+                                                    C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
+                                                    c_ptr, c_ptr, c_ptr, c_ptr]),
     "recguru_sample_negatives_devstep": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
                                                    c_i64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
     "recguru_counter_add": (C.c_int, [c_ptr, C.c_uint64, c_ptr]),

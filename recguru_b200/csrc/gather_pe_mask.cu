@@ -124,7 +124,51 @@ pad_mask_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t pad_index, f
     mask[i] = ids[i] != pad_index ? 1.f : 0.f;
   rg::pdl_trigger();
 }
+// The same mask plus its population count: count3 = {accumulator, tickets, result}, zeroed once by
+// the caller.  Integer atomics (exact, order independent); the last CTA to finish publishes the
+// count in count3[2] and clears the other two words for the next call.
+__global__ void __launch_bounds__(256)
+pad_mask_count_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t pad_index, float* __restrict__ mask,
+                      uint32_t* __restrict__ count3) {
+  rg::pdl_wait();
+  __shared__ uint32_t s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  uint32_t mine = 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool live = ids[i] != pad_index;
+    mask[i] = live ? 1.f : 0.f;
+    mine += live ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&count3[0], s_cnt);
+    __threadfence();
+    const uint32_t ticket = atomicAdd(&count3[1], 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      count3[2] = atomicExch(&count3[0], 0u);
+      count3[1] = 0u;
+    }
+  }
+  rg::pdl_trigger();
+}
 }  // namespace rg
+
+extern "C" int recguru_pad_mask_count(const int64_t* ids, int64_t n, int64_t pad_index, float* mask_out,
+                                      uint32_t* count3, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(n > 0 && ids && mask_out && count3, RECGURU_E_SHAPE, "pad_mask_count: null pointer or n <= 0");
+  const int64_t blocks = rg::min64(ceil_div(n, 256 * 4), kNumSMs * 8);
+  rg::launch_pdl((pad_mask_count_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream),
+                 ids, n, pad_index, mask_out, count3);
+  RG_CHECK_LAUNCH("pad_mask_count");
+  return RECGURU_OK;
+}
 
 extern "C" int recguru_pad_mask(const int64_t* ids, int64_t n, int64_t pad_index, float* mask_out,
                                 recguru_stream_t stream) {

@@ -232,7 +232,9 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
                                 int64_t n_pos, int K, const float* __restrict__ mask, int kind,
                                 float* __restrict__ p_out, float* __restrict__ n_out,
                                 float* __restrict__ dp_unit, float* __restrict__ dn_unit,
-                                float2* __restrict__ block_partial, int chunk, int64_t pos_per_cta) {
+                                float2* __restrict__ block_partial, int chunk, int64_t pos_per_cta,
+                                float4* __restrict__ dh, const float* __restrict__ dh_scale,
+                                const uint32_t* __restrict__ live_count) {
   rg::pdl_wait();
   constexpr int LANES = VEC < 32 ? VEC : 32;
   constexpr int G = 32 / LANES;
@@ -286,6 +288,15 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
         }
       }
       __syncthreads();
+      // fused dh: the rows of the dead positions are zero (coalesced 16-byte stores)
+      if (dh != nullptr) {
+        const int tot4 = n_c * VEC;
+        for (int idx = tid; idx < tot4; idx += kSparseThreads) {
+          const int q = idx / VEC;
+          if (s_rank[q] < 0)
+            st_stream_f4(dh + (cb + q) * VEC + (idx - q * VEC), make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
       // negatives: coalesced sweep over the chunk's [n_c, K] id block
       const int tot = n_c * K;
       for (int idx = tid; idx < tot; idx += kSparseThreads) {
@@ -351,6 +362,59 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
     if (kind >= 0 && tid == 0) {
 #pragma unroll 1
       for (int w = 0; w < kWarps; ++w) { tot_l += s_part[w].x; tot_m += s_part[w].y; }
+    }
+    // ---- phase 3 (fused dh): dh[i,:] = s * sum_c (d_c * m) * W[id_c,:] for the live positions ----
+    // The unit derivatives are still in s_sc, the ids in s_id, the table rows just read are L1/L2
+    // hits.  Same coefficient products, same fma chain and group combine as
+    // sampled_score_bwd_dh_kernel: the result is bit-identical to the two-kernel path.
+    if (dh != nullptr) {
+      float sc = dh_scale ? __ldg(dh_scale) : 1.f;
+      sc *= 1.f / static_cast<float>(__ldg(live_count));      // == loss_out[1] of loss_finalize_kernel
+      for (int t = warp; t < n_live; t += kWarps) {
+        const int64_t i = cb + s_list[t];
+        const float m = __ldg(mask + i);
+        float4 acc[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c0 = 0; c0 < C; c0 += G * UN) {
+          float4 w[UN][VPL];
+          float cf[UN];
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const int c = c0 + u * G + g;
+            const int src = c < C ? c : 0;
+            const int64_t id = s_id[t * RS + src];
+            cf[u] = c < C ? (s_sc[t * RS + src] * m) * sc : 0.f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+              w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < UN; ++u)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              acc[v].x = fmaf(cf[u], w[u][v].x, acc[v].x);
+              acc[v].y = fmaf(cf[u], w[u][v].y, acc[v].y);
+              acc[v].z = fmaf(cf[u], w[u][v].z, acc[v].z);
+              acc[v].w = fmaf(cf[u], w[u][v].w, acc[v].w);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= LANES; o >>= 1)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+            acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+            acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+            acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+          }
+        if (g == 0) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) st_stream_f4(dh + i * VEC + v * LANES + sub, acc[v]);
+        }
+      }
+      __syncthreads();                              // s_sc/s_id/s_list are rewritten by the next chunk
     }
   }
   if (kind >= 0 && tid == 0) block_partial[blockIdx.x] = make_float2(tot_l, tot_m);
@@ -636,14 +700,21 @@ extern "C" int64_t recguru_sampled_workspace_bytes(int64_t n_pos, int64_t K) {
   return rg::align_up((rg::ceil_div(n_pos > 0 ? n_pos : 1, rg::kPosPerBlock) + 1) * 8, 256);
 }
 
-extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weight, int64_t V1,
-                                              int64_t d, const int64_t* pos, const int64_t* neg,
-                                              int64_t n_pos, int64_t K, const float* mask, int kind,
-                                              float* p_out, float* n_out, float* loss_out,
-                                              float* dp_unit, float* dn_unit, void* workspace,
-                                              int64_t workspace_bytes, recguru_stream_t stream) {
+static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int64_t V1,
+                                       int64_t d, const int64_t* pos, const int64_t* neg,
+                                       int64_t n_pos, int64_t K, const float* mask, int kind,
+                                       float* p_out, float* n_out, float* loss_out,
+                                       float* dp_unit, float* dn_unit, void* workspace,
+                                       int64_t workspace_bytes, float* dh, const float* dh_scale,
+                                       const uint32_t* live_count, recguru_stream_t stream) {
   using namespace rg;
   const bool skip_masked = kind >= 0 && (kind & RECGURU_LOSS_SKIP_MASKED) && mask != nullptr;
+  if (dh != nullptr) {
+    RG_REQUIRE(skip_masked, RECGURU_E_UNSUPPORTED,
+               "sampled_score_loss_fwd_dh: the fused dh needs a loss kind with RECGURU_LOSS_SKIP_MASKED and a mask");
+    RG_REQUIRE(live_count != nullptr && aligned16(dh), RECGURU_E_SHAPE,
+               "sampled_score_loss_fwd_dh: live_count is null or dh is not 16-byte aligned");
+  }
   if (kind >= 0) kind &= ~RECGURU_LOSS_SKIP_MASKED;
   int rc = check_common("sampled_score_loss_fwd", V1, d, n_pos, K);
   if (rc) return rc;
@@ -683,7 +754,7 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
       }                                                                                          \
       rg::launch_pdl((sampled_score_fwd_sparse_kernel<V>), static_cast<unsigned>(blocks), kSparseThreads, sparse_smem, st,  \
           h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
-          chunk, pos_per_cta);                                                                   \
+          chunk, pos_per_cta, reinterpret_cast<float4*>(dh), dh_scale, live_count);              \
     } else {                                                                                     \
       rg::launch_pdl((sampled_score_fwd_kernel<V>), static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st,    \
           h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part);    \
@@ -702,6 +773,32 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
     RG_CHECK_LAUNCH("loss_finalize");
   }
   return RECGURU_OK;
+}
+
+extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weight, int64_t V1,
+                                              int64_t d, const int64_t* pos, const int64_t* neg,
+                                              int64_t n_pos, int64_t K, const float* mask, int kind,
+                                              float* p_out, float* n_out, float* loss_out,
+                                              float* dp_unit, float* dn_unit, void* workspace,
+                                              int64_t workspace_bytes, recguru_stream_t stream) {
+  return sampled_score_loss_fwd_impl(h, weight, V1, d, pos, neg, n_pos, K, mask, kind, p_out, n_out, loss_out,
+                                     dp_unit, dn_unit, workspace, workspace_bytes, nullptr, nullptr, nullptr,
+                                     stream);
+}
+
+extern "C" int recguru_sampled_score_loss_fwd_dh(const float* h, const float* weight, int64_t V1,
+                                                 int64_t d, const int64_t* pos, const int64_t* neg,
+                                                 int64_t n_pos, int64_t K, const float* mask, int kind,
+                                                 float* p_out, float* n_out, float* loss_out,
+                                                 float* dp_unit, float* dn_unit, void* workspace,
+                                                 int64_t workspace_bytes, const float* grad_scale,
+                                                 const uint32_t* live_count, float* dh,
+                                                 recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(dh != nullptr, RECGURU_E_SHAPE, "sampled_score_loss_fwd_dh: dh is null");
+  return sampled_score_loss_fwd_impl(h, weight, V1, d, pos, neg, n_pos, K, mask, kind, p_out, n_out, loss_out,
+                                     dp_unit, dn_unit, workspace, workspace_bytes, dh, grad_scale, live_count,
+                                     stream);
 }
 
 extern "C" int recguru_sampled_loss_fwd(const float* p, const float* n, int64_t n_pos, int64_t K,

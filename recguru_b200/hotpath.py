@@ -13,6 +13,7 @@ on its output, then :meth:`backward` with the gradient that came back to the inp
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -28,7 +29,7 @@ class TrainHotPath:
 
     def __init__(self, weight: Tensor, pe: Tensor, B: int, L: int, K: int, kind: str = "bpr_sas",
                  pad_index: int = 0, padding_idx: Optional[int] = 0, skip_masked: bool = True,
-                 overlap_plan: bool = True, dense_grad: bool = True):
+                 overlap_plan: bool = True, dense_grad: bool = True, fuse_dh: Optional[bool] = None):
         assert weight.is_cuda and weight.dtype == torch.float32
         self.weight = weight
         self.pe = pe[0] if pe.dim() == 3 else pe
@@ -68,18 +69,45 @@ class TrainHotPath:
         self._join = torch.cuda.Event()
         self._planned = False
         self._side_mask = torch.empty(B, L, **f32)
+        # fuse_dh: d loss / d h comes out of the padding-aware scoring kernel itself
+        # (recguru_sampled_score_loss_fwd_dh) instead of a second kernel that re-reads ids,
+        # derivatives and table rows.  It needs sum(mask) before the loss is reduced: the pad-mask
+        # kernel that runs at the start of the step anyway also counts (recguru_pad_mask_count).
+        if fuse_dh is None:                                # RECGURU_FUSE_DH=0: two-kernel path by default (A/B timing)
+            fuse_dh = skip_masked and os.environ.get("RECGURU_FUSE_DH", "1") != "0"
+        self.fuse_dh = bool(fuse_dh)
+        if self.fuse_dh and not skip_masked:
+            raise RuntimeError("recguru: fuse_dh needs the padding-aware scoring kernel (skip_masked=True)")
+        self._cnt = torch.zeros(3, dtype=torch.int32, device=dev)
+        self._cnt_ready = torch.cuda.Event()
+        self._cnt_state = 0            # 0 = not issued this step, 1 = on the current stream, 2 = on the side stream
+        self._dh_done = False
+        self._dh_scale = None
 
     # -- edge 1: ids -> activations ------------------------------------------------------
     def forward_in(self, dec_in: Tensor) -> Tensor:
         ops.raw_gather_pe_mask(self.weight, dec_in, self.pe, self.pad_index, out=self.x0, mask_out=self.mask)
+        if self.fuse_dh and self._cnt_state == 0:          # no plan forked: count on this stream
+            ops.raw_pad_mask_count(dec_in, self.pad_index, self._side_mask, self._cnt)
+            self._cnt_state = 1
         return self.x0
 
     # -- edge 2: hidden states -> loss ---------------------------------------------------
-    def forward_loss(self, h: Tensor, dec_out: Tensor, n_items: Tensor, mask: Optional[Tensor] = None) -> Tensor:
+    def forward_loss(self, h: Tensor, dec_out: Tensor, n_items: Tensor, mask: Optional[Tensor] = None,
+                     grad_loss: Optional[Tensor] = None) -> Tensor:
         m = self.mask if mask is None else mask
         # the loss is all this edge exports: positions under the pad mask are not scored
-        ops.raw_sampled_score_loss(h, self.weight, dec_out, n_items, m, self.kind, bufs=self.sbuf,
-                                   skip_masked=self.skip_masked)
+        if self.fuse_dh and mask is None and self._cnt_state != 0:
+            if self._cnt_state == 2:
+                torch.cuda.current_stream().wait_event(self._cnt_ready)
+            ops.raw_sampled_score_loss(h, self.weight, dec_out, n_items, m, self.kind, bufs=self.sbuf,
+                                       skip_masked=True, dh_out=self.dh, live_count=self._cnt,
+                                       grad_scale=grad_loss)
+            self._dh_done = True
+            self._dh_scale = grad_loss
+        else:
+            ops.raw_sampled_score_loss(h, self.weight, dec_out, n_items, m, self.kind, bufs=self.sbuf,
+                                       skip_masked=self.skip_masked)
         return self.sbuf["aux"][0]
 
     # -- table-backward plan: depends on the ids and the pad mask only -----------------------
@@ -96,7 +124,12 @@ class TrainHotPath:
             if mask is None:
                 # the side stream derives the pad mask itself (a 2 us kernel), so the plan does not
                 # have to wait for K1 and can be issued at the very start of the step
-                m = ops.raw_pad_mask(dec_in, self.pad_index, out=self._side_mask).view(n)
+                if self.fuse_dh:
+                    m = ops.raw_pad_mask_count(dec_in, self.pad_index, self._side_mask, self._cnt).view(n)
+                    self._cnt_ready.record(self._side)
+                    self._cnt_state = 2
+                else:
+                    m = ops.raw_pad_mask(dec_in, self.pad_index, out=self._side_mask).view(n)
             else:
                 m = mask.view(n)
             if self.dense_grad:
@@ -116,8 +149,14 @@ class TrainHotPath:
         """Returns (dh, dW).  ``g_x0`` is d loss / d x0 as it comes back through the transformer."""
         go = self.one if grad_loss is None else grad_loss
         inv_m = self.sbuf["aux"][1:2]
-        ops.raw_sampled_score_bwd_dh(self.sbuf["dp"], self.sbuf["dn"], self.weight, dec_out, n_items,
-                                     scale=go, scale2=inv_m, out=self.dh)
+        if self._dh_done and (grad_loss is None) == (self._dh_scale is None) and \
+                (grad_loss is None or grad_loss.data_ptr() == self._dh_scale.data_ptr()):
+            pass                                           # dh was written by the forward kernel
+        else:
+            ops.raw_sampled_score_bwd_dh(self.sbuf["dp"], self.sbuf["dn"], self.weight, dec_out, n_items,
+                                         scale=go, scale2=inv_m, out=self.dh)
+        self._dh_done = False
+        self._cnt_state = 0
         n = self.B * self.L
         h2 = h.view(n, self.d)
         m = self.mask.view(n)
@@ -195,5 +234,12 @@ class TrainHotPath:
             # apply: one source row per live index, one dW row per distinct id
             "embedding_bwd_apply": live * 4 * d + (4 * d * distinct_rows if distinct_rows is not None else 0),
         }
+        if self.fuse_dh:
+            # dh comes out of the scoring kernel: its dense write moves there, the re-reads of ids,
+            # derivatives and table rows by the second kernel disappear
+            b["sampled_score_loss_fwd"] += n * 4 * d
+            b["sampled_score_bwd_dh_standalone"] = b.pop("sampled_score_bwd_dh")
+            b["total"] = sum(v for k, v in b.items() if k != "sampled_score_bwd_dh_standalone")
+            return b
         b["total"] = sum(b.values())
         return b

@@ -227,6 +227,20 @@ def raw_pad_mask(ids: Tensor, pad_index: int, out: Optional[Tensor] = None) -> T
     return out
 
 
+def raw_pad_mask_count(ids: Tensor, pad_index: int, out: Tensor, count3: Tensor) -> Tensor:
+    """:func:`raw_pad_mask` plus the number of non-pad ids in ``count3[2]`` (``count3``: CUDA int32
+    ``[3]``, zeroed once; the kernel leaves words 0-1 cleared)."""
+    ids = _need(ids, torch.int64, "ids")
+    if count3.dtype != torch.int32 or count3.numel() != 3 or not count3.is_cuda or not count3.is_contiguous():
+        raise RuntimeError("recguru: count3 must be a contiguous CUDA int32 [3] tensor")
+    out = _need(out, torch.float32, "mask_out")
+    if out.numel() != ids.numel() or not out.is_contiguous():
+        raise RuntimeError("recguru: mask_out must be contiguous with one entry per id")
+    check(_lib.load().recguru_pad_mask_count(_ptr(ids), ids.numel(), int(pad_index), _ptr(out), _ptr(count3),
+                                             _stream()), "pad_mask_count")
+    return out
+
+
 def raw_fill_zero(x: Tensor) -> Tensor:
     x = _need(x, torch.float32, "x")
     check(_lib.load().recguru_fill_zero(_ptr(x), x.numel(), _stream()), "fill_zero")
@@ -248,10 +262,16 @@ def raw_sort_ids(ids: Tensor, V1: int) -> Tuple[Tensor, Tensor]:
 
 def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
                            mask: Optional[Tensor], kind: Optional[str], want_grads: bool = True,
-                           bufs: Optional[dict] = None, skip_masked: bool = False):
+                           bufs: Optional[dict] = None, skip_masked: bool = False,
+                           dh_out: Optional[Tensor] = None, live_count: Optional[Tensor] = None,
+                           grad_scale: Optional[Tensor] = None):
     """p = h.W[pos], n = h.W[neg]; loss per tools/lossfunctions.py:36-49,:56-72,:79-96.
     ``skip_masked``: do not score positions with mask == 0 (loss and derivatives unchanged, the
     logits of those positions are reported as 0 instead of the values nobody consumes).
+
+    ``dh_out`` (with ``skip_masked``): also write d loss / d h in the same kernel
+    (``recguru_sampled_score_loss_fwd_dh``); ``live_count`` = the int32 ``[3]`` buffer
+    :func:`raw_pad_mask_count` filled for this mask, ``grad_scale`` an optional device scalar.
 
     Returns (p [..,1], n [..,K], loss_aux [2] or None, dp_unit, dn_unit).  loss_aux[0] is the
     loss, loss_aux[1] = 1/sum(mask)."""
@@ -285,6 +305,19 @@ def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
             dp = b.get("dp") if "dp" in b else torch.empty(n_pos, dtype=torch.float32, device=dev)
             dn = b.get("dn") if "dn" in b else torch.empty(n_pos, K, dtype=torch.float32, device=dev)
         ws = b.get("ws") if "ws" in b else _workspace(lib.recguru_sampled_workspace_bytes(n_pos, K), dev)
+    if dh_out is not None:
+        dh_out = _need(dh_out, torch.float32, "dh_out")
+        if dh_out.numel() != n_pos * d or not dh_out.is_contiguous():
+            raise RuntimeError("recguru: dh_out must be a contiguous [n_pos, d] tensor")
+        if live_count is None or live_count.dtype != torch.int32 or live_count.numel() != 3 or not live_count.is_cuda:
+            raise RuntimeError("recguru: live_count must be the CUDA int32 [3] buffer of raw_pad_mask_count")
+        gs = None if grad_scale is None else _need(grad_scale, torch.float32, "grad_scale")
+        check(lib.recguru_sampled_score_loss_fwd_dh(_ptr(h), _ptr(weight), V1, d, _ptr(pos), _ptr(neg), n_pos,
+                                                    K, _ptr(mask), kind_i, _ptr(p), _ptr(n), _ptr(aux),
+                                                    _ptr(dp), _ptr(dn), _ptr(ws), 0 if ws is None else ws.numel(),
+                                                    _ptr(gs), live_count.data_ptr() + 8, _ptr(dh_out), _stream()),
+              "sampled_score_loss_fwd_dh")
+        return p, n, aux, dp, dn
     check(lib.recguru_sampled_score_loss_fwd(_ptr(h), _ptr(weight), V1, d, _ptr(pos), _ptr(neg), n_pos,
                                              K, _ptr(mask), kind_i, _ptr(p), _ptr(n), _ptr(aux),
                                              _ptr(dp), _ptr(dn), _ptr(ws),

@@ -62,8 +62,11 @@ def test_step_matches_reference_autograd(hp_mod, kind, B, L, d, K, V):
     x0_ref, mask_ref, loss_ref, dh_ref, dW_ref = oracle_step(W, pe, dec_in, dec_out, n_items, h, g_x0, K, kind)
     c = lambda x: x.cuda()
     results = []
-    for skip, overlap in [(False, False), (True, False), (False, True), (True, True)]:
-        hp = hotpath.TrainHotPath(c(W), c(pe), B, L, K, kind, skip_masked=skip, overlap_plan=overlap)
+    variants = [(False, False, None), (True, False, None), (False, True, None), (True, True, None),
+                (True, True, False), (True, False, False)]         # fuse_dh: None = default (on with skip_masked)
+    for skip, overlap, fuse in variants:
+        hp = hotpath.TrainHotPath(c(W), c(pe), B, L, K, kind, skip_masked=skip, overlap_plan=overlap, fuse_dh=fuse)
+        assert hp.fuse_dh == (skip if fuse is None else fuse)
         loss, dh, dW = hp.step(c(dec_in), c(dec_out), c(n_items), c(h), c(g_x0))
         torch.cuda.synchronize()
         results.append((loss.clone(), dh.clone(), dW.clone()))
@@ -73,7 +76,7 @@ def test_step_matches_reference_autograd(hp_mod, kind, B, L, d, K, V):
         assert torch.allclose(dW.cpu(), dW_ref, rtol=1e-4, atol=1e-6)
     # every variant: gradients bit-identical to the plain one; the loss scalar too when the same
     # scoring kernel ran (the padding-aware kernel sums the same terms in another order)
-    for (skip, overlap), r in zip([(False, False), (True, False), (False, True), (True, True)], results):
+    for (skip, overlap, fuse), r in zip(variants, results):
         assert torch.equal(r[1], results[0][1]) and torch.equal(r[2], results[0][2])
         assert torch.equal(r[0], results[1 if skip else 0][0])
         assert torch.allclose(r[0], results[0][0], rtol=1e-6, atol=0)

@@ -253,6 +253,57 @@ def test_sampled_score_bwd_dh(ops, d, K):
     assert torch.allclose(dh.cpu(), 2.0 * h.grad, rtol=1e-5, atol=1e-5)
 
 
+def test_pad_mask_count(ops):
+    g = torch.Generator().manual_seed(2)
+    count3 = torch.zeros(3, dtype=torch.int32, device="cuda")
+    for n, frac in [(1, 0.0), (7, 0.5), (4096, 0.9), (204800, 0.926), (1_000_003, 0.1)]:
+        ids = torch.randint(1, 1000, (n,), generator=g)
+        ids[torch.rand(n, generator=g) < frac] = 0
+        out = torch.empty(n, dtype=torch.float32, device="cuda")
+        for _ in range(2):                                 # self-clearing scratch: a second call gives the same count
+            ops.raw_pad_mask_count(dev(ids), 0, out, count3)
+            assert count3.tolist() == [0, 0, int((ids != 0).sum())]
+        assert torch.equal(out.cpu(), (ids != 0).float())
+
+
+@pytest.mark.parametrize("kind", ["bpr", "bpr_sas", "sce"])
+@pytest.mark.parametrize("d,K", [(32, 5), (64, 30), (128, 5), (128, 30), (256, 3), (64, 1)])
+def test_fused_forward_dh_bit_identical_to_two_kernels(ops, kind, d, K):
+    """recguru_sampled_score_loss_fwd_dh writes the same dh bits as the forward followed by
+    recguru_sampled_score_bwd_dh, and leaves loss / logits / derivatives untouched; several chunks
+    per CTA, dead positions in between, a non-unit upstream scale."""
+    torch.manual_seed(5 * d + K)
+    B, L, V1 = 37, 61, 977
+    W = dev(torch.randn(V1, d) * 0.3)
+    h = dev(torch.randn(B, L, d) * 0.3)
+    pos = dev(torch.randint(1, V1, (B, L)))
+    neg = dev(torch.randint(1, V1, (B, L * K)))
+    ids = torch.randint(1, V1, (B, L))
+    ids[torch.rand(B, L) < 0.7] = 0
+    mask = torch.empty(B, L, device="cuda")
+    count3 = torch.zeros(3, dtype=torch.int32, device="cuda")
+    ops.raw_pad_mask_count(dev(ids), 0, mask, count3)
+    go = dev(torch.tensor([0.75]))
+    m = mask.view(-1)
+    p1, n1, aux1, dp1, dn1 = ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=True)
+    dh_ref = ops.raw_sampled_score_bwd_dh(dp1, dn1, W, pos, neg, go, aux1[1:2])
+    dh = torch.full((B * L, d), float("nan"), device="cuda")
+    p2, n2, aux2, dp2, dn2 = ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=True, dh_out=dh,
+                                                        live_count=count3, grad_scale=go)
+    assert torch.equal(aux1, aux2) and torch.equal(p1, p2) and torch.equal(n1, n2)
+    assert torch.equal(dp1, dp2) and torch.equal(dn1, dn2)
+    assert torch.equal(dh.view_as(dh_ref), dh_ref)
+    assert not bool(dh.view(B * L, d)[m == 0].any())
+    # no upstream scale (NULL) == scale 1
+    dh1 = torch.empty(B * L, d, device="cuda")
+    ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=True, dh_out=dh1, live_count=count3)
+    one = dev(torch.ones(1))
+    assert torch.equal(dh1.view_as(dh_ref), ops.raw_sampled_score_bwd_dh(dp1, dn1, W, pos, neg, one, aux1[1:2]))
+    # the fused form needs the padding-aware kernel
+    with pytest.raises(RuntimeError):
+        ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=False, dh_out=dh1, live_count=count3)
+
+
 # ---------------------------------------------------------------- op layer / autograd --------
 def test_modules_autograd_end_to_end_golden(ops):
     """FusedItemEmbedding + FusedPositionalEncoding + fused loss reproduce the reference's loss
