@@ -65,6 +65,11 @@ class TrainHotPath:
         self.overlap_plan = overlap_plan
         # high priority: its short kernels slip in between the waves of the bandwidth-bound kernels
         self._side = torch.cuda.Stream(device=dev, priority=-1)
+        # the dense zero fill of dW is bandwidth-bound and independent of the plan's latency-bound
+        # chain: its own branch (RECGURU_ZERO_STREAM=0 puts it back at the head of the plan stream)
+        self._zero_own = os.environ.get("RECGURU_ZERO_STREAM", "1") != "0"
+        self._zstream = torch.cuda.Stream(device=dev)
+        self._zero_done = torch.cuda.Event()
         self._fork = torch.cuda.Event()
         self._join = torch.cuda.Event()
         self._planned = False
@@ -120,6 +125,11 @@ class TrainHotPath:
         cur = torch.cuda.current_stream()
         self._fork.record(cur)
         self._side.wait_event(self._fork)
+        if self.dense_grad and self._zero_own:
+            self._zstream.wait_event(self._fork)
+            with torch.cuda.stream(self._zstream):
+                ops.raw_fill_zero(self.dW)
+                self._zero_done.record(self._zstream)
         with torch.cuda.stream(self._side):
             if mask is None:
                 # the side stream derives the pad mask itself (a 2 us kernel), so the plan does not
@@ -132,7 +142,7 @@ class TrainHotPath:
                     m = ops.raw_pad_mask(dec_in, self.pad_index, out=self._side_mask).view(n)
             else:
                 m = mask.view(n)
-            if self.dense_grad:
+            if self.dense_grad and not self._zero_own:
                 ops.raw_fill_zero(self.dW)
             sites = [Site(dec_in, None, live=m), Site(dec_out, None, live=m),
                      Site(n_items, None, group=self.K, live=m)]
@@ -167,6 +177,8 @@ class TrainHotPath:
         ]
         if self._planned:
             torch.cuda.current_stream().wait_event(self._join)
+            if self.dense_grad and self._zero_own:
+                torch.cuda.current_stream().wait_event(self._zero_done)
             ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
             self._planned = False
         elif self.dense_grad:
