@@ -8,7 +8,7 @@ echo "== bench reference arm"; timeout 600 python bench.py --impl reference --st
 echo "== candidate protocol"; timeout 200 python scripts/candidate_bench.py 2>&1 | tee gpurun_out/candidate_bench.log
 echo "== catalog knobs"; timeout 300 python scripts/catalog_exp.py 2>&1 | tee gpurun_out/catalog_exp_final.log
 echo "== launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 3 --warmup 3 --only train,cfg4 --skip-cpu --no-graph > /dev/null 2>&1; echo rc=$?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 3 --warmup 3 --only train,cfg4 --skip-cpu --no-graph > /dev/null 2>&1; echo rc=$?
 echo "== full captures"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:catalog_sweep -s 3 -c 1 -o gpurun_out/r01_sweep -f python bench.py --steps 3 --warmup 3 --only cfg4 --skip-cpu > /dev/null 2>&1; echo rc=$?
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gather_pe_mask|sampled_score|chunk_reduce|radix_scatter|compact_scatter|span_fixup' -s 27 -c 9 -o gpurun_out/r01_train -f python bench.py --steps 3 --warmup 3 --only train --skip-cpu --no-graph > /dev/null 2>&1; echo rc=$?
