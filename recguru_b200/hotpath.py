@@ -134,7 +134,7 @@ class TrainHotPath:
             if mask is None:
                 # the side stream derives the pad mask itself (a 2 us kernel), so the plan does not
                 # have to wait for K1 and can be issued at the very start of the step
-                if self.fuse_dh:
+                if self.fuse_dh and self._cnt_state == 0:   # (state 1: forward_in already counted on its stream)
                     m = ops.raw_pad_mask_count(dec_in, self.pad_index, self._side_mask, self._cnt).view(n)
                     self._cnt_ready.record(self._side)
                     self._cnt_state = 2

@@ -140,3 +140,35 @@ def test_graph_replay_equals_eager(hp_mod):
     torch.cuda.synchronize()
     assert all(torch.equal(a, b) for a, b in zip(got2, e2))          # same kernels, same bits
     assert not torch.equal(got2[0], ref[0])
+
+
+def test_edges_called_one_by_one_equal_step(hp_mod):
+    """The caller-driven order of INTEGRATION.md (forward_in, plan_backward, [transformer], forward_loss,
+    backward) gives the same bits as step(), whichever of forward_in / plan_backward comes first, with
+    and without an upstream gradient scale tensor."""
+    hotpath, ops = hp_mod
+    B, L, d, K, V = 16, 40, 128, 5, 3000
+    W, pe, dec_in, dec_out, n_items, h, g_x0 = [x.cuda() for x in make_step(B, L, d, K, V, seed=11)]
+    ref = hotpath.TrainHotPath(W, pe, B, L, K, "bpr_sas").step(dec_in, dec_out, n_items, h, g_x0)
+    ref = tuple(t.clone() for t in ref)
+    one = torch.ones(1, device="cuda")
+    for plan_first in (True, False, None):
+        for go in (None, one):
+            hp = hotpath.TrainHotPath(W, pe, B, L, K, "bpr_sas")
+            for _ in range(2):                                       # twice: per-step state must reset
+                if plan_first is True:
+                    hp.plan_backward(dec_in, dec_out, n_items)
+                x0 = hp.forward_in(dec_in)
+                if plan_first is False:
+                    hp.plan_backward(dec_in, dec_out, n_items)
+                loss = hp.forward_loss(h, dec_out, n_items, grad_loss=go)
+                dh, dW = hp.backward(h, dec_in, dec_out, n_items, g_x0, grad_loss=go)
+                torch.cuda.synchronize()
+                assert torch.equal(loss, ref[0]) and torch.equal(dh, ref[1]) and torch.equal(dW, ref[2]), (plan_first, go)
+    # an upstream scale that differs between forward and backward falls back to the stand-alone dh kernel
+    hp = hotpath.TrainHotPath(W, pe, B, L, K, "bpr_sas")
+    hp.forward_in(dec_in)
+    hp.forward_loss(h, dec_out, n_items)
+    half = torch.full((1,), 0.5, device="cuda")
+    dh, dW = hp.backward(h, dec_in, dec_out, n_items, g_x0, grad_loss=half)
+    assert torch.allclose(dh, 0.5 * ref[1], rtol=1e-6, atol=0)
