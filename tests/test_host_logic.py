@@ -144,3 +144,35 @@ def test_alias_table_reproduces_weights():
     np.add.at(p, np.arange(1000), prob / 1000)
     np.add.at(p, alias, (1 - prob) / 1000)
     assert np.allclose(p, g / g.sum(), atol=1e-7)
+
+
+def test_sequence_store_host_logic():
+    """The packing of the pickles' ragged lists (CSR) and the loud failures of the loader module on a
+    box without a GPU."""
+    from recguru_b200 import loader
+    seqs = [[5, 6, 7], [], [9], list(range(1, 12))]
+    items, offsets = loader.pack_sequences(seqs)
+    assert items.dtype == np.int64 and offsets.tolist() == [0, 3, 3, 4, 15]
+    for s, lo, hi in zip(seqs, offsets[:-1], offsets[1:]):
+        assert items[lo:hi].tolist() == s
+    e, o = loader.pack_sequences([])
+    assert e.size == 0 and o.tolist() == [0]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        loader.SequenceStore(seqs, None, None, eos=99, enc_len=6, device="cpu")
+    # CPU tensors are refused before anything is launched
+    t = torch.zeros(4, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loader.raw_build_batches(t, t, None, None, 1, 6, 6, 99, loader.BATCH_TRAIN, None, None, None)
+
+
+def test_new_entry_points_refuse_cpu_tensors():
+    from recguru_b200 import ops
+    w = torch.zeros(8, 4)
+    e = torch.zeros(8, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.raw_table_adam_rows(w, w.clone(), w.clone(), w.clone(), e, 1, 1e-3, 0.9, 0.99, 1e-9, 1)
+    with pytest.raises(RuntimeError):
+        ops.raw_pad_mask_count(torch.zeros(4, dtype=torch.int64), 0, torch.zeros(4), torch.zeros(3, dtype=torch.int32))
+    from recguru_b200.sampler import NegativeSampler
+    with pytest.raises(RuntimeError, match="CUDA"):
+        NegativeSampler.advance(torch.zeros(1, dtype=torch.int64))
