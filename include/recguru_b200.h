@@ -302,6 +302,17 @@ int recguru_sample_negatives_devstep(const int64_t* history, int64_t B, int64_t 
                                      const float* alias_prob, const int32_t* alias_idx,
                                      int64_t num_n, uint64_t seed, const uint64_t* step_dev,
                                      int64_t* n_items_out, recguru_stream_t stream);
+/* Same law with the exclusion list read from the ragged store of recguru_build_batches: the WHOLE
+ * sequence of user u = user_idx[b] (items[offsets[u] .. offsets[u+1]), as `for val in seq:
+ * weights[seq] = 0` does, data_loader.py:291-293,:301-303 -- not just the window that fits
+ * enc_in), val[u] and test[u] (per-user arrays, either may be NULL).  max_len >= the longest stored
+ * sequence (<= 12000).  step_dev NULL: the immediate `step` is used.  Same Philox counters as the
+ * matrix form: for a user whose sequence fits its enc_in row both calls draw identical negatives. */
+int recguru_sample_negatives_csr(const int64_t* items, const int64_t* offsets, const int64_t* user_idx,
+                                 int64_t B, int64_t max_len, const int64_t* val, const int64_t* test,
+                                 int64_t v_size, const float* alias_prob, const int32_t* alias_idx,
+                                 int64_t num_n, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                 int64_t* n_items_out, recguru_stream_t stream);
 /* *counter += inc on the stream (a one-thread kernel; graph-capturable step bookkeeping). */
 int recguru_counter_add(uint64_t* counter, uint64_t inc, recguru_stream_t stream);
 

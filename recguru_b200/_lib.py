@@ -75,6 +75,8 @@ SIGNATURES = {
                                                     c_ptr, c_ptr, c_ptr, c_ptr]),
     "recguru_sample_negatives_devstep": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
                                                    c_i64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
+    "recguru_sample_negatives_csr": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
+                                               c_i64, C.c_uint64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
     "recguru_counter_add": (C.c_int, [c_ptr, C.c_uint64, c_ptr]),
     "recguru_embedding_bwd_mark_rows": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_ptr, c_i64, c_ptr, C.c_uint32, c_ptr]),
     "recguru_table_adam_rows": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_uint32, c_i64, c_i64, C.c_double,

@@ -43,6 +43,7 @@ sample_negatives_kernel(const int64_t* __restrict__ history, int H, int64_t pad_
                         uint32_t v_size, const float* __restrict__ alias_prob,
                         const int32_t* __restrict__ alias_idx, int64_t num_n, uint32_t seed_lo,
                         uint32_t seed_hi, uint32_t step, const uint64_t* __restrict__ step_dev,
+                        const int64_t* __restrict__ offsets, const int64_t* __restrict__ user_idx,
                         int64_t* __restrict__ out) {
   rg::pdl_wait();
   if (step_dev != nullptr) step = static_cast<uint32_t>(*step_dev);   // device-side step counter (CUDA graphs)
@@ -51,15 +52,21 @@ sample_negatives_kernel(const int64_t* __restrict__ history, int H, int64_t pad_
   const int64_t b = blockIdx.x;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
+  // Where this sequence's history lives: row b of a padded [B, H] matrix, or (offsets != NULL) the
+  // ragged store -- history = all sequences back to back, user u = user_idx[b] owns
+  // [offsets[u], offsets[u+1]), and val / test are indexed by user.
+  const int64_t u = offsets ? (user_idx ? user_idx[b] : b) : b;
+  const int64_t* hist = offsets ? history + offsets[u] : history + b * H;
+  const int n_h = offsets ? static_cast<int>(rg::min64(offsets[u + 1] - offsets[u], H)) : H;
   // exclusion list: the non-pad entries of this sequence's history (order irrelevant)
-  for (int i = threadIdx.x; i < H; i += kSamplerThreads) {
-    const int64_t id = history[b * H + i];
+  for (int i = threadIdx.x; i < n_h; i += kSamplerThreads) {
+    const int64_t id = hist[i];
     if (id != pad_index && id > 0 && id < v_size) s_hist[atomicAdd(&s_n, 1)] = static_cast<int>(id);
   }
   __syncthreads();
   const int n_hist = s_n;
-  const int v0 = val ? static_cast<int>(val[b]) : 0;
-  const int t0 = test ? static_cast<int>(test[b]) : 0;
+  const int v0 = val ? static_cast<int>(val[u]) : 0;
+  const int t0 = test ? static_cast<int>(test[u]) : 0;
   const uint32_t n_choices = v_size - 1;                        // ids 1 .. v_size-1
   for (int64_t slot = threadIdx.x; slot < num_n; slot += kSamplerThreads) {
     int id = 1;
@@ -112,6 +119,7 @@ static int sample_negatives_impl(const int64_t* history, int64_t B, int64_t H, i
                                  const int64_t* val, const int64_t* test, int64_t v_size,
                                  const float* alias_prob, const int32_t* alias_idx, int64_t num_n,
                                  uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                 const int64_t* offsets, const int64_t* user_idx,
                                  int64_t* n_items_out, recguru_stream_t stream);
 
 extern "C" int recguru_sample_negatives(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
@@ -120,7 +128,7 @@ extern "C" int recguru_sample_negatives(const int64_t* history, int64_t B, int64
                                         int64_t num_n, uint64_t seed, uint64_t step,
                                         int64_t* n_items_out, recguru_stream_t stream) {
   return sample_negatives_impl(history, B, H, pad_index, val, test, v_size, alias_prob, alias_idx, num_n, seed,
-                               step, nullptr, n_items_out, stream);
+                               step, nullptr, nullptr, nullptr, n_items_out, stream);
 }
 
 extern "C" int recguru_sample_negatives_devstep(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
@@ -131,13 +139,26 @@ extern "C" int recguru_sample_negatives_devstep(const int64_t* history, int64_t 
   using namespace rg;
   RG_REQUIRE(step_dev != nullptr, RECGURU_E_SHAPE, "sample_negatives_devstep: null step counter");
   return sample_negatives_impl(history, B, H, pad_index, val, test, v_size, alias_prob, alias_idx, num_n, seed,
-                               0, step_dev, n_items_out, stream);
+                               0, step_dev, nullptr, nullptr, n_items_out, stream);
+}
+
+extern "C" int recguru_sample_negatives_csr(const int64_t* items, const int64_t* offsets, const int64_t* user_idx,
+                                            int64_t B, int64_t max_len, const int64_t* val, const int64_t* test,
+                                            int64_t v_size, const float* alias_prob, const int32_t* alias_idx,
+                                            int64_t num_n, uint64_t seed, uint64_t step,
+                                            const uint64_t* step_dev, int64_t* n_items_out,
+                                            recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(offsets != nullptr, RECGURU_E_SHAPE, "sample_negatives_csr: null offsets");
+  return sample_negatives_impl(items, B, max_len, /*pad_index=*/0, val, test, v_size, alias_prob, alias_idx, num_n,
+                               seed, step, step_dev, offsets, user_idx, n_items_out, stream);
 }
 
 static int sample_negatives_impl(const int64_t* history, int64_t B, int64_t H, int64_t pad_index,
                                  const int64_t* val, const int64_t* test, int64_t v_size,
                                  const float* alias_prob, const int32_t* alias_idx, int64_t num_n,
                                  uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                 const int64_t* offsets, const int64_t* user_idx,
                                  int64_t* n_items_out, recguru_stream_t stream) {
   using namespace rg;
   RG_REQUIRE(B >= 0 && H >= 0 && num_n >= 0 && v_size >= 2 && v_size < (1ll << 31), RECGURU_E_SHAPE,
@@ -151,7 +172,8 @@ static int sample_negatives_impl(const int64_t* history, int64_t B, int64_t H, i
   rg::launch_pdl((sample_negatives_kernel), static_cast<unsigned>(B), kSamplerThreads, static_cast<size_t>(H) * 4 + 16,
                  static_cast<cudaStream_t>(stream), history, static_cast<int>(H), pad_index, val, test,
                  static_cast<uint32_t>(v_size), alias_prob, alias_idx, num_n, static_cast<uint32_t>(seed),
-                 static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(step), step_dev, n_items_out);
+                 static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(step), step_dev, offsets, user_idx,
+                 n_items_out);
   RG_CHECK_LAUNCH("sample_negatives");
   return RECGURU_OK;
 }

@@ -106,6 +106,9 @@ class SequenceStore:
         _lib.load()
         items, offsets = pack_sequences(seqs)
         self.n_users = len(seqs)
+        self.max_len = int(np.diff(offsets).max()) if len(seqs) else 0
+        if self.max_len > 12000:
+            raise RuntimeError("recguru: sequences longer than 12000 items are not supported by the device sampler")
         self.items = torch.from_numpy(items).to(device)
         self.offsets = torch.from_numpy(offsets).to(device)
         self.val = None if val is None else torch.as_tensor(np.asarray(val, dtype=np.int64)).to(device)

@@ -91,6 +91,32 @@ class NegativeSampler:
               "sample_negatives")
         return out
 
+    def sample_store(self, store, user_idx: Optional[Tensor], B: Optional[int] = None, step: Optional[int] = None,
+                     out: Optional[Tensor] = None, step_dev: Optional[Tensor] = None) -> Tensor:
+        """Negatives for the users ``user_idx`` of a :class:`recguru_b200.loader.SequenceStore`: the
+        exclusion list is the user's WHOLE stored sequence plus ``store.val`` / ``store.test`` -- what
+        the reference zeroes (data_loader.py:291-295) -- not only the window that fits ``enc_in``."""
+        if user_idx is not None:
+            user_idx = _need(user_idx, torch.int64, "user_idx")
+            B = int(user_idx.numel())
+        else:
+            B = int(len(store) if B is None else B)
+            if B > len(store):
+                raise RuntimeError(f"recguru: B={B} exceeds the {len(store)} stored sequences")
+        if out is None:
+            out = torch.empty(B, self.num_n, dtype=torch.int64, device=store.items.device)
+        if step_dev is not None:
+            step_dev = _need(step_dev, torch.int64, "step_dev")
+            step = 0
+        elif step is None:
+            step = self.step
+            self.step += 1
+        check(_lib.load().recguru_sample_negatives_csr(
+            _ptr(store.items), _ptr(store.offsets), _ptr(user_idx), B, max(int(store.max_len), 1), _ptr(store.val),
+            _ptr(store.test), self.v_size, _ptr(self.alias_prob), _ptr(self.alias_idx), self.num_n, self.seed,
+            int(step), _ptr(step_dev), _ptr(out), _stream()), "sample_negatives_csr")
+        return out
+
     @staticmethod
     def advance(step_dev: Tensor, inc: int = 1) -> None:
         """``step_dev += inc`` on the current stream (one-thread kernel; capturable)."""

@@ -98,3 +98,39 @@ def test_sampler_device_step_counter_matches_immediate_step(built_lib):
         g.replay()
         assert torch.equal(out, smp.sample(h, v, t, step=s)), s
     assert int(step_dev.item()) == 12
+
+
+def test_sampler_from_the_ragged_store(built_lib):
+    """recguru_sample_negatives_csr: exclusions come from the user's WHOLE stored sequence (the
+    reference zeroes weights[seq] for the full list, data_loader.py:291-293), val/test are looked up
+    per user; for users whose sequence fits the enc_in window the draws are identical to the matrix
+    form fed with the device-built enc_in rows."""
+    from recguru_b200.loader import SequenceStore
+    from recguru_b200.sampler import NegativeSampler
+    rng = np.random.default_rng(21)
+    v_size, L, num_n = 400, 12, 5000
+    lens = [0, 1, 5, 11, 12, 40, 150, 3, 7, 11]
+    seqs = [rng.integers(1, v_size, n).tolist() for n in lens]
+    val, test = rng.integers(1, v_size, len(seqs)), rng.integers(1, v_size, len(seqs))
+    store = SequenceStore(seqs, val, test, eos=v_size, enc_len=L)
+    assert store.max_len == 150
+    idx = torch.tensor([6, 0, 5, 2, 9, 3, 4, 1, 8, 7], device="cuda")
+    smp = NegativeSampler(v_size, num_n, seed=3)
+    out = smp.sample_store(store, idx, step=5).cpu().numpy()
+    assert out.shape == (len(idx), num_n) and out.min() >= 1 and out.max() < v_size
+    for b, u in enumerate(idx.tolist()):
+        bad = set(seqs[u]) | {int(val[u]), int(test[u])}
+        assert not (set(out[b].tolist()) & bad), (b, u)               # incl. items older than the window
+        allowed = v_size - 1 - len(bad - {0})
+        assert len(set(out[b].tolist())) > 0.9 * min(allowed, num_n) * (1 - np.exp(-num_n / allowed)) * 0.9
+    rows = store.train_batch(idx)
+    mat = smp.sample(rows.enc_in, rows.val, rows.test, step=5).cpu().numpy()
+    for b, u in enumerate(idx.tolist()):
+        if len(seqs[u]) <= L - 1:                                       # whole sequence visible in enc_in
+            assert np.array_equal(mat[b], out[b]), (b, u)
+    assert not np.array_equal(mat[0], out[0])                           # user 6: 150 items, window of 11
+    # device step counter and identity batch
+    step_dev = torch.tensor([5], dtype=torch.int64, device="cuda")
+    assert np.array_equal(smp.sample_store(store, idx, step_dev=step_dev).cpu().numpy(), out)
+    first = smp.sample_store(store, None, B=4, step=5).cpu().numpy()
+    assert np.array_equal(first, smp.sample_store(store, torch.arange(4, device="cuda"), step=5).cpu().numpy())
