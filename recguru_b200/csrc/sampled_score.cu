@@ -726,7 +726,17 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
   if (n_pos == 0) return RECGURU_OK;
   // dense: one CTA per 128 positions; padding-aware: one persistent CTA per SM
   const int RS = static_cast<int>(K + 1) | 1;
-  const int chunk = RS <= 13 ? 1024 : 512;                   // 2 * chunk * RS * 4 B of shared memory
+  int chunk = RS <= 13 ? 1024 : 512;                         // 2 * chunk * RS * 4 B of shared memory
+  {
+    // RECGURU_SPARSE_CHUNK=<n>: smaller chunks for the padding-aware kernel (a multiple of 32, at
+    // most the default), e.g. 704 = two equal chunks per CTA at cfg2.  Measurement knob, default off.
+    static int env_chunk = -1;
+    if (env_chunk < 0) {
+      const char* e = getenv("RECGURU_SPARSE_CHUNK");
+      env_chunk = e ? atoi(e) : 0;
+    }
+    if (env_chunk >= 32 && env_chunk <= chunk && env_chunk % 32 == 0) chunk = env_chunk;
+  }
   int64_t blocks = ceil_div(n_pos, kScoreWarps * kDensePW);
   int64_t pos_per_cta = 0;
   if (skip_masked) {
