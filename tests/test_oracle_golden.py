@@ -220,3 +220,36 @@ def test_batch_layout_closed_form_matches_golden():
         assert np.array_equal(enc, c["eval_enc_in"]) and np.array_equal(dec, c["eval_dec_in"])
         enc, dec = rows(c["items"], c["offsets"], c["val"], Le, Ld, eos, 1, 1)
         assert np.array_equal(enc, c["test_enc_in"]) and np.array_equal(dec, c["t_dec_in"])
+
+
+def test_batch_layout_closed_form_random_windows():
+    """Property check of the closed form recguru_build_batches evaluates (csrc/batch_builder.cu) against
+    the oracle's list surgery over random window sizes and history lengths, including dec_len <
+    enc_len and histories far longer than the window (hypothesis-driven, CPU only)."""
+    from hypothesis import given, settings, strategies as st
+
+    def closed(seq, Le, Ld, eos, shift_in, first_zero):
+        n = len(seq)
+        E = lambda j: eos if j == Le - 1 else (seq[j - (Le - 1 - n)] if j - (Le - 1 - n) >= 0 else 0)
+        enc = [E(j) for j in range(Le)]
+        dec = [0 if (Le - Ld + jd) < first_zero else E(Le - Ld + jd - shift_in) for jd in range(Ld)]
+        return enc, dec
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(2, 40), st.data())
+    def check(Le, data):
+        Ld = data.draw(st.integers(1, Le))
+        seq = data.draw(st.lists(st.integers(1, 10 ** 6), min_size=0, max_size=3 * Le))
+        val = data.draw(st.integers(1, 10 ** 6))
+        eos = 10 ** 6 + 1
+        e, di, do = O.seq_padding(seq, Le, Ld, eos)
+        enc, dec_in = closed(seq, Le, Ld, eos, 2, 2)
+        _, dec_out = closed(seq, Le, Ld, eos, 1, 2)
+        assert e.tolist() == enc and di.tolist() == dec_in and do.tolist() == dec_out
+        ee, edi, te, tdi = O.test_seq_gen(seq, Le, Ld, eos, val)
+        enc, dec = closed(seq, Le, Ld, eos, 1, 1)
+        assert ee.tolist() == enc and edi.tolist() == dec
+        enc, dec = closed(seq + [val], Le, Ld, eos, 1, 1)
+        assert te.tolist() == enc and tdi.tolist() == dec
+
+    check()
