@@ -253,3 +253,22 @@ def test_batch_layout_closed_form_random_windows():
         assert te.tolist() == enc and tdi.tolist() == dec
 
     check()
+
+
+def test_survey_kats_metrics_and_pad_mask():
+    """SURVEY 8c known answers computed with the reference in the authoring container:
+    (i) ranks [0, 3, 12], k = 10 -> HR 0.666667, NDCG 0.476892, MRR 0.416667;
+    (v) the input of the reference's own pad_mask_test (Transformer/transformer.py:553-557)."""
+    r = [0, 3, 12]
+    assert abs(O.hit_at_k_batch(r, 10) - 0.666667) < 1e-6
+    assert abs(O.NDCG_at_k_batch(r, 10) - 0.476892) < 1e-6
+    assert abs(O.mrr_at_k_batch(r, 10) - 0.416667) < 1e-6
+    from recguru_b200.catalog import metrics_from_histogram
+    hist = np.bincount(np.minimum(np.array(r), 30), minlength=31)
+    m = metrics_from_histogram(hist, len(r), (10,))[10]
+    assert abs(m["hr"] - 2 / 3) < 1e-12 and abs(m["ndcg"] - (1 + 1 / np.log2(5)) / 3) < 1e-12
+    assert abs(m["mrr"] - (1 + 1 / 4) / 3) < 1e-12
+    ids = torch.tensor([[1, 0, 0, 0, 0, 0], [1, 3, 0, 0, 0, 0], [1, 3, 4, 0, 0, 0], [1, 3, 4, 1, 0, 0]])
+    want = [[1, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0], [1, 1, 1, 1, 0, 0]]
+    mask = O.pad_mask(ids, 0)
+    assert mask.dtype == torch.float32 and mask.tolist() == want
