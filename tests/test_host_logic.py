@@ -176,3 +176,24 @@ def test_new_entry_points_refuse_cpu_tensors():
     from recguru_b200.sampler import NegativeSampler
     with pytest.raises(RuntimeError, match="CUDA"):
         NegativeSampler.advance(torch.zeros(1, dtype=torch.int64))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) runs without a GPU and
+    prints ONE JSON line carrying the contract keys: same metric/unit as our arm, impl, a
+    cpu_baseline describing the run, and an e2e object with zero transfer bytes."""
+    import json, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "train seqs/sec" and j["unit"] == "seqs/s"
+    assert j["higher_is_better"] is True and j["n_gpus"] == 1 and j["warmup"] >= 3 and j["value"] > 0
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"] and j["vs_baseline"] is None
