@@ -18,6 +18,7 @@ There is no CPU path: the store refuses CPU devices and raises if the CUDA libra
 """
 from __future__ import annotations
 
+import itertools
 from typing import NamedTuple, Optional, Sequence
 
 import numpy as np
@@ -35,9 +36,8 @@ def pack_sequences(seqs: Sequence[Sequence[int]]):
     lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
     offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
-    items = np.empty(int(offsets[-1]), dtype=np.int64)
-    for s, lo, hi in zip(seqs, offsets[:-1], offsets[1:]):
-        items[lo:hi] = s
+    # one pass over all items (C loop inside numpy) instead of a slice assignment per sequence
+    items = np.fromiter(itertools.chain.from_iterable(seqs), dtype=np.int64, count=int(offsets[-1]))
     return items, offsets
 
 
