@@ -33,7 +33,9 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+CFG1 = dict(n_items=10_000, L=50, d=64, B=256)                     # configs[0]: AutoRec (K=30 sce, K=5 bpr_sas)
 CFG2 = dict(n_items=100_000, L=200, d=128, B=1024, K=5, kind="bpr_sas")
+CFG3 = dict(n_items=500_000, L=100, d=128, B=1024, K=30, kind="sce")  # configs[2]: RecGURU, per domain
 CFG4 = dict(n_items=1_000_000, d=128, k=10, users_total=1_000_000)
 CFG5 = dict(n_items=10_000_000, d=128, k=10, users_total=1_000_000)
 USERS_PER_STEP = 148 * 4 * 128          # 4 full waves of 128-user tiles on 148 SMs
@@ -42,13 +44,21 @@ USERS_PER_STEP = 148 * 4 * 128          # 4 full waves of 128-user tiles on 148 
 # ----------------------------------------------------------------------------------------------
 # plumbing
 # ----------------------------------------------------------------------------------------------
+TRAFFIC_FILES = ("r02_traffic.json", "r01_traffic.json")
+
+
 def ncu_traffic(*kernel_prefixes):
     """DRAM bytes per launch (read + write) of the named kernels, summed, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json, written by scripts/ncu_summary.py)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
-    try:
-        tab = json.load(open(path))
-    except (OSError, ValueError):
+    `ncu --set full` capture (profiles/r02_traffic.json, else r01; written by scripts/ncu_summary.py)."""
+    tab = None
+    for fn in TRAFFIC_FILES:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", fn)
+        try:
+            tab = json.load(open(path))
+            break
+        except (OSError, ValueError):
+            continue
+    if tab is None:
         return None
     total, found = 0.0, 0
     for pre in kernel_prefixes:
@@ -302,16 +312,27 @@ def bench_train(D: Dist, args, peaks):
     ms_eager = timed_loop(D, lambda i: hp.step(batches[i % n_batches]["tb"].dec_in, batches[i % n_batches]["tb"].dec_out,
                                                batches[i % n_batches]["tb"].n_items, batches[i % n_batches]["h"],
                                                batches[i % n_batches]["g"]), K, Wm)
+    # The timed region is exactly K steps (contract).  At 0.15 ms per step K = 20 is 3 ms -- shorter than
+    # one nvidia-smi sample and than the time clocks take to settle -- so it is preceded, inside the same
+    # clock-sampler window, by >= 60 ms of the same step (untimed), and a sustained figure over >= 400
+    # steps is reported beside it.
+    def run_step(i):
+        b = batches[i % n_batches]
+        hp.step(b["tb"].dec_in, b["tb"].dec_out, b["tb"].n_items, b["h"], b["g"])
+
     if args.no_graph:
-        with ClockSampler(torch.cuda.current_device()) as cs:
-            ms = timed_loop(D, lambda i: hp.step(batches[i % n_batches]["tb"].dec_in, batches[i % n_batches]["tb"].dec_out,
-                                                 batches[i % n_batches]["tb"].n_items, batches[i % n_batches]["h"],
-                                                 batches[i % n_batches]["g"]), K, Wm)
+        timed_fn = run_step
     else:
         graphs = [hp.capture_step(b["tb"].dec_in, b["tb"].dec_out, b["tb"].n_items, b["h"], b["g"])
                   for b in batches]
-        with ClockSampler(torch.cuda.current_device()) as cs:
-            ms = timed_loop(D, lambda i: graphs[i % n_batches].replay(), K, Wm)
+
+        def timed_fn(i):
+            graphs[i % n_batches].replay()
+    n_sustain = max(400, K)
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms_sustain = timed_loop(D, timed_fn, n_sustain, Wm)      # pre-load: clocks at their under-load state
+        ms = timed_loop(D, timed_fn, K, Wm)
+        timed_loop(D, timed_fn, n_sustain, 0)                       # keeps the sampler window under load
     dh_name = "sampled_score_bwd_dh_standalone" if hp.fuse_dh else "sampled_score_bwd_dh"
     stage_names = ["embedding_bwd_plan", "gather_pe_mask", "sampled_score_loss_fwd", dh_name, "embedding_bwd_apply"]
     stage_ms = {nme: sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)) / K
@@ -354,6 +375,34 @@ def bench_train(D: Dist, args, peaks):
                     "with the kernels serialised on one stream; whole_step = all algorithmic bytes of a step "
                     "over the timed step"}
 
+    # ---- the drop-in surface: what the reference's UNCHANGED call sites execute --
+    # FusedItemEmbedding.lookup_pe_mask + sampled_loss_fused + loss.backward() through
+    # torch.ops.recguru.* and torch autograd, eager launches; the table gradient of all lookup sites is
+    # reduced in one K2 pass per backward() (ops.enable_one_pass_backward) and lands in weight.grad
+    from recguru_b200.modules import FusedItemEmbedding, FusedPositionalEncoding, sampled_loss_fused
+    dropin = {}
+    for one_pass in (True, False):
+        emb = FusedItemEmbedding(hp.V1, hp.d, padding_idx=0, _weight=W.clone(), one_pass_backward=one_pass)
+        posm = FusedPositionalEncoding(hp.d, 0.0, max_len=max(cfg["L"], 256)).to(dev).eval()
+        hs = [b["h"].clone().requires_grad_(True) for b in batches]
+
+        def dropin_step(i, emb=emb, posm=posm, hs=hs):
+            b = batches[i % n_batches]
+            h_ = hs[i % n_batches]
+            emb.weight.grad = None
+            h_.grad = None
+            x_, m_ = emb.lookup_pe_mask(b["tb"].dec_in, posm, pad_index=0)
+            loss_, _, _ = sampled_loss_fused(h_, emb, b["tb"].dec_out, b["tb"].n_items, m_.view(-1), cfg["kind"])
+            torch.autograd.backward([loss_, x_], [None, b["g"]])
+        ms_d = timed_loop(D, dropin_step, K, Wm) / K
+        dropin["one_pass_backward" if one_pass else "per_site_dense_gradients"] = {
+            "ms_per_step": round(ms_d, 4), "seqs_per_s": round(cfg["B"] * D.world / (ms_d * 1e-3))}
+        del emb, posm, hs
+    dropin["ratio_vs_hotpath_eager"] = round(dropin["one_pass_backward"]["ms_per_step"] / (ms_eager / K), 3)
+    dropin["note"] = ("eager launches through torch.ops.recguru.* + autograd (no CUDA graph, no side-stream plan, "
+                      "allocations by torch's caching allocator); dense scoring kernel (every position scored, "
+                      "the logits are returned to the caller as MyRec.forward does)")
+
     # ---- next row: the optimizer step of the table, timed on its own (NOT part of
     # the step above: north_star stops at the dense gradient)
     from recguru_b200.optim import FusedTableAdam
@@ -392,19 +441,30 @@ def bench_train(D: Dist, args, peaks):
     # reference's loop does with loss.item().  All copies happen inside the timed region.
     pin = [dict(dec_in=t.dec_in.pin_memory(), dec_out=t.dec_out.pin_memory(), n_items=t.n_items.pin_memory())
            for t in host]
+    # The ids of a batch are < V1 < 2^31: a loader that collates into pinned INT32 buffers halves the
+    # per-step host->device bytes (the PCIe-bound part of this loop, and the part that collapses when 8
+    # replicas share the host links); recguru_widen_ids restores the int64 layout the ops take, on the
+    # copy stream.  The int64-over-PCIe form (what default_collate hands over, data_loader.py:418-421)
+    # is timed beside it.
+    pin32 = [{k: v.to(torch.int32).pin_memory() for k, v in pb.items()} for pb in pin]
     d_in = [{k: torch.empty_like(v, device=dev) for k, v in pin[0].items()} for _ in range(2)]
+    d_in32 = [{k: torch.empty_like(v, device=dev) for k, v in pin32[0].items()} for _ in range(2)]
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream()
     copied = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {"primed": -1}
+    state = {"primed": -1, "ids32": True}
 
     def enqueue_copy(i):
         slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # buffer free (its previous step finished)
             for k in d_in[slot]:
-                d_in[slot][k].copy_(pin[i % n_batches][k], non_blocking=True)
+                if state["ids32"]:
+                    d_in32[slot][k].copy_(pin32[i % n_batches][k], non_blocking=True)
+                    ops.raw_widen_ids(d_in32[slot][k], out=d_in[slot][k])
+                else:
+                    d_in[slot][k].copy_(pin[i % n_batches][k], non_blocking=True)
             copied[slot].record(copy_stream)
 
     for ev in consumed:
@@ -427,6 +487,12 @@ def bench_train(D: Dist, args, peaks):
         loss_host.copy_(hp.sbuf["aux"][0:1], non_blocking=True)
         cur.synchronize()                                    # the reference reads loss.item() every step
 
+    def restart_e2e(ids32):
+        state["primed"], state["ids32"] = -1, ids32
+        torch.cuda.synchronize()
+        for ev in consumed:
+            ev.record()
+
     # batch b always lands in id slot b % 2 (n_batches is even), so one graph per batch suffices
     for slot in range(2):                       # valid ids in the static buffers while capturing
         for k in d_in[slot]:
@@ -435,15 +501,15 @@ def bench_train(D: Dist, args, peaks):
     # as a CUDA graph; the headline e2e is the faster one and says which it was
     e2e_graphs = None
     ms_e2e_eager = timed_loop(D, e2e_step, K, Wm)
-    ms_e2e_graph = None
+    ms_e2e_graph = ms_e2e_i64 = None
     if not args.no_graph:
-        state["primed"] = -1
-        torch.cuda.synchronize()
-        for ev in consumed:
-            ev.record()
+        restart_e2e(True)
         e2e_graphs = [hp.capture_step(d_in[b % 2]["dec_in"], d_in[b % 2]["dec_out"], d_in[b % 2]["n_items"],
                                       batches[b]["h"], batches[b]["g"]) for b in range(n_batches)]
         ms_e2e_graph = timed_loop(D, e2e_step, K, Wm)
+    restart_e2e(False)
+    ms_e2e_i64 = timed_loop(D, e2e_step, K, Wm)              # same loop, int64 ids over PCIe
+    restart_e2e(True)
     ms_e2e = ms_e2e_eager if ms_e2e_graph is None else min(ms_e2e_eager, ms_e2e_graph)
 
     # next row: negatives drawn on the device by recguru_sample_negatives instead of
@@ -562,20 +628,31 @@ def bench_train(D: Dist, args, peaks):
                            "device; only the batch's user indices cross PCIe; value = the faster of eager launches and one "
                            "CUDA graph per batch (sampler step read from a device counter the graph advances)"}
     e2e_mode = "eager (TrainHotPath.step)" if ms_e2e == ms_e2e_eager else "cuda_graph (TrainHotPath.capture_step)"
-    h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
+    h2d = sum(v.numel() * v.element_size() for v in pin32[0].values())
+    h2d_i64 = sum(v.numel() * v.element_size() for v in pin[0].values())
     seqs = cfg["B"] * D.world
     out = {
         "value": seqs * K / (ms / 1e3), "ms_per_step": ms / K, "stages": stages, "roofline": roof,
+        "sustained": {"steps": n_sustain, "ms_per_step": ms_sustain / n_sustain,
+                      "value": seqs * n_sustain / (ms_sustain / 1e3), "unit": "seqs/s",
+                      "note": "same step, same launch mode, timed over >= 400 steps right before the K-step region "
+                              "(the clock sampler covers both)"},
         "e2e": {"value": seqs * K / (ms_e2e / 1e3), "unit": "seqs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
                 "launch_mode": e2e_mode, "ms_per_step_eager": ms_e2e_eager / K,
                 "ms_per_step_graph": None if ms_e2e_graph is None else ms_e2e_graph / K,
+                "ids_on_host": "int32 (collated into pinned int32 by the loader; widened to int64 on the device "
+                               "by recguru_widen_ids on the copy stream)",
+                "int64_ids": {"value": seqs * K / (ms_e2e_i64 / 1e3), "ms_per_step": ms_e2e_i64 / K,
+                              "h2d_bytes_per_step": h2d_i64,
+                              "note": "same loop with int64 ids over PCIe (what default_collate hands over)"},
                 "note": "ids from pinned host memory each step, loss read back each step; h and the "
                         "gradient w.r.t. the input activations come from the (out-of-scope) transformer "
                         "and are device resident"},
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
         "launch_mode": "eager" if args.no_graph else "cuda_graph (one graph per rotating batch)",
         "table_adam": table_adam, "e2e_device_negatives": e2e_sampler, "e2e_device_batches": e2e_builder,
+        "dropin_surface": dropin,
         "ms_per_step_eager": ms_eager / K, "ms_per_step_serialised_stages": ms_serial / K,
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
         "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,
@@ -612,17 +689,257 @@ def bench_gather(D: Dist, args, peaks, W, pe, batches):
         ops.raw_gather_pe_mask(W, ids[j], pe, 0, out=outs[j], mask_out=masks[j])
 
     ms2 = timed_loop(D, step2, max(args.steps, 20), args.warmup) / max(args.steps, 20)
-    return {"gbs": round(mb / per, 1), "frac_of_hbm_peak": round(mb / per / peaks["hbm"], 3),
-            "ms": round(per, 4), "algorithmic_mb": round(mb, 1),
-            "dense_ids": {"gbs": round(mb / ms2, 1), "frac_of_hbm_peak": round(mb / ms2 / peaks["hbm"], 3),
-                          "ms": round(ms2, 4)},
-            "note": "amazon-shaped batch (93% pad tokens hit one row) and a no-padding batch; "
-                    "4 rotating out buffers = 420 MB > L2"}
+    out = {"gbs": round(mb / per, 1), "frac_of_hbm_peak": round(mb / per / peaks["hbm"], 3),
+           "ms": round(per, 4), "algorithmic_mb": round(mb, 1),
+           "dense_ids": {"gbs": round(mb / ms2, 1), "frac_of_hbm_peak": round(mb / ms2 / peaks["hbm"], 3),
+                         "ms": round(ms2, 4)},
+           "note": "cfg2's 51 MB table lives in the 126 MB L2: these two are L2 figures, NOT HBM (amazon-shaped "
+                   "batch: 93% pad tokens hit one row; dense_ids: a no-padding batch); 4 rotating out buffers "
+                   "= 420 MB > L2.  The HBM figures are in `hbm_table`."}
+    del outs, masks, ids
+    out["hbm_table"] = bench_gather_hbm(D, args, peaks)
+    return out
 
+
+def bench_gather_hbm(D: Dist, args, peaks):
+    """K1 against HBM: a table far larger than L2 -- cfg4's 1M x 128 fp32 =
+    512 MB -- with uniform and Zipf(1.05) ids, no padding; 'cold' rotates over 8 id/out sets (each
+    call touches 105 MB of rows spread over the 512 MB table and writes a fresh 105 MB output, so
+    what a call finds in L2 is at most what the previous seven left), 'hot' repeats one set.  The
+    DRAM bytes at the pins come from the ncu capture of this same loop (profiles/r02_traffic.json,
+    key gather_hbm_*; scripts/gather_hbm.py)."""
+    from recguru_b200 import ops, synth, modules
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_items, d, B, L = 1_000_000, 128, CFG2["B"], CFG2["L"]
+    n = B * L
+    gen = torch.Generator(device=dev).manual_seed(4242)
+    W = torch.randn(n_items + 2, d, generator=gen, device=dev)
+    pe = modules.sinusoid_table(max(L, 256), d)[0].to(dev)
+    n_sets = 8
+    outs = [torch.empty(B, L, d, device=dev) for _ in range(n_sets)]
+    masks = [torch.empty(B, L, device=dev) for _ in range(n_sets)]
+    ids_u = torch.randint(1, n_items + 1, (n_sets, B, L), generator=gen, device=dev)
+    ids_z = synth.zipf_ids(n_sets * n, n_items, seed=99).view(n_sets, B, L).to(dev)
+    mb = n * (8 + 8 * d + 4) / 1e6
+    steps = max(args.steps, 40)
+    res = {"table_mb": round(W.numel() * 4 / 1e6, 1), "algorithmic_mb": round(mb, 1), "tokens": n}
+    for name, ids in (("uniform", ids_u), ("zipf", ids_z)):
+        distinct = int(torch.unique(ids[0]).numel())
+        compulsory_mb = (n * (8 + 4 * d + 4) + distinct * 4 * d) / 1e6      # every distinct row once + ids + output
+
+        def cold(i, ids=ids):
+            j = i % n_sets
+            ops.raw_gather_pe_mask(W, ids[j], pe, 0, out=outs[j], mask_out=masks[j])
+
+        def hot(i, ids=ids):
+            ops.raw_gather_pe_mask(W, ids[0], pe, 0, out=outs[0], mask_out=masks[0])
+
+        t_cold = timed_loop(D, cold, steps, args.warmup) / steps
+        t_hot = timed_loop(D, hot, steps, args.warmup) / steps
+        tr = ncu_traffic(f"gather_hbm_{name}_cold")
+        res[name] = {
+            "distinct_rows": distinct,
+            "cold": {"ms": round(t_cold, 4), "gbs": round(mb / t_cold, 1),
+                     "frac_of_hbm_peak": round(mb / t_cold / peaks["hbm"], 3),
+                     "compulsory_mb": round(compulsory_mb, 1),
+                     "compulsory_frac_of_hbm_peak": round(compulsory_mb / t_cold / peaks["hbm"], 3),
+                     "dram_bytes_ncu": tr,
+                     "dram_frac_of_hbm_peak": None if tr is None else round(tr / 1e6 / t_cold / peaks["hbm"], 3)},
+            "hot": {"ms": round(t_hot, 4), "gbs": round(mb / t_hot, 1),
+                    "frac_of_hbm_peak": round(mb / t_hot / peaks["hbm"], 3)},
+        }
+    res["note"] = ("algorithmic bytes = 8 (id) + 4d (row) + 4d (out) + 4 (mask) per token, cache hits not discounted; "
+                   "compulsory = each distinct row read once; dram_bytes_ncu = dram read+write of one launch of the "
+                   "cold loop under ncu (cold-cache, serialised) -- the claim against HBM is dram_frac_of_hbm_peak")
+    return res
+
+
+
+# ----------------------------------------------------------------------------------------------
+# workload 1b: the other two step topologies (configs[0] AutoRec, configs[2] RecGURU)
+# ----------------------------------------------------------------------------------------------
+def _site_stats(pairs, padding_idx):
+    """pairs: (ids [n*group], live mask [n], group).  -> (live gathered indices, distinct live ids)."""
+    live_ids = []
+    for ids, m, group in pairs:
+        keep = m.view(-1, 1).expand(-1, group).reshape(-1) != 0
+        v = ids.reshape(-1)[keep]
+        if padding_idx is not None:
+            v = v[v != padding_idx]
+        live_ids.append(v)
+    allv = torch.cat(live_ids)
+    return int(allv.numel()), int(torch.unique(allv).numel())
+
+
+def bench_topology(D: Dist, args, peaks, which: str):
+    """Hot-path step of configs[0] (AutoRec: two input sites, K=30 sampled softmax and K=5 BPR) or
+    configs[2] (RecGURU reconstruction: two domains x (enc_in, dec_in, pos, 30 negatives), tables
+    without padding_idx, the two domains on two streams), CUDA-graph replay over 4 rotating batches,
+    inputs resident; transformer replaced by given h and returned gradients, as in the cfg2 line."""
+    from recguru_b200 import synth, modules
+    from recguru_b200.hotpath import TrainStep, RecGuruStep
+    dev = torch.device("cuda", torch.cuda.current_device())
+    K_steps, Wm = args.steps, args.warmup
+    n_batches = 4
+    out = {}
+    if which == "cfg1":
+        cfg = CFG1
+        variants = [("recon_sce_k30", 30, "sce"), ("bpr_sas_k5", 5, "bpr_sas")]
+    else:
+        cfg = CFG3
+        variants = [("recon_sce_k30", cfg["K"], cfg["kind"])]
+    B, L, d, n_items = cfg["B"], cfg["L"], cfg["d"], cfg["n_items"]
+    pe = modules.sinusoid_table(max(L, 256), d)[0].to(dev)
+    for vname, K, kind in variants:
+        def mk(seed0):
+            bs = []
+            for b in range(n_batches):
+                tb = synth.train_batch(B, L, n_items, K, seed=seed0 + 100 * b).to(dev)
+                bs.append(dict(tb=tb, h=synth.hidden_states(B, L, d, seed=seed0 + b).to(dev),
+                               g=[(synth.hidden_states(B, L, d, seed=seed0 + 40 + 2 * b + i) * 0.01).to(dev)
+                                  for i in range(2)]))
+            return bs
+        if which == "cfg1":
+            W = synth.item_table(n_items, d).to(dev)
+            st = TrainStep(W, pe, B, L, K, kind, n_inputs=2, padding_idx=0)
+            bs = mk(synth.SEED_DATA)
+            graphs = [st.capture_run([b["tb"].enc_in, b["tb"].dec_in], b["tb"].dec_out, b["tb"].n_items, b["h"], b["g"],
+                                     loss_mask_ids=b["tb"].dec_in) for b in bs]
+            tb0 = bs[0]["tb"]
+            m_enc, m_dec = (tb0.enc_in != 0).float(), (tb0.dec_in != 0).float()
+            live, distinct = _site_stats([(tb0.enc_in, m_enc, 1), (tb0.dec_in, m_dec, 1), (tb0.dec_out, m_dec, 1),
+                                          (tb0.n_items, m_dec, K)], 0)
+            ab = st.algorithmic_bytes(distinct, live, int(m_dec.sum()))["total"]
+            seqs, tables = B, 1
+            steps_obj = [st]
+        else:
+            Wa = synth.item_table(n_items, d, seed=synth.SEED_WEIGHTS).to(dev)
+            Wb = synth.item_table(n_items, d, seed=synth.SEED_WEIGHTS + 1).to(dev)
+            rg_ = RecGuruStep(Wa, Wb, pe, B, L, K, kind)
+            bsa, bsb = mk(synth.SEED_DATA), mk(synth.SEED_DATA + 5000)
+            graphs = [rg_.capture_run(a["tb"], b["tb"], a["h"], b["h"], a["g"], b["g"]) for a, b in zip(bsa, bsb)]
+            ab = 0
+            for st_, b0 in ((rg_.dom[0], bsa[0]["tb"]), (rg_.dom[1], bsb[0]["tb"])):
+                m_out, m_enc = (b0.dec_out != 0).float(), (b0.enc_in != 0).float()
+                live, distinct = _site_stats([(b0.enc_in, m_out, 1), (b0.dec_in, m_enc, 1), (b0.dec_out, m_out, 1),
+                                              (b0.n_items, m_out, K)], None)
+                ab += st_.algorithmic_bytes(distinct, live, int(m_out.sum()))["total"]
+            seqs, tables = 2 * B, 2
+            steps_obj = rg_.dom
+        from recguru_b200 import _lib
+        l0 = _lib.launch_count()
+        graphs[0].replay()                      # graph replays do not pass through the C ABI: count eagerly below
+        torch.cuda.synchronize()
+        n_sustain = max(200, K_steps)
+        with ClockSampler(torch.cuda.current_device()) as cs:
+            timed_loop(D, lambda i: graphs[i % n_batches].replay(), n_sustain, Wm)
+            ms = timed_loop(D, lambda i: graphs[i % n_batches].replay(), K_steps, Wm)
+        per = ms / K_steps
+        out[vname] = {"metric": "train seqs/sec", "value": seqs * D.world / (per * 1e-3), "unit": "seqs/s",
+                      "ms_per_step": per, "steps": K_steps,
+                      "sequences_per_step": seqs, "tables": tables, "K": K, "kind": kind,
+                      "loss": float(steps_obj[0].sbuf["aux"][0].item()),
+                      "roofline": {"bound": "hbm", "kernel": "whole step", "algorithmic_mb": round(ab / 1e6, 1),
+                                   "achieved": round(ab / 1e6 / per, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                   "frac": round(ab / 1e6 / per / peaks["hbm"], 3), "traffic": None,
+                                   "note": "all algorithmic bytes of the step (every lookup site, one table backward "
+                                           "per table incl. its dense zero fill) over the timed step"},
+                      "clocks": cs.summary()}
+        del graphs
+        torch.cuda.empty_cache()
+    conf = {"cfg1": "configs[0] AutoRec single-domain hot-path step: 10k items, L=50, d=64, B=256; input sites enc_in + "
+                    "dec_in; reconstruction (K=30 sampled softmax) and BPR fine-tune (K=5 BPRLoss_sas)",
+            "cfg3": "configs[2] RecGURU two-domain hot-path step (reconstruction phase): 2 x 500k items, L=100, d=128, "
+                    "B=1024 per domain, K=30 sampled softmax, tables without padding_idx, 4 lookup sites per domain"}
+    return {"config": {"workload": conf[which], **cfg}, "launch_mode": "cuda_graph (one graph per rotating batch)",
+            "variants": out}
 
 # ----------------------------------------------------------------------------------------------
 # workload 2: full-catalog eval
 # ----------------------------------------------------------------------------------------------
+def grid_rows(lo: int, hi: int, d: int, salt: int, dev) -> torch.Tensor:
+    """Rows [lo, hi) of a grid-valued matrix (values k/16, |k| <= 32) as a pure function of (row, column,
+    salt): any rank can generate any row, so the data -- and every exact score on it -- does not depend on
+    how the catalog is sharded."""
+    out = torch.empty(hi - lo, d, dtype=torch.float32, device=dev)
+    c = torch.arange(d, device=dev, dtype=torch.int64)[None, :]
+    for r0 in range(lo, hi, 1 << 20):
+        r1 = min(hi, r0 + (1 << 20))
+        i = torch.arange(r0, r1, device=dev, dtype=torch.int64)[:, None]
+        h = i * 2654435761 + c * 40503 + (i >> 5) * (c + 7) * 977 + salt * 7919
+        h = (h ^ (h >> 13)) * 1274126177
+        h = h ^ (h >> 16)
+        out[r0 - lo:r1 - lo] = ((h % 65) - 32).to(torch.float32) / 16.0
+    return out
+
+
+def catalog_checksums(D: Dist, ev, cfg, u_step: int, G: int, dev):
+    """One step of the TIMED path (same evaluator class, same shard layout, same user count, same
+    kernels) on grid-valued users/items, where every bf16 x bf16 -> fp32 score is exact in any
+    summation order: ranks and top-k are then a function of the data alone, so these checksums must
+    be IDENTICAL at N = 1/2/4/8 (SURVEY 8e "shard-count-independent bit-identical") -- and rank 0
+    verifies 256 of its users against plain fp32 torch arithmetic over the whole catalog."""
+    from recguru_b200 import ops, catalog
+    n_items, d, k = cfg["n_items"], cfg["d"], cfg["k"]
+    lo, hi = ev.id_lo - 1, ev.id_lo - 1 + ev.n_local
+    chk = catalog.CatalogEvaluator.__new__(catalog.CatalogEvaluator)
+    chk.__dict__.update(ev.__dict__)
+    chk.items = ops.raw_cast_bf16(grid_rows(lo, hi, d, 1, dev))
+    u_loc = u_step // G
+    u0 = ev.rank * u_loc
+    users = grid_rows(u0, u0 + u_loc, d, 2, dev)
+    ui = torch.arange(u0, u0 + u_loc, device=dev, dtype=torch.int64)
+    target = (ui * 2654435761 + 12345) % n_items + 1
+    val, idx, rank = chk.rank_topk(users, target, u_max=u_loc)
+    rank_only = chk.target_rank(users, target, u_max=u_loc)
+    acc = torch.zeros(2 + 24, dtype=torch.float64, device=dev)
+    acc[0] = rank.sum().double()
+    acc[1] = val.double().sum()
+    for b in range(24):
+        acc[2 + b] = ((idx >> b) & 1).sum().double()
+    same_rank = torch.tensor([float(torch.equal(rank, rank_only))], dtype=torch.float64, device=dev)
+    if D.dist is not None:
+        D.dist.all_reduce(acc)
+        D.dist.all_reduce(same_rank, op=D.dist.ReduceOp.MIN)
+    xor = 0
+    for b in range(24):
+        xor |= (int(acc[2 + b].item()) & 1) << b
+    out = {"users": u_step, "rank_sum": int(acc[0].item()), "topk_id_xor": xor, "topk_val_sum": float(acc[1].item()),
+           "rank_only_equals_topk_mode": bool(same_rank.item() == 1.0),
+           "data": "grid-valued (k/16) users and items generated from (row, column) hashes: shard-count independent"}
+    if D.rank == 0:
+        # parity against fp32 torch on the whole catalog for the first 256 users of rank 0
+        torch.backends.cuda.matmul.allow_tf32 = False
+        nu = min(256, u_loc)
+        uu, tt = users[:nu], target[:nu] - 1
+        ref_rank = torch.zeros(nu, dtype=torch.int64, device=dev)
+        best = torch.full((nu, k), float("-inf"), device=dev)
+        tsc = None
+        for n0 in range(0, n_items, 1 << 20):
+            n1 = min(n_items, n0 + (1 << 20))
+            it = grid_rows(n0, n1, d, 1, dev)
+            s_ = uu @ it.t()
+            if tsc is None:
+                tsc = torch.zeros(nu, device=dev)
+            inside = (tt >= n0) & (tt < n1)
+            if bool(inside.any()):
+                tsc[inside] = s_[inside, (tt[inside] - n0)]
+            best = torch.cat([best, s_.topk(k, dim=1).values], 1).topk(k, dim=1).values
+            del s_, it
+        for n0 in range(0, n_items, 1 << 20):
+            n1 = min(n_items, n0 + (1 << 20))
+            s_ = uu @ grid_rows(n0, n1, d, 1, dev).t()
+            cols = torch.arange(n0, n1, device=dev)[None, :]
+            ref_rank += (s_ > tsc[:, None]).sum(1) + ((s_ == tsc[:, None]) & (cols < tt[:, None])).sum(1)
+            del s_
+        vi = val[:nu]
+        ii = idx[:nu]
+        ties_ok = bool((~(vi[:, 1:] == vi[:, :-1]) | (ii[:, 1:] > ii[:, :-1])).all())
+        out["vs_torch_fp32"] = {"users_checked": nu, "ranks_equal": bool(torch.equal(rank[:nu], ref_rank)),
+                                "topk_values_equal": bool(torch.equal(vi, best)), "ties_ascending_id": ties_ok}
+    return out
+
+
 def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
     from recguru_b200 import _lib, ops, catalog
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -639,7 +956,7 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
         items[r0:r1] = ops.raw_cast_bf16(torch.randn(r1 - r0, d, generator=gen, device=dev))
     ev = catalog.CatalogEvaluator.__new__(catalog.CatalogEvaluator)
     ev.k, ev.group, ev.world, ev.rank = k, (D.group() if sharded else None), G, (D.rank if sharded else 0)
-    ev.id_lo, ev.n_local, ev.n_items, ev.d, ev.items = 1 + lo, hi - lo, n_items, d, items
+    ev.id_lo, ev.n_local, ev.n_items, ev.d, ev.items, ev.id_first = 1 + lo, hi - lo, n_items, d, items, 1
     u_step = USERS_PER_STEP
     u_loc = u_step // G
     n_chunks = 4
@@ -650,10 +967,12 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
     steps = max(3, min(args.steps, 10 if n_items <= 1_000_000 else 4))
     warm = max(3, min(args.warmup, 3))
     res = {}
+    parity = catalog_checksums(D, ev, cfg, u_step, G, dev)     # before timing: proves THIS path on THIS box
+    torch.cuda.empty_cache()
 
     def step(i):
         j = i % n_chunks
-        res["out"] = ev.rank_topk(users_bf[j], targets[j])
+        res["out"] = ev.rank_topk(users_bf[j], targets[j], u_max=u_loc)
 
     l0 = _lib.launch_count()
     with ClockSampler(torch.cuda.current_device()) as cs:
@@ -672,7 +991,8 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
             ops.raw_catalog_topk_rank(users_bf[i % n_chunks], items, targets[i % n_chunks], ts, k, ev.id_lo, bufs=bufs)
         sweep_ms = timed_loop(D, sweep, steps, warm) / steps
     # rank-only mode (k = 0; what HR/NDCG/MRR need -- CatalogEvaluator.target_rank / evaluate)
-    ms_rank = timed_loop(D, lambda i: ev.target_rank(users[i % n_chunks], targets[i % n_chunks]), steps, warm) / steps
+    ms_rank = timed_loop(D, lambda i: ev.target_rank(users[i % n_chunks], targets[i % n_chunks], u_max=u_loc),
+                         steps, warm) / steps
     flops = 2.0 * u_step * (hi - lo) * d
     rank_only = {"ms_per_step": round(ms_rank, 3), "users_per_s": round(u_step / (ms_rank * 1e-3)),
                  "tflops": round(flops / (ms_rank * 1e-3) / 1e12, 1),
@@ -694,7 +1014,7 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
 
     def e2e(i):
         d_u.copy_(pin_u[i % 2], non_blocking=True); d_t.copy_(pin_t[i % 2], non_blocking=True)
-        _, _, rk = ev.rank_topk(d_u, d_t)               # includes the fp32->bf16 cast kernel
+        _, _, rk = ev.rank_topk(d_u, d_t, u_max=u_loc)  # includes the fp32->bf16 cast kernel
         rank_host.copy_(rk, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     ms_e2e = timed_loop(D, e2e, steps, warm) / steps
@@ -710,7 +1030,7 @@ def bench_catalog(D: Dist, args, peaks, cfg, name, sharded: bool):
         "e2e": {"value": u_step / (ms_e2e * 1e-3), "unit": "users/s",
                 "h2d_bytes_per_step": u_loc * (d * 4 + 8), "d2h_bytes_per_step": u_loc * 8, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "clocks": cs.summary(),
-        "hr10_synthetic": met[10]["hr"],
+        "hr10_synthetic": met[10]["hr"], "parity": parity,
     }
 
 
@@ -752,6 +1072,14 @@ def cpu_catalog_fn(cfg, U_cpu: int):
     return step
 
 
+def train_config():
+    """`config` of the primary line -- identical in both arms (the reference arm runs the same workload)."""
+    return {"workload": "cfg2 SASRec hot-path training step (configs[1]): 100k items, L=200, "
+                        "d=128, B=1024/GPU, K=5, BPRLoss_sas; replicas only for N>1",
+            "l2": "4 rotating batches (h+g+out = 315 MB each) > 126 MB L2",
+            **{k: v for k, v in CFG2.items()}}
+
+
 def time_cpu(fn, steps, warmup):
     for _ in range(warmup):
         fn()
@@ -774,13 +1102,13 @@ def run_reference(args):
         sample = f"{U_cpu} users x {cfg['n_items']} items per step (u@W^T + double argsort + metrics)"
         conf = {"workload": "cfg5 full-catalog eval, 10M items, d=128 (bounded CPU sample)"}
     else:
-        cfg, B_cpu = CFG2, 512
+        cfg, B_cpu = CFG2, CFG2["B"]
         steps = max(1, min(args.steps, 20))
         sec = time_cpu(cpu_train_step_fn(cfg, B_cpu), steps, max(1, min(args.warmup, 3)))
         val, unit, metric = B_cpu / sec, "seqs/s", "train seqs/sec"
-        sample = (f"{B_cpu} of {cfg['B']} sequences per step (F.embedding+pe+mask, sampled matmuls, "
+        sample = (f"the full batch: {B_cpu} of {cfg['B']} sequences per step (F.embedding+pe+mask, sampled matmuls, "
                   f"BPRLoss_sas, autograd backward incl. dense [V1,d] embedding grads)")
-        conf = {"workload": "cfg2 SASRec hot-path training step: 100k items, L=200, d=128, K=5 (bounded CPU sample)"}
+        conf = train_config()
     line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf,
@@ -793,13 +1121,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "catalog"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
-    ap.add_argument("--only", default="", help="comma list of sections: train,gather,cfg4,cfg5")
+    ap.add_argument("--only", default="", help="comma list of sections: train,gather,cfg1,cfg3,cfg4,cfg5")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     # The JSON line must be the only thing on stdout.  Libraries write there too (NCCL prints its
@@ -831,6 +1159,11 @@ def main():
             gather = bench_gather(D, args, peaks, W, pe, batches)
         del W, pe, batches
         torch.cuda.empty_cache()
+    topo = {}
+    for which in ("cfg1", "cfg3"):
+        if want(which):
+            topo[which] = bench_topology(D, args, peaks, which)
+            torch.cuda.empty_cache()
     cat = {}
     if D.world == 1 and want("cfg4"):
         cat["cfg4"] = bench_catalog(D, args, peaks, CFG4, "cfg4 full-catalog eval 1M users x 1M items, d=128, top-10", False)
@@ -845,10 +1178,18 @@ def main():
         cores = os.cpu_count()
         torch.set_num_threads(cores)
         if args.workload == "train":
-            B_cpu = 512
+            B_cpu = CFG2["B"]
             sec = time_cpu(cpu_train_step_fn(CFG2, B_cpu), 10, 2)
+            for cname, ccfg, U_cpu in (("cfg4", CFG4, 64), ("cfg5", CFG5, 16)):
+                if cname in cat:
+                    csec = time_cpu(cpu_catalog_fn(ccfg, U_cpu), 2, 1)
+                    cat[cname]["cpu_baseline"] = {
+                        "value": U_cpu / csec, "unit": "users/s", "cores": cores, "kind": "port",
+                        "sample": f"{U_cpu} users x {ccfg['n_items']} items per step, 2 steps: the reference's "
+                                  "u @ W^T (AutoEnc4Rec.py:230) + double argsort (train_auto.py:234-237) + "
+                                  "metrics.*_batch, fp32; users/s is linear in the user count (extrapolated)"}
             cpu = {"value": B_cpu / sec, "unit": "seqs/s", "cores": cores, "kind": "port",
-                   "sample": f"{B_cpu} of {CFG2['B']} sequences per step, 10 steps, reference ATen op sequence (oracle/ref_path.py)"}
+                   "sample": f"the full batch ({B_cpu} sequences) per step, 10 steps, reference ATen op sequence (oracle/ref_path.py)"}
         else:
             U_cpu = 8
             sec = time_cpu(cpu_catalog_fn(CFG5, U_cpu), 2, 1)
@@ -861,21 +1202,24 @@ def main():
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": train["ms_per_step"],
                     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                     "data": "synthetic",
-                    "config": {"workload": "cfg2 SASRec hot-path training step (configs[1]): 100k items, L=200, "
-                                           "d=128, B=1024/GPU, K=5, BPRLoss_sas; replicas only for N>1",
-                               "l2": "4 rotating batches (h+g+out = 315 MB each) > 126 MB L2",
-                               **{k: v for k, v in CFG2.items()}},
+                    "config": train_config(),
                     "roofline": train["roofline"], "stages": train["stages"], "e2e": train["e2e"],
                     "gpu_launches": train["gpu_launches"], "clocks": train["clocks"],
                     "algorithmic_mb_per_step": train["algorithmic_mb_per_step"],
                     "table_backward": train["table_backward"], "launch_mode": train["launch_mode"],
                     "ms_per_step_eager": train["ms_per_step_eager"],
                     "ms_per_step_serialised_stages": train["ms_per_step_serialised_stages"],
+                    "sustained": train["sustained"], "dropin_surface": train["dropin_surface"],
                     "table_adam": train["table_adam"], "e2e_device_negatives": train["e2e_device_negatives"],
                     "e2e_device_batches": train["e2e_device_batches"]}
             if gather is not None:
                 line["gather"] = gather
             line["catalog"] = cat
+            line["train_topologies"] = topo
+            if "cfg5" in cat:       # top-level copies of the strong-scaling metric (the primary line is replicas)
+                line["catalog_cfg5_users_per_s"] = cat["cfg5"]["value"]
+                line["catalog_cfg5_e2e_users_per_s"] = cat["cfg5"]["e2e"]["value"]
+                line["catalog_cfg5_scaling"] = "strong"
         else:
             c = cat.get("cfg5") or cat.get("cfg4")
             line = {"metric": c["metric"], "value": c["value"], "unit": c["unit"], "n_gpus": D.world,

@@ -17,6 +17,15 @@
  *       RECGURU_E_UNSUPPORTED(-2)  unsupported d / K / size
  *       RECGURU_E_CUDA       (-3)  CUDA launch error (see recguru_last_error())
  *       RECGURU_E_WORKSPACE  (-4)  workspace too small
+ *       RECGURU_E_INDEX      (-5)  an item id outside [0, V1) -- only reported when the
+ *                                  environment has RECGURU_CHECK_IDS=1 (debug aid: the check
+ *                                  synchronises the stream; nn.Embedding raises IndexError /
+ *                                  a device assert for the same input)
+ *   - thread / device model: entry points may be called concurrently from several host
+ *     threads and on several devices of one process (nn.DataParallel, train_auto.py:350-351);
+ *     work goes to the CURRENT device (cudaGetDevice) on `stream`.  Host-side caches (SM
+ *     count, kernel attributes) are kept per device; the only process-wide state is the
+ *     launch counter and the thread-local error string.
  *   - row-major fp32 tables; ids are int64 on arrival (numpy int64 -> default_collate,
  *     data/data_loader.py:36,418-421) and are narrowed to int32 internally (V1 < 2^31).
  */
@@ -34,6 +43,7 @@ extern "C" {
 #define RECGURU_E_UNSUPPORTED (-2)
 #define RECGURU_E_CUDA (-3)
 #define RECGURU_E_WORKSPACE (-4)
+#define RECGURU_E_INDEX (-5)
 
 /* loss kinds for the sampled-scoring ops */
 #define RECGURU_LOSS_BPR 0     /* tools/lossfunctions.py:52-72  BPRLoss               */
@@ -315,6 +325,11 @@ int recguru_sample_negatives_csr(const int64_t* items, const int64_t* offsets, c
                                  int64_t* n_items_out, recguru_stream_t stream);
 /* *counter += inc on the stream (a one-thread kernel; graph-capturable step bookkeeping). */
 int recguru_counter_add(uint64_t* counter, uint64_t inc, recguru_stream_t stream);
+/* ids_out[i] = (int64) ids32_in[i].  The reference's loaders hand over int64 ids (numpy int64 ->
+ * default_collate, data/data_loader.py:36,:418-421) although every id is < V1 < 2^31; a loader
+ * that collates into pinned int32 halves the per-step host->device traffic (11.5 -> 5.7 MB at
+ * cfg2, the PCIe-bound part of the end-to-end step) and widens here.  16-byte aligned buffers. */
+int recguru_widen_ids(const int32_t* ids32_in, int64_t n, int64_t* ids_out, recguru_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * SURVEY 8f rank 3 (second half) -- batch builder of the loaders:

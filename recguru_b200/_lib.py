@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "librecguru_b200.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_SITES = 8
 LOSS_KINDS = {"bpr": 0, "bpr_sas": 1, "sce": 2}
 LOSS_SKIP_MASKED = 0x100
@@ -78,6 +78,7 @@ SIGNATURES = {
     "recguru_sample_negatives_csr": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
                                                c_i64, C.c_uint64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
     "recguru_counter_add": (C.c_int, [c_ptr, C.c_uint64, c_ptr]),
+    "recguru_widen_ids": (C.c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "recguru_embedding_bwd_mark_rows": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_ptr, c_i64, c_ptr, C.c_uint32, c_ptr]),
     "recguru_table_adam_rows": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_uint32, c_i64, c_i64, C.c_double,
                                           C.c_double, C.c_double, C.c_double, c_i64, c_ptr]),

@@ -47,7 +47,16 @@ def _stale(target: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, debug_knobs: bool | None = None) -> Path:
+    """``debug_knobs`` (or ``RECGURU_BUILD_DEBUG_KNOBS=1``): also compile the catalog sweep's bisection
+    knobs, clock64 trace globals and experimental instantiations (-DRECGURU_DEBUG_KNOBS).  The
+    production library is built without them."""
+    if debug_knobs is None:
+        debug_knobs = os.environ.get("RECGURU_BUILD_DEBUG_KNOBS", "0") not in ("", "0")
+    flags = NVCC_FLAGS + (["-DRECGURU_DEBUG_KNOBS"] if debug_knobs else [])
+    stamp = OBJDIR / ("flavour_debug" if debug_knobs else "flavour_prod")
+    if not stamp.exists():          # switching flavour rebuilds everything
+        force = True
     srcs = sources()
     headers = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "recguru_b200.h"]
     if not force and not _stale(LIB, srcs + headers):
@@ -55,11 +64,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     OBJDIR.mkdir(parents=True, exist_ok=True)
     LIBDIR.mkdir(parents=True, exist_ok=True)
+    for f in OBJDIR.glob("flavour_*"):
+        f.unlink()
 
     def compile_one(src: Path) -> Path:
         obj = OBJDIR / (src.stem + ".o")
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [nvcc, *flags, "-c", str(src), "-o", str(obj)]
             if verbose:
                 print(" ".join(cmd), flush=True)
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -75,6 +86,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    stamp.touch()
     return LIB
 
 
@@ -82,8 +94,10 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("--debug-knobs", action="store_true", default=None,
+                    help="compile the catalog sweep's debug knobs and experimental variants in")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, debug_knobs=a.debug_knobs))
 
 
 if __name__ == "__main__":

@@ -124,8 +124,11 @@ class CatalogEvaluator:
         self.id_lo = id_lo + lo                      # catalog id of local row 0
         self.n_local = hi - lo
         self.n_items = n_items
+        self.id_first = id_lo                        # first catalog id of the whole (unsharded) range
         self.d = weight.shape[1]
-        self.items = self._prepare_items(weight[id_lo + lo: id_lo + hi])
+        rows = weight[id_lo + lo: id_lo + hi]
+        # an empty shard (n_items < world) keeps no items and skips its local sweep
+        self.items = self._prepare_items(rows) if self.n_local > 0 else rows.new_zeros((0, self.d), dtype=torch.bfloat16)
 
     # -- local compute: CUDA kernels (tests for the host logic subclass and override these) --
     def _prepare_items(self, rows: Tensor) -> Tensor:
@@ -145,58 +148,97 @@ class CatalogEvaluator:
     def _merge(self, vals: Tensor, ids: Tensor, counts: Tensor):
         return ops.raw_topk_merge(vals, ids, counts)
 
+    # -- sharded plumbing ---------------------------------------------------------------
+    def _uniform_count(self, U_loc: int, device, u_max: Optional[int]) -> int:
+        """Every rank must enter the fixed-size collectives with the same number of users.  Ranks
+        may hold different counts (a ragged last batch): the maximum is agreed on with one small
+        all-reduce (a host sync) unless the caller states it (``u_max``), and each rank pads up."""
+        if u_max is not None:
+            if u_max < U_loc:
+                raise ValueError(f"recguru: u_max={u_max} is smaller than this rank's {U_loc} users")
+            return int(u_max)
+        t = torch.tensor([U_loc], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    @staticmethod
+    def _pad_rows(x: Tensor, n: int, fill=0) -> Tensor:
+        if x.shape[0] == n:
+            return x
+        out = x.new_full((n, *x.shape[1:]), fill)
+        out[: x.shape[0]] = x
+        return out
+
+    def _gather_users(self, u: Tensor, target: Tensor, u_max: Optional[int]):
+        G = self.world
+        U_loc = u.shape[0]
+        U_pad = self._uniform_count(U_loc, u.device, u_max)
+        u = self._pad_rows(u, U_pad)                       # padded users: zero vectors, target = first id
+        target = self._pad_rows(target.contiguous(), U_pad, fill=self.id_first)
+        u_all = torch.empty(G * U_pad, self.d, dtype=u.dtype, device=u.device)
+        t_all = torch.empty(G * U_pad, dtype=torch.int64, device=u.device)
+        dist.all_gather_into_tensor(u_all, u, group=self.group)
+        dist.all_gather_into_tensor(t_all, target, group=self.group)
+        # target score: the owner shard computes it on its tensor cores, the others add 0
+        if self.n_local > 0:
+            ts = self._local_target_scores(u_all, t_all)
+        else:                                              # empty shard (n_items < world): contributes nothing
+            ts = torch.zeros(G * U_pad, dtype=torch.float32, device=u.device)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=self.group)
+        return u_all, t_all, ts, U_loc, U_pad
+
     # -- public ---------------------------------------------------------------------------
-    def rank_topk(self, users: Tensor, target: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    def rank_topk(self, users: Tensor, target: Tensor, u_max: Optional[int] = None
+                  ) -> Tuple[Tensor, Tensor, Tensor]:
         """users [U_local, d] (fp32 or bf16), target [U_local] int64 catalog ids ->
-        (topk_val [U_local,k] fp32, topk_id [U_local,k] int64, rank [U_local] int64)."""
+        (topk_val [U_local,k] fp32, topk_id [U_local,k] int64, rank [U_local] int64).
+
+        Sharded: ranks may pass different numbers of users (also 0); ``u_max`` = the largest
+        count over the ranks if the caller knows it (skips one small all-reduce + host sync).
+        Shards may be empty (``n_items < world``)."""
         u = self._prepare_users(users)
         if self.world == 1:
             ts = self._local_target_scores(u, target)
             return self._local_topk_rank(u, target, ts)
-        G, g = self.world, self.rank
-        U_loc = u.shape[0]
-        # (1) all-gather user reps (bf16) and targets: every shard scores every user
-        u_all = torch.empty(G * U_loc, self.d, dtype=u.dtype, device=u.device)
-        t_all = torch.empty(G * U_loc, dtype=torch.int64, device=u.device)
-        dist.all_gather_into_tensor(u_all, u, group=self.group)
-        dist.all_gather_into_tensor(t_all, target.contiguous(), group=self.group)
-        # (2) target score: the owner shard computes it on its tensor cores, the others add 0
-        ts = self._local_target_scores(u_all, t_all)
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=self.group)
+        G, k = self.world, self.k
+        # (1)+(2) all-gather user reps (bf16) and targets, all-reduce the target score
+        u_all, t_all, ts, U_loc, U_pad = self._gather_users(u, target, u_max)
         # (3) local sweep over this shard's items
-        val, idx, cnt = self._local_topk_rank(u_all, t_all, ts)
+        if self.n_local > 0:
+            val, idx, cnt = self._local_topk_rank(u_all, t_all, ts)
+        else:
+            val = torch.full((G * U_pad, k), float("-inf"), dtype=torch.float32, device=u.device)
+            idx = torch.full((G * U_pad, k), -1, dtype=torch.int64, device=u.device)
+            cnt = torch.zeros(G * U_pad, dtype=torch.int64, device=u.device)
         # (4) exchange: rank r receives every shard's results for ITS users (all-to-all by user)
-        k = self.k
-        val_x = torch.empty(G, U_loc, k, dtype=val.dtype, device=val.device)
-        idx_x = torch.empty(G, U_loc, k, dtype=idx.dtype, device=idx.device)
-        cnt_x = torch.empty(G, U_loc, dtype=cnt.dtype, device=cnt.device)
-        dist.all_to_all_single(val_x, val.view(G, U_loc, k), group=self.group)
-        dist.all_to_all_single(idx_x, idx.view(G, U_loc, k), group=self.group)
-        dist.all_to_all_single(cnt_x, cnt.view(G, U_loc), group=self.group)
+        val_x = torch.empty(G, U_pad, k, dtype=val.dtype, device=val.device)
+        idx_x = torch.empty(G, U_pad, k, dtype=idx.dtype, device=idx.device)
+        cnt_x = torch.empty(G, U_pad, dtype=cnt.dtype, device=cnt.device)
+        dist.all_to_all_single(val_x, val.view(G, U_pad, k), group=self.group)
+        dist.all_to_all_single(idx_x, idx.view(G, U_pad, k), group=self.group)
+        dist.all_to_all_single(cnt_x, cnt.view(G, U_pad), group=self.group)
         # (5) merge the G per-shard lists (desc score, asc id) and sum the rank counts
-        return self._merge(val_x, idx_x, cnt_x)
+        v, i, r = self._merge(val_x, idx_x, cnt_x)
+        return v[:U_loc], i[:U_loc], r[:U_loc]
 
     def _local_rank(self, users_bf16: Tensor, target: Tensor, tscore: Tensor) -> Tensor:
         return ops.raw_catalog_topk_rank(users_bf16, self.items, target, tscore, 0, self.id_lo)[2]
 
-    def target_rank(self, users: Tensor, target: Tensor) -> Tensor:
+    def target_rank(self, users: Tensor, target: Tensor, u_max: Optional[int] = None) -> Tensor:
         """Target ranks only (what HR/NDCG/MRR need): the sweep runs in its rank-only mode -- no
         group maxima, no top-k lists -- and the shards exchange one count per user."""
         u = self._prepare_users(users)
         if self.world == 1:
             return self._local_rank(u, target, self._local_target_scores(u, target))
         G = self.world
-        U_loc = u.shape[0]
-        u_all = torch.empty(G * U_loc, self.d, dtype=u.dtype, device=u.device)
-        t_all = torch.empty(G * U_loc, dtype=torch.int64, device=u.device)
-        dist.all_gather_into_tensor(u_all, u, group=self.group)
-        dist.all_gather_into_tensor(t_all, target.contiguous(), group=self.group)
-        ts = self._local_target_scores(u_all, t_all)
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=self.group)
-        cnt = self._local_rank(u_all, t_all, ts)
-        cnt_x = torch.empty(G, U_loc, dtype=cnt.dtype, device=cnt.device)
-        dist.all_to_all_single(cnt_x, cnt.view(G, U_loc), group=self.group)
-        return cnt_x.sum(0)
+        u_all, t_all, ts, U_loc, U_pad = self._gather_users(u, target, u_max)
+        if self.n_local > 0:
+            cnt = self._local_rank(u_all, t_all, ts)
+        else:
+            cnt = torch.zeros(G * U_pad, dtype=torch.int64, device=u.device)
+        cnt_x = torch.empty(G, U_pad, dtype=cnt.dtype, device=cnt.device)
+        dist.all_to_all_single(cnt_x, cnt.view(G, U_pad), group=self.group)
+        return cnt_x.sum(0)[:U_loc]
 
     def evaluate(self, users: Tensor, target: Tensor, ks: Sequence[int] = (5, 10, 20, 30)):
         """Ranks + HR/NDCG/MRR@k for this rank's users (global metrics need a sum of the

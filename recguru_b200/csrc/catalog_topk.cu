@@ -44,8 +44,22 @@ constexpr int kFmaSignCols = 16;  // of every 32 columns, sign bits accumulated 
 
 enum CatalogMode { kModeTopK = 0, kModeDense = 1, kModeRank = 2 };   // Rank: target rank only (k = 0)
 
-// debug profile (RECGURU_CATALOG_PROF=1): cycles CTA (0,0) spends in each wait, per role
+// Build flag RECGURU_DEBUG_KNOBS (python -m recguru_b200.build --debug-knobs): compiles the
+// RECGURU_CATALOG_DEBUG bisection knobs, the clock64 profile/trace globals and the experimental
+// instantiations (4 epilogue sets, cluster multicast, A-in-TMEM, 256-item tiles, deeper smem ring,
+// software-pipelined epilogue) into the library.  The production library carries none of them.
+#ifdef RECGURU_DEBUG_KNOBS
+constexpr bool kDebugKnobs = true;
+#else
+constexpr bool kDebugKnobs = false;
+#endif
+// debug profile (RECGURU_CATALOG_DEBUG & 512): cycles CTA (0,0) spends in each wait, per role
+#ifdef RECGURU_DEBUG_KNOBS
 __device__ long long g_prof[16];
+#define RG_DBG(...) __VA_ARGS__
+#else
+#define RG_DBG(...)
+#endif
 // debug flag 65536: per-tile timestamps (clock64, CTA 0) of a window of tiles:
 // [tile][0] MMA warp: accumulator slot seen empty   [1] operands seen full   [2] MMAs + commit issued
 // [tile][3] epilogue: accumulator seen full         [4] epilogue: slot handed back
@@ -54,7 +68,7 @@ constexpr int kTraceTiles = 64, kTraceFirst = 2000;
 // setmaxnreg budget with 12 warps (NSETS == 2): 4*32*kCtlRegs + 8*32*kEpiRegs <= 12*32*168
 constexpr int kCtlRegs = 56, kEpiRegs = 224;
 static_assert(4 * kCtlRegs + 8 * kEpiRegs <= 12 * 168, "register budget");
-__device__ long long g_trace[kTraceTiles][8];
+RG_DBG(__device__ long long g_trace[kTraceTiles][8];)
 
 struct CatalogParams {
   int64_t U;
@@ -196,8 +210,8 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       // both.  Otherwise (deeper smem ring, or a cluster whose peer's MMAs count too) the stage has
       // its own barrier.
       ptx::mbar_wait_warp(kCoupled ? &bar_acc_full[s] : &bar_empty[s], ph ^ 1, spin);
-      if (prof && lane == 0) g_prof[0] += clock64() - tp0;
-      if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) g_trace[j - kTraceFirst][5] = clock64();
+      RG_DBG(if (prof && lane == 0) g_prof[0] += clock64() - tp0;)
+      RG_DBG(if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) g_trace[j - kTraceFirst][5] = clock64();)
       if (leader) {
         if ((dflags & 4u) && j >= NSTG) {   // debug: no operand traffic (timing floor)
           ptx::mbar_arrive(&bar_full[s]);
@@ -219,7 +233,7 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         }
       }
       __syncwarp();
-      if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) g_trace[j - kTraceFirst][6] = clock64();
+      RG_DBG(if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) g_trace[j - kTraceFirst][6] = clock64();)
     }
   } else if (warp == 1 || warp == 2) {
     // ===================== MMA issuers (whole warp loops; one elected lane issues) =========
@@ -276,10 +290,10 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
       }
       __syncwarp();
       if (prof && lane == 0 && warp == 1) {
-        g_prof[1] += tm1 - tm0; g_prof[2] += tm2 - tm1; g_prof[3] += clock64() - tm2; g_prof[4] += 1;
+        RG_DBG(g_prof[1] += tm1 - tm0; g_prof[2] += tm2 - tm1; g_prof[3] += clock64() - tm2; g_prof[4] += 1;)
       }
       if (trace && lane == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) {
-        g_trace[j - kTraceFirst][0] = tm1; g_trace[j - kTraceFirst][1] = tm2; g_trace[j - kTraceFirst][2] = clock64();
+        RG_DBG(g_trace[j - kTraceFirst][0] = tm1; g_trace[j - kTraceFirst][1] = tm2; g_trace[j - kTraceFirst][2] = clock64();)
       }
     }
   } else if (warp == 3) {
@@ -694,11 +708,11 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
         if (lane == 0) ptx::mbar_arrive_addr(acc_empty_addr + a * 8);
       }
       if (trace && lane == 0 && quarter == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceTiles) {
-        g_trace[j - kTraceFirst][3] = te1; g_trace[j - kTraceFirst][4] = clock64();
+        RG_DBG(g_trace[j - kTraceFirst][3] = te1; g_trace[j - kTraceFirst][4] = clock64();)
       }
       if (prof && lane == 0 && (warp == 4 || warp == 8)) {
         const int o = warp == 4 ? 5 : 8;
-        g_prof[o] += te1 - te0; g_prof[o + 1] += clock64() - te1; g_prof[o + 2] += 1;
+        RG_DBG(g_prof[o] += te1 - te0; g_prof[o + 1] += clock64() - te1; g_prof[o + 2] += 1;)
       }
     }
     cnt += static_cast<int>(cf[0] + cf[1] + cf[2] + cf[3] + ca[0] + ca[1] + ca[2] + ca[3] + cf2[0] + cf2[1] +
@@ -859,16 +873,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encoder() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // function-local static: initialised once, thread-safe (C++11); the driver entry point is
+  // process-wide, not per device
+  static const EncodeTiledFn fn = [] {
     void* sym = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
+      return reinterpret_cast<EncodeTiledFn>(sym);
+    return static_cast<EncodeTiledFn>(nullptr);
+  }();
   return fn;
 }
 
@@ -893,8 +907,8 @@ static int make_rowmajor_map(CUtensorMap* map, const void* base, int64_t rows, i
 static int pick_splits(int64_t U, int64_t n_items, int bn) {
   const int64_t m_tiles = ceil_div(U, kBlockM);
   const int64_t n_tiles = ceil_div(n_items, bn);
-  if (m_tiles >= 2 * kNumSMs) return 1;
-  int64_t s = ceil_div(2 * kNumSMs, m_tiles);
+  if (m_tiles >= 2 * static_cast<int64_t>(num_sms())) return 1;
+  int64_t s = ceil_div(2 * static_cast<int64_t>(num_sms()), m_tiles);
   const int64_t max_s = n_tiles / 8 > 0 ? n_tiles / 8 : 1;  // >= 8 tiles per split
   if (s > max_s) s = max_s;
   if (s > 64) s = 64;
@@ -910,8 +924,12 @@ static int env_int(const char* name, int dflt) {
 // two 64 KB smem stages, which exposes the TMA latency: measured 46 ms vs 34 ms on cfg4
 // (profiles/catalog_exp23.log); kept as a knob.
 static int catalog_bn() {
+#ifdef RECGURU_DEBUG_KNOBS
   const int bn = env_int("RECGURU_CATALOG_BN", 128);
   return bn == 256 ? 256 : 128;
+#else
+  return 128;
+#endif
 }
 
 template <int D, int MODE, int NSETS, int CL, bool TS, int BN, int NST = 0, bool PIPE = false, bool RL = false>
@@ -919,23 +937,31 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
                           cudaStream_t st) {
   const int smem = CatSmem<D, BN, NST>::bytes(MODE == kModeTopK ? p.k : 0, NSETS);
   RG_REQUIRE(smem <= 227 * 1024, RECGURU_E_UNSUPPORTED, "catalog: k=%d needs %d B of shared memory", p.k, smem);
-  auto kern = p.debug_flags ? catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true, RL>
-                            : catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false, RL>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true, RL>,
+  auto kern = catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false, RL>;
+#ifdef RECGURU_DEBUG_KNOBS
+  if (p.debug_flags) kern = catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true, RL>;
+#endif
+  // the dynamic shared-memory limit is a per-device function attribute
+  static PerDeviceOnce once;
+  const int dev = current_device();
+  if (once.need(dev)) {
+    cudaError_t e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false, RL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#ifdef RECGURU_DEBUG_KNOBS
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, false, RL>,
+      e = cudaFuncSetAttribute(catalog_sweep_kernel<D, MODE, NSETS, CL, TS, BN, NST, PIPE, true, RL>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#endif
     RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog: cudaFuncSetAttribute: %s",
                cudaGetErrorString(e));
-    attr_set = true;
+    once.done(dev);
   }
+#ifdef RECGURU_DEBUG_KNOBS
   if (p.debug_flags & 512u) {
     long long z[16] = {0};
     cudaMemcpyToSymbol(g_prof, z, sizeof(z));
   }
+#endif
   cudaLaunchConfig_t cfg = {};
   const int64_t m_tiles = ceil_div(p.U, kBlockM);
   cfg.gridDim = dim3(static_cast<unsigned>(ceil_div(m_tiles, CL) * CL), static_cast<unsigned>(p.n_splits));
@@ -950,6 +976,7 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mu, mi, p);
   RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog_sweep: launch failed: %s", cudaGetErrorString(e));
   RG_CHECK_LAUNCH("catalog_sweep");
+#ifdef RECGURU_DEBUG_KNOBS
   if (p.debug_flags & 65536u) {
     static long long tr[kTraceTiles][8];
     cudaStreamSynchronize(st);
@@ -968,22 +995,28 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
             "epi set0 wait_full %lld work %lld tiles %lld | epi set1 wait_full %lld work %lld tiles %lld\n",
             h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10]);
   }
+#endif
   return RECGURU_OK;
 }
 
-// Epilogue sets: 2 (8 warps, one 128-register TMEM load per tile) by default; 4 is kept for
-// experiments.  Cluster of 2 with TMA multicast whenever there are at least two user tiles.
+// Production: 2 epilogue sets (8 warps, one 128-register TMEM load per tile), 128-item tiles, 4
+// coupled smem/TMEM stages, top-k lists in registers for k <= 16.  Everything else that was
+// measured without gain is compiled only with RECGURU_DEBUG_KNOBS.
 template <int D, int MODE>
 static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams p, int bn, cudaStream_t st) {
   p.two = 2u;
   p.debug_flags = static_cast<uint32_t>(env_int("RECGURU_CATALOG_DEBUG", 0));
+  RG_REQUIRE(kDebugKnobs || p.debug_flags == 0, RECGURU_E_UNSUPPORTED,
+             "catalog: RECGURU_CATALOG_DEBUG needs a library built with RECGURU_DEBUG_KNOBS "
+             "(python -m recguru_b200.build --debug-knobs)");
   p.tiles_per_split = static_cast<int>(ceil_div(ceil_div(p.n_items, bn), p.n_splits));
+  CUtensorMap mi;
+#ifdef RECGURU_DEBUG_KNOBS
   int nsets = env_int("RECGURU_CATALOG_SETS", 2);
   if (nsets != 2 && nsets != 4) nsets = 2;
   int cl = env_int("RECGURU_CATALOG_CLUSTER", 1);
   if (cl != 1 && cl != 2) cl = 1;
   if (p.U <= kBlockM) cl = 1;
-  CUtensorMap mi;
   if (bn == 256) {
     // 2 epilogue sets <-> 2 accumulators of 256 columns; knobs for sets / cluster / TS apply to
     // the 128-item variant only
@@ -991,19 +1024,19 @@ static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams 
     if (rc) return rc;
     return launch_sweep_n<D, MODE, 2, 1, false, 256>(mu, mi, p, st);
   }
-  int rc = make_rowmajor_map(&mi, items, p.n_items, D, 128 / cl);
-  if (rc) return rc;
+  {
+    int rc = make_rowmajor_map(&mi, items, p.n_items, D, 128 / cl);
+    if (rc) return rc;
+  }
   const bool ts = D == 128 && env_int("RECGURU_CATALOG_TS", 0) != 0;
-  if (ts) {   // experimental knob: measured no faster than SS; 2 epilogue sets only
+  if (ts) {   // measured no faster than SS; 2 epilogue sets only
     if constexpr (D == 128) return launch_sweep_n<D, MODE, 2, 1, true, 128>(mu, mi, p, st);
   }
   if (nsets == 4) return cl == 2 ? launch_sweep_n<D, MODE, 4, 2, false, 128>(mu, mi, p, st) : launch_sweep_n<D, MODE, 4, 1, false, 128>(mu, mi, p, st);
   if (cl == 2) return launch_sweep_n<D, MODE, 2, 2, false, 128>(mu, mi, p, st);
   // RECGURU_CATALOG_STAGES=5|6: item-tile ring deeper than (and decoupled from) the accumulator ring
-  int nst = env_int("RECGURU_CATALOG_STAGES", 0);
+  const int nst = env_int("RECGURU_CATALOG_STAGES", 0);
   const int k_eff = MODE == kModeTopK ? p.k : 0;
-  if (nst == 0) nst = 4;   // measured: 5 decoupled stages 34.4 ms vs 34.7 coupled (cfg4): within noise
-  // measured slower (41.8 vs 34.5 ms at cfg4): a warp's 64-column TMEM load is rate limited per warp
   const bool pipe = MODE == kModeTopK && env_int("RECGURU_CATALOG_PIPE", 0) != 0;
   if (nst == 6 && CatSmem<D, 128, 6>::bytes(k_eff, 2) <= 227 * 1024)
     return pipe ? launch_sweep_n<D, MODE, 2, 1, false, 128, 6, MODE == kModeTopK>(mu, mi, p, st)
@@ -1013,8 +1046,17 @@ static int launch_sweep(const void* items, const CUtensorMap& mu, CatalogParams 
                 : launch_sweep_n<D, MODE, 2, 1, false, 128, 5>(mu, mi, p, st);
   if (pipe && p.k <= 16) return launch_sweep_n<D, MODE, 2, 1, false, 128, 0, MODE == kModeTopK, MODE == kModeTopK>(mu, mi, p, st);
   if (pipe) return launch_sweep_n<D, MODE, 2, 1, false, 128, 0, MODE == kModeTopK>(mu, mi, p, st);
-  // default: k <= 16 keeps the top-k lists in registers (RECGURU_CATALOG_REGLIST=0: shared memory)
-  if (MODE == kModeTopK && p.k <= 16 && env_int("RECGURU_CATALOG_REGLIST", 1) != 0)
+  if (MODE == kModeTopK && p.k <= 16 && env_int("RECGURU_CATALOG_REGLIST", 1) == 0)
+    return launch_sweep_n<D, MODE, 2, 1, false, 128>(mu, mi, p, st);
+#else
+  (void)bn;
+  {
+    int rc = make_rowmajor_map(&mi, items, p.n_items, D, 128);
+    if (rc) return rc;
+  }
+#endif
+  // k <= 16 keeps the top-k lists in registers; larger k uses shared-memory lists
+  if (MODE == kModeTopK && p.k <= 16)
     return launch_sweep_n<D, MODE, 2, 1, false, 128, 0, false, MODE == kModeTopK>(mu, mi, p, st);
   return launch_sweep_n<D, MODE, 2, 1, false, 128>(mu, mi, p, st);
 }
@@ -1055,11 +1097,14 @@ extern "C" int recguru_catalog_target_scores(const void* users_bf16, int64_t U,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>(ceil_div(U, kBlockM));
   const int smem = static_cast<int>(2 * kBlockN * d * 2 + 64 + 1024);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(catalog_target_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(catalog_target_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
+  static PerDeviceOnce once;          // per-device function attribute
+  const int dev = current_device();
+  if (once.need(dev)) {
+    cudaError_t e = cudaFuncSetAttribute(catalog_target_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(catalog_target_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog_target: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    once.done(dev);
   }
   const __nv_bfloat16* items = static_cast<const __nv_bfloat16*>(items_bf16);
   if (d == 64)

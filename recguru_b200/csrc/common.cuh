@@ -39,7 +39,38 @@ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
-constexpr int kNumSMs = 148;  // B200
+// ---- per-device state ------------------------------------------------------------------
+// The library may be driven from one process on several devices and from several host threads
+// (the reference's only parallel mode is nn.DataParallel: one Python thread per GPU,
+// train_auto.py:350-351).  Everything cached on the host side is therefore keyed by the CURRENT
+// device; nothing is process-wide.
+constexpr int kMaxDevices = 64;
+int current_device();          // cudaGetDevice, -1 on error
+int num_sms();                 // multiprocessor count of the current device (148 on B200), cached
+// "done once per device" flag for per-device function attributes (cudaFuncSetAttribute is per
+// device, a process-wide static would leave every device but the first without it).
+struct PerDeviceOnce {
+  unsigned long long mask = 0;   // bit d set <=> done on device d (accessed with atomics)
+  bool need(int dev) const {
+    if (dev < 0 || dev >= kMaxDevices) return true;
+    return ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> dev) & 1ull) == 0;
+  }
+  void done(int dev) {
+    if (dev >= 0 && dev < kMaxDevices) __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELEASE);
+  }
+};
+// RECGURU_CHECK_IDS=1 (read once): every entry point that takes item ids verifies
+// 0 <= id < V1 on the device before launching and SYNCHRONISES the stream to report the first
+// offender (RECGURU_E_INDEX).  Debug aid: off by default, skipped while the stream is capturing.
+bool check_ids_enabled();
+int check_ids(const char* who, const int64_t* ids, int64_t n, int64_t lo, int64_t hi, cudaStream_t st);
+#define RG_CHECK_IDS(who, ids, n, lo, hi, st)                                  \
+  do {                                                                         \
+    if (rg::check_ids_enabled()) {                                             \
+      const int rc__ = rg::check_ids(who, ids, n, lo, hi, st);                 \
+      if (rc__) return rc__;                                                   \
+    }                                                                          \
+  } while (0)
 
 // ---- programmatic dependent launch ---------------------------------------------------
 // The training-step path is a chain of short kernels on one stream.  Every kernel of the chain

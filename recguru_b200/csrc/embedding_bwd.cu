@@ -790,7 +790,7 @@ extern "C" int recguru_sort_ids(const int64_t* ids, int64_t count, int64_t V1, i
              (long long)workspace_bytes, (long long)p.end);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
-  int64_t blocks = rg::min64(ceil_div(count, 256 * 4), kNumSMs * 8);
+  int64_t blocks = rg::min64(ceil_div(count, 256 * 4), static_cast<int64_t>(num_sms()) * 8);
   rg::launch_pdl((narrow_keys_kernel), static_cast<unsigned>(blocks), 256, 0, st, 
       ids, count, reinterpret_cast<uint32_t*>(ws + p.off_keys_a));
   RG_CHECK_LAUNCH("narrow_keys");
@@ -854,7 +854,7 @@ extern "C" int recguru_fill_zero(float* p, int64_t n_floats, recguru_stream_t st
              "fill_zero: need a 16-byte aligned buffer of a multiple of 4 floats");
   if (n_floats == 0) return RECGURU_OK;
   const int64_t n_vec = n_floats / 4;
-  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 4), kNumSMs * 16);
+  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 4), static_cast<int64_t>(num_sms()) * 16);
   rg::launch_pdl((zero_fill_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<float4*>(p), n_vec);
   RG_CHECK_LAUNCH("zero_fill");
@@ -874,6 +874,8 @@ extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_hos
   if (rc) return rc;
   if (total == 0) return RECGURU_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int s = 0; s < n_sites; ++s)
+    RG_CHECK_IDS("embedding_bwd_plan (site ids)", sites_host[s].ids, sites_host[s].count, 0, V1, st);
   int64_t n_rows = 0;
   const bool by_row = row_mode(sites_host, n_sites, &n_rows);
   // by_row: one more key value (the sentinel V1) must sort correctly
@@ -1028,7 +1030,7 @@ extern "C" int recguru_embedding_bwd_mark_rows(const recguru_lookup_site_t* site
   const char* ws = static_cast<const char*>(workspace);
   const uint32_t* n_live = reinterpret_cast<const uint32_t*>(ws + p.off_nlive);
   const uint32_t* sk = reinterpret_cast<const uint32_t*>(ws + ((p.passes & 1) ? p.off_keys_b : p.off_keys_a));
-  const unsigned blocks = static_cast<unsigned>(rg::min64(ceil_div(total, 256), kNumSMs * 8));
+  const unsigned blocks = static_cast<unsigned>(rg::min64(ceil_div(total, 256), static_cast<int64_t>(num_sms()) * 8));
   // keys >= V1 are the by-row sentinel of dropped occurrences (padding ids at live rows)
   rg::launch_pdl((mark_rows_kernel), blocks, 256, 0, static_cast<cudaStream_t>(stream), sk, n_live,
                  static_cast<uint32_t>(V1), epoch, row_epoch);

@@ -163,7 +163,7 @@ extern "C" int recguru_pad_mask_count(const int64_t* ids, int64_t n, int64_t pad
                                       uint32_t* count3, recguru_stream_t stream) {
   using namespace rg;
   RG_REQUIRE(n > 0 && ids && mask_out && count3, RECGURU_E_SHAPE, "pad_mask_count: null pointer or n <= 0");
-  const int64_t blocks = rg::min64(ceil_div(n, 256 * 4), kNumSMs * 8);
+  const int64_t blocks = rg::min64(ceil_div(n, 256 * 4), static_cast<int64_t>(num_sms()) * 8);
   rg::launch_pdl((pad_mask_count_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream),
                  ids, n, pad_index, mask_out, count3);
   RG_CHECK_LAUNCH("pad_mask_count");
@@ -175,7 +175,7 @@ extern "C" int recguru_pad_mask(const int64_t* ids, int64_t n, int64_t pad_index
   using namespace rg;
   RG_REQUIRE(n >= 0 && (n == 0 || (ids && mask_out)), RECGURU_E_SHAPE, "pad_mask: null pointer");
   if (n == 0) return RECGURU_OK;
-  const int64_t blocks = rg::min64(ceil_div(n, 256 * 4), kNumSMs * 8);
+  const int64_t blocks = rg::min64(ceil_div(n, 256 * 4), static_cast<int64_t>(num_sms()) * 8);
   rg::launch_pdl((pad_mask_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), ids, n,
                  pad_index, mask_out);
   RG_CHECK_LAUNCH("pad_mask");
@@ -197,6 +197,7 @@ extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d
   RG_REQUIRE(aligned16(weight) && aligned16(out) && aligned16(pe), RECGURU_E_SHAPE,
              "gather_pe_mask: weight/pe/out must be 16-byte aligned");
   if (n_tokens == 0) return RECGURU_OK;
+  RG_CHECK_IDS("gather_pe_mask", ids, n_tokens, 0, V1, static_cast<cudaStream_t>(stream));
   const int vec = static_cast<int>(d / 4);
   const int tok_per_block = (kGatherThreads * kGatherUnroll) / vec;
   const int64_t blocks = ceil_div(n_tokens, tok_per_block);
@@ -234,7 +235,7 @@ extern "C" int recguru_pe_mask(const float* x, const float* pe, const float* mas
   const int vec = static_cast<int>(d / 4);
   const int64_t n_vec = n_tokens * vec;
   int64_t blocks = ceil_div(n_vec, 256 * 4);
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > static_cast<int64_t>(num_sms()) * 16) blocks = static_cast<int64_t>(num_sms()) * 16;
   rg::launch_pdl((pe_mask_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pe), mask, n_vec, vec,
       static_cast<int>(L), reinterpret_cast<float4*>(out));

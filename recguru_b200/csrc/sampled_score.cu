@@ -724,6 +724,8 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
   RG_REQUIRE(kind <= RECGURU_LOSS_SCE, RECGURU_E_UNSUPPORTED, "sampled_score_loss_fwd: kind=%d", kind);
   RG_REQUIRE(kind < 0 || loss_out, RECGURU_E_SHAPE, "sampled_score_loss_fwd: loss_out is null");
   if (n_pos == 0) return RECGURU_OK;
+  RG_CHECK_IDS("sampled_score_loss_fwd (pos)", pos, n_pos, 0, V1, static_cast<cudaStream_t>(stream));
+  RG_CHECK_IDS("sampled_score_loss_fwd (neg)", neg, n_pos * K, 0, V1, static_cast<cudaStream_t>(stream));
   // dense: one CTA per 128 positions; padding-aware: one persistent CTA per SM
   const int RS = static_cast<int>(K + 1) | 1;
   int chunk = RS <= 13 ? 1024 : 512;                         // 2 * chunk * RS * 4 B of shared memory
@@ -740,7 +742,7 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
   int64_t blocks = ceil_div(n_pos, kScoreWarps * kDensePW);
   int64_t pos_per_cta = 0;
   if (skip_masked) {
-    blocks = rg::min64(kNumSMs, ceil_div(n_pos, chunk));
+    blocks = rg::min64(num_sms(), ceil_div(n_pos, chunk));
     pos_per_cta = align_up(ceil_div(n_pos, blocks), 32);
     blocks = ceil_div(n_pos, pos_per_cta);
   }
@@ -756,11 +758,14 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
 #define RG_LAUNCH_SCORE(V)                                                                       \
   do {                                                                                           \
     if (skip_masked) {                                                                           \
-      static bool attr_set = false;                                                              \
-      if (!attr_set) {                                                                           \
-        cudaFuncSetAttribute(sampled_score_fwd_sparse_kernel<V>,                                 \
+      static rg::PerDeviceOnce once;           /* the attribute is per device */                \
+      const int dev = rg::current_device();                                                      \
+      if (once.need(dev)) {                                                                      \
+        const cudaError_t ea = cudaFuncSetAttribute(sampled_score_fwd_sparse_kernel<V>,          \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);           \
-        attr_set = true;                                                                         \
+        RG_REQUIRE(ea == cudaSuccess, RECGURU_E_CUDA, "sampled_score_fwd: cudaFuncSetAttribute: %s", \
+                   cudaGetErrorString(ea));                                                      \
+        once.done(dev);                                                                          \
       }                                                                                          \
       rg::launch_pdl((sampled_score_fwd_sparse_kernel<V>), static_cast<unsigned>(blocks), kSparseThreads, sparse_smem, st,  \
           h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
@@ -848,6 +853,8 @@ extern "C" int recguru_sampled_score_bwd_dh(const float* dp, const float* dn, co
   RG_REQUIRE(aligned16(weight) && aligned16(dh), RECGURU_E_SHAPE,
              "sampled_score_bwd_dh: weight/dh must be 16-byte aligned");
   if (n_pos == 0) return RECGURU_OK;
+  RG_CHECK_IDS("sampled_score_bwd_dh (pos)", pos, n_pos, 0, V1, static_cast<cudaStream_t>(stream));
+  RG_CHECK_IDS("sampled_score_bwd_dh (neg)", neg, n_pos * K, 0, V1, static_cast<cudaStream_t>(stream));
   const int64_t blocks = ceil_div(n_pos, kPosPerBlock);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float4* w4 = reinterpret_cast<const float4*>(weight);
@@ -879,6 +886,8 @@ extern "C" int recguru_candidate_scores_rank(const float* u, const float* weight
   RG_REQUIRE(aligned16(u) && aligned16(weight), RECGURU_E_SHAPE,
              "candidate_scores_rank: u/weight must be 16-byte aligned");
   if (B == 0) return RECGURU_OK;
+  RG_CHECK_IDS("candidate_scores_rank (target)", target, B, 0, V1, static_cast<cudaStream_t>(stream));
+  RG_CHECK_IDS("candidate_scores_rank (candidates)", cand, B * C, 0, V1, static_cast<cudaStream_t>(stream));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float4* u4 = reinterpret_cast<const float4*>(u);
   const float4* w4 = reinterpret_cast<const float4*>(weight);

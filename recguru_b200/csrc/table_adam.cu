@@ -83,7 +83,7 @@ extern "C" int recguru_table_adam_rows(float* weight, float* exp_avg, float* exp
   const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   const double step_size = lr / bc1;
   const int64_t n_vec = V1 * d / 4;
-  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 2), kNumSMs * 16);
+  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 2), static_cast<int64_t>(num_sms()) * 16);
   table_adam_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(weight), reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq),
       reinterpret_cast<const float4*>(grad_rows), row_epoch, epoch, n_vec, static_cast<int>(d / 4),
@@ -107,7 +107,7 @@ extern "C" int recguru_table_adam(float* weight, float* exp_avg, float* exp_avg_
   const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   const double step_size = lr / bc1;
   const int64_t n_vec = n_floats / 4;
-  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 2), kNumSMs * 16);
+  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 2), static_cast<int64_t>(num_sms()) * 16);
   table_adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(weight), reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq),
       reinterpret_cast<const float4*>(grad), n_vec, static_cast<float>(1.0 - beta1), static_cast<float>(beta2),

@@ -38,11 +38,15 @@ class FusedItemEmbedding(nn.Module):
     ``state_dict()`` keys are unchanged."""
 
     def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: Optional[int] = None,
-                 _weight: Optional[Tensor] = None):
+                 _weight: Optional[Tensor] = None, one_pass_backward: Optional[bool] = None):
         super().__init__()
         self.num_embeddings = num_embeddings
         self.embedding_dim = embedding_dim
         self.padding_idx = padding_idx
+        # one deterministic table backward per backward() for ALL lookups of this table (input ids,
+        # positives, negatives) instead of one dense [V1, d] gradient per lookup site summed by
+        # autograd: see ops.enable_one_pass_backward.  RECGURU_ONE_PASS_BWD=0 turns the default off.
+        self.one_pass_backward = ops.ONE_PASS_DEFAULT if one_pass_backward is None else bool(one_pass_backward)
         if _weight is None:
             w = torch.empty(num_embeddings, embedding_dim)
             nn.init.normal_(w)  # nn.Embedding.reset_parameters
@@ -58,14 +62,22 @@ class FusedItemEmbedding(nn.Module):
         m = cls(emb.num_embeddings, emb.embedding_dim, emb.padding_idx, _weight=emb.weight.data)
         return m
 
+    def _register(self) -> None:
+        # keyed by the storage address: re-registered on every call because .to()/.cuda() move it
+        if self.one_pass_backward and self.weight.is_cuda and torch.is_grad_enabled() and self.weight.requires_grad \
+                and type(self.weight.data) is Tensor:
+            ops.enable_one_pass_backward(self.weight, self.padding_idx)
+
     def forward(self, ids: Tensor) -> Tensor:
         pad = -1 if self.padding_idx is None else int(self.padding_idx)
+        self._register()
         return torch.ops.recguru.gather_rows(self.weight, ids, pad)
 
     def lookup_pe_mask(self, ids: Tensor, pos_emb: "FusedPositionalEncoding",
                        pad_index: Optional[int] = 0, mask: Optional[Tensor] = None):
         """Fused ``pos_emb(src_emb(ids), mask)`` (K1).  With ``mask=None`` the 0/1 mask is derived
         from ``ids != pad_index`` inside the kernel and returned: ``(out, mask)``."""
+        self._register()
         if mask is None:
             out, m = torch.ops.recguru.gather_pe_mask(self.weight, ids, pos_emb.pe, int(pad_index))
         else:
@@ -134,6 +146,7 @@ def sampled_logits(h: Tensor, table: FusedItemEmbedding, dec_out: Tensor, n_item
     (tools/utils.py:103-124) without the gathered-row intermediates:
     returns ``(p_logits [B,L,1], n_logits [B,L,K])``."""
     pad = -1 if table.padding_idx is None else int(table.padding_idx)
+    table._register()
     return torch.ops.recguru.sampled_scores(h, table.weight, dec_out, n_items, pad)
 
 
@@ -149,6 +162,7 @@ def sampled_loss_fused(h: Tensor, table: FusedItemEmbedding, dec_out: Tensor, n_
     """Scores + loss in one kernel (K3).  ``kind`` in {"bpr", "bpr_sas", "sce"}.
     Returns ``(loss, p_logits, n_logits)``; backward produces dh and the dense table grad."""
     pad = -1 if table.padding_idx is None else int(table.padding_idx)
+    table._register()
     aux, p, n, _, _ = torch.ops.recguru.sampled_score_loss(h, table.weight, dec_out, n_items, mask,
                                                            kind, pad)
     return aux[0], p, n

@@ -12,6 +12,9 @@ Op layer    : ``torch.ops.recguru.*`` with register_fake (shape inference) and
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import os
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -238,6 +241,20 @@ def raw_pad_mask_count(ids: Tensor, pad_index: int, out: Tensor, count3: Tensor)
         raise RuntimeError("recguru: mask_out must be contiguous with one entry per id")
     check(_lib.load().recguru_pad_mask_count(_ptr(ids), ids.numel(), int(pad_index), _ptr(out), _ptr(count3),
                                              _stream()), "pad_mask_count")
+    return out
+
+
+def raw_widen_ids(ids32: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """int32 ids (as a loader that collates into pinned int32 ships them) -> the int64 ids every
+    entry point takes (data/data_loader.py:36,:418-421 delivers int64)."""
+    if not ids32.is_cuda or ids32.dtype != torch.int32:
+        raise RuntimeError("recguru: ids32 must be a CUDA int32 tensor")
+    ids32 = ids32 if ids32.is_contiguous() else ids32.contiguous()
+    if out is None:
+        out = torch.empty(ids32.shape, dtype=torch.int64, device=ids32.device)
+    elif out.dtype != torch.int64 or out.numel() != ids32.numel() or not out.is_contiguous():
+        raise RuntimeError("recguru: out must be a contiguous int64 tensor of the same size")
+    check(_lib.load().recguru_widen_ids(_ptr(ids32), ids32.numel(), _ptr(out), _stream()), "widen_ids")
     return out
 
 
@@ -527,6 +544,51 @@ def raw_table_adam_rows(weight: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, gra
 
 
 # --------------------------------------------------------------------------------------
+# device guard: every raw_* call runs on the device of its tensors
+# --------------------------------------------------------------------------------------
+def _tensor_devices(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            yield a
+        elif isinstance(a, Site):
+            yield from (t for t in (a.ids, a.X, a.coef, a.scale, a.scale2, a.live) if t is not None)
+        elif isinstance(a, (list, tuple)) and a and isinstance(a[0], Site):
+            for s in a:
+                yield from (t for t in (s.ids, s.X, s.coef, s.scale, s.scale2, s.live) if t is not None)
+        elif isinstance(a, dict):
+            yield from (t for t in a.values() if isinstance(t, torch.Tensor))
+
+
+def _on_tensor_device(fn):
+    """The C ABI launches on the CURRENT device and the stream it is handed.  A caller that drives
+    several GPUs from one process (nn.DataParallel replicas, train_auto.py:350-351) may call with
+    tensors of a device that is not current: run under that device's guard (and its current stream)
+    and refuse tensors that live on different devices -- a raw pointer of the wrong device would be
+    an illegal address, not an exception."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = args[0] if args else None
+        if not isinstance(t, torch.Tensor):
+            t = next(_tensor_devices(args, kwargs), None)
+        # fast path (one comparison per call): the first tensor lives on the current device
+        if t is None or not t.is_cuda or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        dev = t.device
+        for o in _tensor_devices(args, kwargs):
+            if o.is_cuda and o.device != dev:
+                raise RuntimeError(f"recguru: {fn.__name__}: tensors on different devices ({dev} and {o.device})")
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name, _f in list(globals().items()):
+    if _name.startswith("raw_") and callable(_f):
+        globals()[_name] = _on_tensor_device(_f)
+del _name, _f
+
+
+# --------------------------------------------------------------------------------------
 # op layer: torch.library custom ops + autograd
 # --------------------------------------------------------------------------------------
 _lib_def = torch.library.Library("recguru", "DEF")
@@ -740,6 +802,68 @@ def _(rank, kmax):
     return rank.new_empty(kmax + 1)
 
 
+# ---- one table backward per backward pass (drop-in surface) -----------------------------------
+# The reference's unchanged call sites look a table up several times per step (input ids,
+# positives, negatives; AutoEnc4Rec.py:92,:115,:118).  Through plain autograd every lookup op
+# would return its own dense [V1, d] gradient and autograd would add them (what ATen does:
+# embedding_dense_backward per site).  For a table registered here the lookup
+# ops' backward functions return NO weight gradient: they queue their (ids, source rows,
+# coefficients) as sites, and one engine callback -- run when the whole backward pass has
+# finished -- reduces all of them in ONE deterministic sort + segmented-reduce pass and
+# accumulates the dense result into ``param.grad`` (the optimizer sees what it always saw).
+_one_pass = {}        # weight.data_ptr() -> (weakref to the Parameter, padding_idx)
+_pending = {}         # weight.data_ptr() -> list[Site] of the running backward pass
+ONE_PASS_DEFAULT = os.environ.get("RECGURU_ONE_PASS_BWD", "1") != "0"
+
+
+def enable_one_pass_backward(param: Tensor, padding_idx: Optional[int] = None) -> None:
+    """Register ``param`` (an item table): gradients of the recguru lookup ops w.r.t. it are reduced
+    in one pass per ``backward()`` and written to ``param.grad``.  (``torch.autograd.grad`` w.r.t.
+    the table then returns nothing for these ops -- use ``backward()``, as the reference does.)"""
+    _one_pass[param.data_ptr()] = (weakref.ref(param), -1 if padding_idx is None else int(padding_idx))
+
+
+def disable_one_pass_backward(param: Tensor) -> None:
+    _one_pass.pop(param.data_ptr(), None)
+
+
+def _flush_table(key: int) -> None:
+    sites = _pending.pop(key, [])
+    ent = _one_pass.get(key)
+    param = ent[0]() if ent is not None else None
+    if not sites or param is None:
+        return
+    V1, d = param.shape
+    dW = None
+    for i in range(0, len(sites), _lib.MAX_SITES):          # > 8 lookup sites: several passes, accumulated
+        grp = sites[i:i + _lib.MAX_SITES]
+        dW = raw_embedding_bwd(grp, V1, d, ent[1], out=dW, zero_fill=dW is None)
+    with torch.no_grad():
+        if param.grad is None:
+            param.grad = dW
+        else:
+            param.grad.add_(dW)
+
+
+def _defer_sites(weight: Tensor, sites) -> bool:
+    """Queue ``sites`` for the table ``weight`` if it is registered; True if queued."""
+    if not _one_pass:
+        return False
+    key = weight.data_ptr()
+    ent = _one_pass.get(key)
+    if ent is None:
+        return False
+    if ent[0]() is None:
+        _one_pass.pop(key, None)
+        return False
+    lst = _pending.get(key)
+    if lst is None:
+        lst = _pending[key] = []
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_table(key))
+    lst.extend(sites)
+    return True
+
+
 # ---- autograd ------------------------------------------------------------------------------
 def _setup_gather_pe_mask(ctx, inputs, output):
     weight, ids, pe, pad_index = inputs
@@ -747,11 +871,14 @@ def _setup_gather_pe_mask(ctx, inputs, output):
     ctx.save_for_backward(ids, mask)
     ctx.mark_non_differentiable(mask)   # a 0/1 function of the ids: keep it out of the graph
     ctx.V1 = weight.shape[0]
+    ctx.wref = weight.detach()          # same storage, no graph: identifies the table in backward
 
 
 def _bwd_gather_pe_mask(ctx, g_out, g_mask):
     ids, mask = ctx.saved_tensors
     d = g_out.shape[-1]
+    if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g_out.reshape(-1, d), coef=mask.reshape(-1))]):
+        return None, None, None, None
     # d out / d W[id] = mask ; pad rows get coef 0 (== the reference: x*mask kills their grad,
     # and nn.Embedding(padding_idx) would skip them anyway)
     dW = torch.ops.recguru.embedding_bwd(g_out.reshape(-1, d), ids.reshape(-1), mask.reshape(-1),
@@ -767,11 +894,14 @@ def _setup_gather_pe_mask_m(ctx, inputs, output):
     weight, ids, pe, mask = inputs
     ctx.save_for_backward(ids, mask)
     ctx.V1 = weight.shape[0]
+    ctx.wref = weight.detach()
 
 
 def _bwd_gather_pe_mask_m(ctx, g_out):
     ids, mask = ctx.saved_tensors
     d = g_out.shape[-1]
+    if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g_out.reshape(-1, d), coef=mask.reshape(-1))]):
+        return None, None, None, None
     dW = torch.ops.recguru.embedding_bwd(g_out.reshape(-1, d), ids.reshape(-1), mask.reshape(-1),
                                          ctx.V1, -1)
     return dW, None, None, None
@@ -806,6 +936,11 @@ def _bwd_sampled_scores(ctx, g_p, g_n):
     K = neg.numel() // n_pos
     dp = g_p.reshape(n_pos).contiguous()
     dn = g_n.reshape(n_pos, K).contiguous()
+    if weight.data_ptr() in _one_pass:
+        dh = raw_sampled_score_bwd_dh(dp, dn, weight, pos, neg).view(h.shape)
+        h2 = h.reshape(n_pos, h.shape[-1])
+        if _defer_sites(weight, [Site(pos.reshape(-1), h2, dp), Site(neg.reshape(-1), h2, dn.view(-1), group=K)]):
+            return dh, None, None, None, None
     dh, dW = torch.ops.recguru.sampled_score_bwd(dp, dn, None, None, h, weight, pos, neg,
                                                  ctx.padding_idx)
     return dh, dW, None, None, None
@@ -849,6 +984,12 @@ def _bwd_sampled_score_loss(ctx, g_aux, g_p, g_n, g_dp, g_dn):
     inv_m = aux[1:2]                      # 1/sum(mask), still missing from dp/dn
     if g_p is None and g_n is None and g_aux is not None:
         go = g_aux[0:1].contiguous()      # upstream grad of the scalar loss (device scalar)
+        if weight.data_ptr() in _one_pass:
+            dh = raw_sampled_score_bwd_dh(dp, dn, weight, pos, neg, go, inv_m).view(h.shape)
+            h2 = h.reshape(n_pos, h.shape[-1])
+            if _defer_sites(weight, [Site(pos.reshape(-1), h2, dp, go, inv_m),
+                                     Site(neg.reshape(-1), h2, dn.view(-1), go, inv_m, group=K)]):
+                return dh, None, None, None, None, None, None
         dh, dW = torch.ops.recguru.sampled_score_bwd(dp, dn, go, inv_m, h, weight, pos, neg,
                                                      ctx.padding_idx)
     else:
@@ -873,11 +1014,14 @@ def _setup_gather_rows(ctx, inputs, output):
     ctx.save_for_backward(ids)
     ctx.V1 = weight.shape[0]
     ctx.padding_idx = padding_idx
+    ctx.wref = weight.detach()
 
 
 def _bwd_gather_rows(ctx, g):
     (ids,) = ctx.saved_tensors
     d = g.shape[-1]
+    if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g.reshape(-1, d).contiguous())]):
+        return None, None, None
     dW = torch.ops.recguru.embedding_bwd(g.reshape(-1, d).contiguous(), ids.reshape(-1), None, ctx.V1,
                                          ctx.padding_idx)
     return dW, None, None

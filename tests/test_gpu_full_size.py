@@ -117,3 +117,111 @@ def test_cfg3_shaped_domain_step_vs_oracle(built_lib, domain_seed):
     p, n = O.sampled_scores(h, Wp, tb.dec_out, tb.n_items, L, K)
     (O.LOSSES["sce"](p, n, mask.view(-1)) + (x0 * g).sum()).backward()
     assert torch.allclose(dW.cpu(), Wp.grad, rtol=1e-3, atol=5e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# catalog scoring at the shapes bench.py TIMES: cfg4's 75 776 users x 1M items
+# takes the single-split path (7 813 tiles per CTA) that no smaller test reaches, and nothing
+# touched a 10M-item catalog.  Grid-valued data (k/16): every bf16 x bf16 -> fp32 score is exact in
+# any summation order, so ranks / top-k ids / values must be bit-identical to fp32 torch arithmetic.
+# ------------------------------------------------------------------------------------------------
+def _grid_dev(shape, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(-32, 33, shape, generator=g, device="cuda").float() / 16.0
+
+
+def _reference_rank(users, items, target_local, u_chunk, n_chunk):
+    """count-greater rank with ties -> lower id, chunked fp32 matmuls (exact on grid data)."""
+    U, N = users.shape[0], items.shape[0]
+    rank = torch.zeros(U, dtype=torch.int64, device="cuda")
+    tsc = (users * items[target_local]).sum(1)                       # exact: same products, any order
+    for u0 in range(0, U, u_chunk):
+        u1 = min(U, u0 + u_chunk)
+        t_ = tsc[u0:u1, None]
+        tl = target_local[u0:u1, None]
+        for n0 in range(0, N, n_chunk):
+            n1 = min(N, n0 + n_chunk)
+            s = users[u0:u1] @ items[n0:n1].t()
+            cols = torch.arange(n0, n1, device="cuda")[None, :]
+            rank[u0:u1] += (s > t_).sum(1) + ((s == t_) & (cols < tl)).sum(1)
+    return rank, tsc
+
+
+def _check_topk_exact(users, items, val, idx, id_lo, k, n_chunk):
+    """top-k (score desc, id asc) without sorting a [U, N] matrix: the k best VALUES are unique
+    as a multiset (merge of per-chunk torch.topk values); every returned id must carry its
+    returned value; ties must be in ascending id order; and at the boundary value the returned ids
+    must be the smallest ids that carry it."""
+    U, N = users.shape[0], items.shape[0]
+    best = torch.full((U, k), float("-inf"), device="cuda")
+    for n0 in range(0, N, n_chunk):
+        s = users @ items[n0:min(N, n0 + n_chunk)].t()
+        best = torch.cat([best, s.topk(min(k, s.shape[1]), dim=1).values], 1).topk(k, dim=1).values
+    assert torch.equal(val, best), "top-k values differ"
+    loc = idx - id_lo
+    assert bool(((loc >= 0) & (loc < N)).all())
+    got = (users[:, None, :] * items[loc]).sum(2)                      # [U, k] exact
+    assert torch.equal(got, val), "a returned id does not carry its returned value"
+    same = val[:, 1:] == val[:, :-1]
+    assert bool((~same | (idx[:, 1:] > idx[:, :-1])).all()), "ties not in ascending id order"
+    vk = val[:, -1:]                                                   # boundary value
+    at_b = val == vk
+    m = at_b.sum(1)
+    max_id = torch.where(at_b, loc, torch.full_like(loc, -1)).max(1).values
+    cnt = torch.zeros(U, dtype=torch.int64, device="cuda")
+    for n0 in range(0, N, n_chunk):
+        n1 = min(N, n0 + n_chunk)
+        s = users @ items[n0:n1].t()
+        cols = torch.arange(n0, n1, device="cuda")[None, :]
+        cnt += ((s == vk) & (cols <= max_id[:, None])).sum(1)
+    assert torch.equal(cnt, m), "boundary ties are not the lowest ids"
+
+
+def test_catalog_cfg4_timed_shape_single_split(built_lib):
+    """75 776 users (= bench.USERS_PER_STEP) x 1M items, d=128, top-10: n_splits == 1."""
+    from recguru_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    U, N, d, k, id_lo = 148 * 4 * 128, 1_000_000, 128, 10, 1
+    users, items = _grid_dev((U, d), 41), _grid_dev((N, d), 42)
+    items[123_456:123_556] = items[7]                                  # 100 exact duplicates of item 8
+    target = torch.randint(id_lo, id_lo + N, (U,), generator=torch.Generator(device="cuda").manual_seed(3), device="cuda")
+    target[:64] = id_lo + 123_500                                      # targets inside the tie block
+    target[64:128] = id_lo + N - 1                                     # ... and in the ragged last tile
+    ub, ib = ops.raw_cast_bf16(users), ops.raw_cast_bf16(items)
+    ts = ops.raw_catalog_target_scores(ub, ib, target, id_lo)
+    val, idx, cnt = ops.raw_catalog_topk_rank(ub, ib, target, ts, k, id_lo)
+    rank_only = ops.raw_catalog_topk_rank(ub, ib, target, ts, 0, id_lo)[2]
+    ref_rank, ref_ts = _reference_rank(users, items, target - id_lo, 4096, 250_000)
+    assert torch.equal(ts, ref_ts)
+    assert torch.equal(cnt, ref_rank), f"{int((cnt != ref_rank).sum())} ranks differ"
+    assert torch.equal(rank_only, ref_rank)
+    sub = torch.cat([torch.arange(0, 256), torch.arange(U - 256, U), torch.arange(30_000, 30_512)]).cuda()
+    _check_topk_exact(users[sub], items, val[sub], idx[sub], id_lo, k, 250_000)
+    # size-independent checksum of the whole result (what bench.py prints per N)
+    assert int(idx.min()) >= id_lo and int(idx.max()) < id_lo + N
+
+
+def test_catalog_10m_items(built_lib):
+    """2 048 users x 10M items (cfg5's catalog on one GPU; multi-split + merge at this user count)
+    and 12 800 users x 10M in rank-only mode."""
+    from recguru_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    U, N, d, k, id_lo = 2048, 10_000_000, 128, 10, 1
+    users, items = _grid_dev((U, d), 51), _grid_dev((N, d), 52)
+    items[9_999_900:] = items[5]                                       # ties in the last tiles
+    target = torch.randint(id_lo, id_lo + N, (U,), generator=torch.Generator(device="cuda").manual_seed(4), device="cuda")
+    target[:32] = id_lo + N - 3
+    ub, ib = ops.raw_cast_bf16(users), ops.raw_cast_bf16(items)
+    ts = ops.raw_catalog_target_scores(ub, ib, target, id_lo)
+    val, idx, cnt = ops.raw_catalog_topk_rank(ub, ib, target, ts, k, id_lo)
+    ref_rank, ref_ts = _reference_rank(users, items, target - id_lo, 2048, 500_000)
+    assert torch.equal(ts, ref_ts) and torch.equal(cnt, ref_rank)
+    _check_topk_exact(users[:512], items, val[:512], idx[:512], id_lo, k, 500_000)
+    U2 = 12_800
+    users2 = _grid_dev((U2, d), 53)
+    target2 = torch.randint(id_lo, id_lo + N, (U2,), generator=torch.Generator(device="cuda").manual_seed(5), device="cuda")
+    ub2 = ops.raw_cast_bf16(users2)
+    ts2 = ops.raw_catalog_target_scores(ub2, ib, target2, id_lo)
+    r2 = ops.raw_catalog_topk_rank(ub2, ib, target2, ts2, 0, id_lo)[2]
+    ref2, _ = _reference_rank(users2, items, target2 - id_lo, 3200, 500_000)
+    assert torch.equal(r2, ref2)

@@ -70,7 +70,7 @@ def _make_oracle_evaluator():
     return OracleEvaluator
 
 
-def _worker(rank, world, port, n_items, U, k, out):
+def _worker(rank, world, port, n_items, U, k, out, counts=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -86,8 +86,11 @@ def _worker(rank, world, port, n_items, U, k, out):
         Ev = _make_oracle_evaluator()
         ev = Ev(W, k=k, group=dist.group.WORLD)
         assert ev.world == world
-        per = U // world
-        sl = slice(rank * per, (rank + 1) * per)
+        if counts is None:
+            per = U // world
+            sl = slice(rank * per, (rank + 1) * per)
+        else:                                   # ragged: rank r holds counts[r] users (possibly none)
+            sl = slice(sum(counts[:rank]), sum(counts[:rank + 1]))
         val, idx, rk = ev.rank_topk(users[sl], target[sl])
         rk_only = ev.target_rank(users[sl], target[sl])                            # rank-only exchange
         assert torch.equal(rk_only, rk)
@@ -125,4 +128,38 @@ def test_sharded_catalog_matches_single_shard(world, n_items):
         assert torch.equal(rk, ref_rank[sl])
         assert torch.equal(idx[:, :kk], ri[sl] + 1)
         assert torch.equal(val[:, :kk], rv[sl])
+    assert covered == n_items
+
+
+@pytest.mark.parametrize("world,n_items,counts", [(2, 1000, [7, 12]), (4, 5, [3, 0, 5, 2]), (3, 2, [1, 1, 4])])
+def test_sharded_ragged_users_and_empty_shards(world, n_items, counts):
+    """a last partial batch that differs across ranks, a rank with no users at all, and
+    shards that own no items (n_items < world) must neither hang nor mis-slice."""
+    U, k = sum(counts), 10
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n_items, U, k, out, counts), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(99)
+    d = 64
+    W = torch.randint(-32, 33, (n_items + 2, d), generator=g).float() / 16
+    W[0] = 0
+    if n_items > 100:
+        W[40:60] = W[7]
+    users = torch.randint(-32, 33, (U, d), generator=g).float() / 16
+    target = torch.randint(1, n_items + 1, (U,), generator=g)
+    s = O.catalog_scores(users, W[1:n_items + 1])
+    ref_rank = O.catalog_rank(s, target - 1)
+    kk = min(k, n_items)
+    rv, ri = O.catalog_topk(s, kk)
+    covered = 0
+    for r in range(world):
+        val, idx, rk, id_lo, n_local = out[r]
+        covered += n_local
+        sl = slice(sum(counts[:r]), sum(counts[:r + 1]))
+        assert rk.shape[0] == counts[r] and val.shape == (counts[r], k)
+        assert torch.equal(rk, ref_rank[sl])
+        assert torch.equal(idx[:, :kk], ri[sl] + 1)
+        assert torch.equal(val[:, :kk], rv[sl])
+        assert (idx[:, kk:] == -1).all()
     assert covered == n_items
