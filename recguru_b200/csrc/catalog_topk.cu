@@ -777,6 +777,10 @@ catalog_sweep_kernel(const __grid_constant__ CUtensorMap map_users,
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+}  // namespace rg
+#include "catalog_sweep2.cuh"
+namespace rg {
+
 // ---- target scores through the same tensor-core path -----------------------------------
 // One CTA = 128 users.  The 128 target rows are gathered into a swizzled B tile by hand,
 // one 128x128 MMA is issued and thread r keeps D[r][r].
@@ -915,6 +919,8 @@ static int pick_splits(int64_t U, int64_t n_items, int bn) {
   return static_cast<int>(s);
 }
 
+constexpr int kSweepWarpsDefault = 2;    // epilogue warps per TMEM lane quarter of the production sweep
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -999,7 +1005,47 @@ static int launch_sweep_n(const CUtensorMap& mu, const CUtensorMap& mi, const Ca
   return RECGURU_OK;
 }
 
-// Production: 2 epilogue sets (8 warps, one 128-register TMEM load per tile), 128-item tiles, 4
+template <int D, int MODE, int KS, int NW, int CH>
+static int launch_sweep2_n(const CUtensorMap& mu, const CUtensorMap& mi, const CatalogParams& p, cudaStream_t st) {
+  const int smem = Cat2Smem<D>::bytes();
+  auto kern = catalog_sweep2_kernel<D, MODE, KS, NW, CH>;
+  static PerDeviceOnce once;          // the dynamic shared-memory limit is a per-device function attribute
+  const int dev = current_device();
+  if (once.need(dev)) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "catalog: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    once.done(dev);
+  }
+  const dim3 grid(static_cast<unsigned>(ceil_div(p.U, kBlockM)), static_cast<unsigned>(p.n_splits));
+  kern<<<grid, 128 + NW * 128, smem, st>>>(mu, mi, p);
+  RG_CHECK_LAUNCH("catalog_sweep2");
+  return RECGURU_OK;
+}
+
+template <int D, int MODE, int NW, int CH>
+static int launch_sweep2_k(const CUtensorMap& mu, const CUtensorMap& mi, const CatalogParams& p, cudaStream_t st) {
+  if (MODE == kModeRank || p.k <= 8) return launch_sweep2_n<D, MODE, 8, NW, CH>(mu, mi, p, st);
+  if (p.k <= 12) return launch_sweep2_n<D, MODE, 12, NW, CH>(mu, mi, p, st);
+  return launch_sweep2_n<D, MODE, 16, NW, CH>(mu, mi, p, st);
+}
+
+// round-2 production sweep (catalog_sweep2.cuh): rank-only, or top-k with k <= 16 in KS register slots.
+// RECGURU_CATALOG_WARPS = epilogue warps per TMEM lane quarter: 2 (128-column loads), 3 (64), 4 (32).
+template <int D, int MODE>
+static int launch_sweep2(const void* items, const CUtensorMap& mu, CatalogParams p, cudaStream_t st) {
+  p.two = 2u;
+  p.debug_flags = 0u;
+  p.tiles_per_split = static_cast<int>(ceil_div(ceil_div(p.n_items, 128), p.n_splits));
+  CUtensorMap mi;
+  const int rc = make_rowmajor_map(&mi, items, p.n_items, D, 128);
+  if (rc) return rc;
+  const int nw = env_int("RECGURU_CATALOG_WARPS", kSweepWarpsDefault);
+  if (nw == 3) return launch_sweep2_k<D, MODE, 3, 64>(mu, mi, p, st);
+  if (nw == 4) return launch_sweep2_k<D, MODE, 4, 32>(mu, mi, p, st);
+  return launch_sweep2_k<D, MODE, 2, 128>(mu, mi, p, st);
+}
+
+// Round-1 form: 2 epilogue sets (8 warps, one 128-register TMEM load per tile), 128-item tiles, 4
 // coupled smem/TMEM stages, top-k lists in registers for k <= 16.  Everything else that was
 // measured without gain is compiled only with RECGURU_DEBUG_KNOBS.
 template <int D, int MODE>
@@ -1151,7 +1197,13 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
     p.out_id = reinterpret_cast<int64_t*>(ws + sv);
     p.out_cnt = reinterpret_cast<int64_t*>(ws + sv + si);
   }
-  if (k == 0)   // rank only: no maxima, no lists -- what HR/NDCG/MRR need
+  // RECGURU_CATALOG_V=1: the round-1 kernel (A/B measurements); k > 16 (shared-memory lists) always uses it
+  const bool v2 = k <= 16 && env_int("RECGURU_CATALOG_V", 2) != 1 && env_int("RECGURU_CATALOG_DEBUG", 0) == 0;
+  if (v2 && k == 0)
+    rc = d == 64 ? launch_sweep2<64, kModeRank>(items_bf16, mu, p, st) : launch_sweep2<128, kModeRank>(items_bf16, mu, p, st);
+  else if (v2)
+    rc = d == 64 ? launch_sweep2<64, kModeTopK>(items_bf16, mu, p, st) : launch_sweep2<128, kModeTopK>(items_bf16, mu, p, st);
+  else if (k == 0)   // rank only: no maxima, no lists -- what HR/NDCG/MRR need
     rc = d == 64 ? launch_sweep<64, kModeRank>(items_bf16, mu, p, 128, st) : launch_sweep<128, kModeRank>(items_bf16, mu, p, 128, st);
   else
     rc = d == 64 ? launch_sweep<64, kModeTopK>(items_bf16, mu, p, bn, st) : launch_sweep<128, kModeTopK>(items_bf16, mu, p, bn, st);

@@ -39,6 +39,10 @@ def run(n_items, label, k=k, **env):
 
 
 n_items = 1_000_000
-run(n_items, "top-10 + rank (default)")
-run(n_items, "rank only (k = 0)", k=0)
-run(10_000_000, "top-10 + rank, 10M items")
+run(n_items, "v1 top-10 + rank", RECGURU_CATALOG_V=1)
+for nw in (2, 3, 4):
+    run(n_items, f"v2 top-10 + rank, {nw} warps/quarter", RECGURU_CATALOG_WARPS=nw)
+    run(n_items, f"v2 rank only, {nw} warps/quarter", k=0, RECGURU_CATALOG_WARPS=nw)
+for nw in (2, 3, 4):
+    run(10_000_000, f"v2 top-10 + rank, 10M items, {nw} warps/quarter", RECGURU_CATALOG_WARPS=nw)
+run(10_000_000, "v2 rank only, 10M items, 3 warps/quarter", k=0, RECGURU_CATALOG_WARPS=3)
