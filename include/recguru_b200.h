@@ -143,6 +143,14 @@ int recguru_embedding_bwd(const recguru_lookup_site_t* sites_host, int n_sites, 
 int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_host, int n_sites, int64_t V1,
                                int64_t padding_idx, void* workspace, int64_t workspace_bytes,
                                recguru_stream_t stream);
+/* recguru_embedding_bwd_plan with the shared pad mask of a training step derived inside (row mode:
+ * every site's `live` must be mask_out, one entry per row of X): mask_out[i] = mask_ids[i] != pad_index,
+ * and -- if count3 != NULL -- its population count as recguru_pad_mask_count publishes it.  Saves the
+ * separate pad-mask launch at the head of the plan branch (AutoEnc4Rec.py:71,:89 + train_auto.py:124). */
+int recguru_embedding_bwd_plan_padmask(const recguru_lookup_site_t* sites, int n_sites, int64_t V1,
+                                       int64_t padding_idx, const int64_t* mask_ids, int64_t pad_index,
+                                       float* mask_out, uint32_t* count3, void* workspace,
+                                       int64_t workspace_bytes, recguru_stream_t stream);
 int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_host, int n_sites, int64_t d,
                                 int64_t V1, float* dW, int zero_fill, void* workspace,
                                 int64_t workspace_bytes, recguru_stream_t stream);
@@ -323,6 +331,10 @@ int recguru_sample_negatives_csr(const int64_t* items, const int64_t* offsets, c
                                  int64_t v_size, const float* alias_prob, const int32_t* alias_idx,
                                  int64_t num_n, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                                  int64_t* n_items_out, recguru_stream_t stream);
+/* *slot = %globaltimer (ns) when the stream reaches this point: a one-thread kernel that can sit
+ * inside a captured CUDA graph, where events cannot be timed -- the step-timeline tool of
+ * scripts/step_timeline.py (which branch of a multi-stream step is the critical one). */
+int recguru_debug_timestamp(uint64_t* slot, recguru_stream_t stream);
 /* *counter += inc on the stream (a one-thread kernel; graph-capturable step bookkeeping). */
 int recguru_counter_add(uint64_t* counter, uint64_t inc, recguru_stream_t stream);
 /* ids_out[i] = (int64) ids32_in[i].  The reference's loaders hand over int64 ids (numpy int64 ->

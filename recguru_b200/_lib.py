@@ -42,6 +42,8 @@ SIGNATURES = {
                                         C.c_int, c_ptr, c_i64, c_ptr]),
     "recguru_embedding_bwd_plan": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_ptr, c_i64,
                                              c_ptr]),
+    "recguru_embedding_bwd_plan_padmask": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_ptr, c_i64,
+                                                     c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "recguru_embedding_bwd_apply": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_ptr,
                                               C.c_int, c_ptr, c_i64, c_ptr]),
     "recguru_fill_zero": (C.c_int, [c_ptr, c_i64, c_ptr]),
@@ -79,6 +81,7 @@ SIGNATURES = {
                                                c_i64, C.c_uint64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
     "recguru_counter_add": (C.c_int, [c_ptr, C.c_uint64, c_ptr]),
     "recguru_widen_ids": (C.c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "recguru_debug_timestamp": (C.c_int, [c_ptr, c_ptr]),
     "recguru_embedding_bwd_mark_rows": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_ptr, c_i64, c_ptr, C.c_uint32, c_ptr]),
     "recguru_table_adam_rows": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_uint32, c_i64, c_i64, C.c_double,
                                           C.c_double, C.c_double, C.c_double, c_i64, c_ptr]),

@@ -456,6 +456,301 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   rg::pdl_trigger();
 }
 
+// ---- 2b. the plan of the table backward in 2 + passes launches (round 2; RECGURU_BWD_PLAN=2) --
+// MEASURED SLOWER than the chain above and therefore not the default -- kept as the record of the
+// experiment and for sizes where launch count matters more than atomic throughput.
+// Round 1 planned a step's table backward with ten launches of 3-13 us (pad mask, row count, scan,
+// row scatter, then {tile histogram, row scan, stable scatter} per radix pass): a latency chain
+// that kept < 20 % of the SMs busy and was what `apply` waited for.  Same algorithm -- stable
+// compaction of the live (id, occurrence) pairs, stable LSD radix sort by id -- with the
+// bookkeeping folded into the kernels that already touch the data:
+//   plan_count    liveness per compaction tile (optionally DERIVING the shared pad mask and its
+//                 population count from the ids: recguru_pad_mask_count folded in), and the zero fill
+//                 of every pass's histogram;
+//   plan_scatter  each CTA sums the tile counts before it itself (a few hundred words: no scan
+//                 kernel), scatters its live pairs and adds them to pass 0's digit histogram with
+//                 integer atomics (exact and order independent, so determinism is untouched);
+//   radix_pass    each 2048-key CTA forms its digit bases from the tile-major histogram itself -- the
+//                 32-tile group counts before its group, the tiles before it inside the group, and
+//                 all live groups for the digit totals (coalesced 2 KB rows: no scan kernel, and
+//                 O(tiles/32 + 32) rows per CTA, so it scales) -- ranks its keys (match_any per
+//                 warp, stable), scatters, and adds the scattered keys to the NEXT pass's histogram.
+// Output (sorted keys / occurrence indices, live count) is bit-identical to the round-1 chain.
+constexpr int kP2Threads = 256;
+constexpr int kP2Items = 8;
+constexpr int kP2Tile = kP2Threads * kP2Items;            // 2048 keys per radix CTA
+constexpr int kC2Items = 4;
+constexpr int kC2Tile = kP2Threads * kC2Items;            // 1024 units (rows or indices) per compaction CTA
+constexpr int kP2Group = 32;                              // radix tiles per histogram group
+constexpr int kMaxPasses = 4;
+// histogram words of one pass: [tiles][512] per-tile counts, then [groups][512] per-group counts
+__host__ __device__ inline int64_t p2_hist_words(int64_t tiles) {
+  return (tiles + (tiles + kP2Group - 1) / kP2Group) * kMaxBins;
+}
+// one key of digit `dig` lands at sorted position `dst` of the NEXT pass's input: count it there
+__device__ __forceinline__ void p2_count(uint32_t* __restrict__ hist, int64_t tiles, uint32_t dst, uint32_t dig) {
+  const int64_t t = dst / kP2Tile;
+  atomicAdd(&hist[t * kMaxBins + dig], 1u);
+  atomicAdd(&hist[(tiles + t / kP2Group) * kMaxBins + dig], 1u);
+}
+
+template <int NS, bool ROW>
+__global__ void __launch_bounds__(kP2Threads)
+plan_count_kernel(SiteTable st, const float* __restrict__ live, const int64_t* __restrict__ mask_ids,
+                  int64_t pad_index, float* __restrict__ mask_out, uint32_t* __restrict__ count3,
+                  int64_t n_units, int64_t padding_idx, uint32_t* __restrict__ tile_count,
+                  uint32_t* __restrict__ hist, int64_t hist_words) {
+  rg::pdl_wait();
+  __shared__ uint32_t s_w[kP2Threads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // histograms of every pass start at zero (plan_scatter / radix_pass add to them)
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kP2Threads + threadIdx.x; i < hist_words;
+       i += static_cast<int64_t>(gridDim.x) * kP2Threads)
+    hist[i] = 0u;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kC2Tile + warp * (32 * kC2Items);
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < kC2Items; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    bool lv = false;
+    if (i < n_units) {
+      if (ROW) {
+        if (mask_ids != nullptr) {
+          lv = mask_ids[i] != pad_index;
+          mask_out[i] = lv ? 1.f : 0.f;
+        } else {
+          lv = live[i] != 0.f;
+        }
+      } else {
+        uint32_t key;
+        lv = occurrence_live<NS>(st, i, padding_idx, &key);
+      }
+    }
+    c += lv ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) s_w[warp] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kP2Threads / 32; ++w) t += s_w[w];
+    tile_count[blockIdx.x] = t;
+    if (ROW && mask_ids != nullptr && count3 != nullptr) {
+      // population count of the mask, published by the last CTA (same protocol as pad_mask_count_kernel)
+      atomicAdd(&count3[0], t);
+      __threadfence();
+      const uint32_t ticket = atomicAdd(&count3[1], 1u);
+      if (ticket == gridDim.x - 1) {
+        __threadfence();
+        count3[2] = atomicExch(&count3[0], 0u);
+        count3[1] = 0u;
+      }
+    }
+  }
+  rg::pdl_trigger();
+}
+
+template <int NS, bool ROW>
+__global__ void __launch_bounds__(kP2Threads)
+plan_scatter_kernel(SiteTable st, const float* __restrict__ live, int64_t n_units, int64_t padding_idx,
+                    uint32_t sentinel, const uint32_t* __restrict__ tile_count, int n_ctiles,
+                    uint32_t* __restrict__ n_live /* [0] live occurrences, [1] live rows */,
+                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                    uint32_t* __restrict__ hist0, int64_t rtiles, uint32_t digit_mask) {
+  rg::pdl_wait();
+  __shared__ uint32_t s_w[kP2Threads / 32];
+  __shared__ uint32_t s_red[2][kP2Threads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // live units in the tiles before this one, and in all tiles
+  uint32_t before = 0, all = 0;
+  for (int t = threadIdx.x; t < n_ctiles; t += kP2Threads) {
+    const uint32_t v = tile_count[t];
+    all += v;
+    before += t < static_cast<int>(blockIdx.x) ? v : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, o);
+    all += __shfl_xor_sync(0xffffffffu, all, o);
+  }
+  if (lane == 0) { s_red[0][warp] = before; s_red[1][warp] = all; }
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kC2Tile + warp * (32 * kC2Items);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t key[kC2Items];
+  uint32_t rank[kC2Items];   // 0xffffffff = dead
+  uint32_t run = 0;
+#pragma unroll
+  for (int j = 0; j < kC2Items; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    bool lv = false;
+    key[j] = 0;
+    if (i < n_units) {
+      if (ROW) lv = live[i] != 0.f;
+      else lv = occurrence_live<NS>(st, i, padding_idx, &key[j]);
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, lv);
+    rank[j] = lv ? run + __popc(b & lt_mask) : 0xffffffffu;
+    run += __popc(b);
+  }
+  if (lane == 0) s_w[warp] = run;
+  __syncthreads();
+  uint32_t base = 0, p_live = 0;
+#pragma unroll
+  for (int w = 0; w < kP2Threads / 32; ++w) {
+    base += s_red[0][w];
+    p_live += s_red[1][w];
+    if (w < warp) base += s_w[w];
+  }
+  if (ROW) {
+    uint32_t g_total = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2)
+      if (s2 < st.n_sites) g_total += static_cast<uint32_t>(st.group[s2]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { n_live[0] = p_live * g_total; n_live[1] = p_live; }
+#pragma unroll
+    for (int j = 0; j < kC2Items; ++j) {
+      if (rank[j] == 0xffffffffu) continue;
+      const int64_t row = warp0 + j * 32 + lane;
+      const uint32_t r = base + rank[j];
+      uint32_t gpre = 0;
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        if (s2 < st.n_sites) {
+          const uint32_t G = static_cast<uint32_t>(st.group[s2]);
+          const int64_t* ids = st.ids[s2] + row * G;
+          const uint32_t out0 = p_live * gpre + r * G;
+          const uint32_t occ0 = static_cast<uint32_t>(st.offset[s2] + row * G);
+          for (uint32_t k = 0; k < G; ++k) {
+            const int64_t id = ids[k];
+            const uint32_t kk = id == padding_idx ? sentinel : static_cast<uint32_t>(id);
+            keys[out0 + k] = kk;
+            vals[out0 + k] = occ0 + k;
+            p2_count(hist0, rtiles, out0 + k, kk & digit_mask);
+          }
+          gpre += G;
+        }
+      }
+    }
+  } else {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { n_live[0] = p_live; n_live[1] = 0u; }
+#pragma unroll
+    for (int j = 0; j < kC2Items; ++j) {
+      if (rank[j] != 0xffffffffu) {
+        const uint32_t dst = base + rank[j];
+        keys[dst] = key[j];
+        vals[dst] = static_cast<uint32_t>(warp0 + j * 32 + lane);
+        p2_count(hist0, rtiles, dst, key[j] & digit_mask);
+      }
+    }
+  }
+  rg::pdl_trigger();
+}
+
+// One LSD pass over 2048-key tiles.  hist_cur (tile-major per-tile + per-group counts) was filled by
+// the kernel that wrote keys_in; hist_next (may be NULL) is filled here for the following pass.
+__global__ void __launch_bounds__(kP2Threads)
+radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                  const uint32_t* __restrict__ n_live, int shift, int bits,
+                  const uint32_t* __restrict__ hist_cur, uint32_t* __restrict__ hist_next, int64_t rtiles,
+                  int next_shift, uint32_t next_mask,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  rg::pdl_wait();
+  __shared__ uint32_t s_cnt[kP2Threads / 32][kMaxBins];
+  __shared__ uint32_t s_base[kMaxBins];
+  __shared__ uint32_t s_wsum[kP2Threads / 32];
+  const int64_t total = static_cast<int64_t>(*n_live);
+  const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kP2Tile;
+  if (tile0 >= total) return;                                          // tile beyond the live range
+  const int live_tiles = static_cast<int>((total + kP2Tile - 1) / kP2Tile);
+  const int live_groups = (live_tiles + kP2Group - 1) / kP2Group;
+  const int my_group = static_cast<int>(blockIdx.x) / kP2Group;
+  const int bins = 1 << bits;
+  const uint32_t mask = bins - 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = threadIdx.x; b < (kP2Threads / 32) * kMaxBins; b += kP2Threads) (&s_cnt[0][0])[b] = 0;
+  // digit bases.  Thread t owns digits 2t and 2t+1 (256 x 2 = 512): keys of that digit in the tiles
+  // before this one (whole groups, then the tiles of this group) and in all live tiles.
+  {
+    const uint32_t* grp = hist_cur + rtiles * kMaxBins;
+    const int b0 = threadIdx.x * 2;
+    uint32_t before0 = 0, before1 = 0, tot0 = 0, tot1 = 0;
+    if (b0 < bins) {
+      for (int g = 0; g < live_groups; ++g) {
+        const uint2 v = *reinterpret_cast<const uint2*>(grp + static_cast<int64_t>(g) * kMaxBins + b0);
+        tot0 += v.x; tot1 += v.y;
+        if (g < my_group) { before0 += v.x; before1 += v.y; }
+      }
+      for (int t = my_group * kP2Group; t < static_cast<int>(blockIdx.x); ++t) {
+        const uint2 v = *reinterpret_cast<const uint2*>(hist_cur + static_cast<int64_t>(t) * kMaxBins + b0);
+        before0 += v.x; before1 += v.y;
+      }
+    }
+    uint32_t incl = tot0 + tot1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < kP2Threads / 32; ++w)
+      if (w < warp) wbase += s_wsum[w];
+    const uint32_t excl = wbase + incl - (tot0 + tot1);
+    s_base[b0] = excl + before0;
+    s_base[b0 + 1] = excl + tot0 + before1;
+  }
+  __syncthreads();
+
+  const int64_t warp0 = tile0 + warp * (32 * kP2Items);
+  uint32_t key[kP2Items];
+  uint32_t rank[kP2Items];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < kP2Items; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    const bool valid = i < total;
+    key[j] = valid ? keys_in[i] : 0xffffffffu;
+    const uint32_t dig = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;  // invalid: own group
+    const uint32_t peers = __match_any_sync(0xffffffffu, dig);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) {
+      base = s_cnt[warp][dig];
+      s_cnt[warp][dig] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[j] = base + __popc(peers & lt_mask);
+  }
+  __syncthreads();
+  // per-digit exclusive prefix over the warps of this CTA, seeded with the global base
+  for (int b = threadIdx.x; b < bins; b += kP2Threads) {
+    uint32_t run = s_base[b];
+#pragma unroll
+    for (int w = 0; w < kP2Threads / 32; ++w) {
+      const uint32_t c = s_cnt[w][b];
+      s_cnt[w][b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kP2Items; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    if (i < total) {
+      const uint32_t dig = (key[j] >> shift) & mask;
+      const uint32_t dst = s_cnt[warp][dig] + rank[j];
+      keys_out[dst] = key[j];
+      vals_out[dst] = vals_in[i];
+      if (hist_next != nullptr) p2_count(hist_next, rtiles, dst, (key[j] >> next_shift) & next_mask);
+    }
+  }
+  rg::pdl_trigger();
+}
+
 // ---- 3. zero fill -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n_vec) {
   rg::pdl_wait();
@@ -716,7 +1011,13 @@ static SortPlan make_sort_plan(int64_t count, int64_t V1) {
   p.off_keys_b = o; o += kb;
   p.off_vals_a = o; o += kb;
   p.off_vals_b = o; o += kb;
-  p.off_hist = o; o += align_up(static_cast<int64_t>(kMaxBins) * p.n_tiles * 4, 256);
+  {
+    // the round-1 chain keeps one digit-major histogram over 2048-key tiles; the fused plan keeps one
+    // tile-major histogram per pass over 8192-key tiles
+    const int64_t old_b = static_cast<int64_t>(kMaxBins) * p.n_tiles * 4;
+    const int64_t new_b = static_cast<int64_t>(p.passes) * p2_hist_words(ceil_div(count > 0 ? count : 1, kP2Tile)) * 4;
+    p.off_hist = o; o += align_up(old_b > new_b ? old_b : new_b, 256);
+  }
   p.off_totals = o; o += align_up(kMaxBins * 4, 256);
   p.off_tilecnt = o; o += align_up(ceil_div(count > 0 ? count : 1, kCompactTile) * 4, 256);
   p.off_nlive = o; o += 256;
@@ -861,28 +1162,24 @@ extern "C" int recguru_fill_zero(float* p, int64_t n_floats, recguru_stream_t st
   return RECGURU_OK;
 }
 
-// Stage A of the table backward: stable compaction of the live (id, occurrence) pairs and the
-// LSD radix sort.  Reads ids and the liveness source only (site.live, else site.coef).
-extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_host, int n_sites,
-                                          int64_t V1, int64_t padding_idx, void* workspace,
-                                          int64_t workspace_bytes, recguru_stream_t stream) {
-  using namespace rg;
-  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "embedding_bwd_plan: bad V1");
-  SiteTable tab;
-  int64_t total = 0;
-  int rc = build_site_table("embedding_bwd_plan", sites_host, n_sites, false, &tab, &total);
-  if (rc) return rc;
-  if (total == 0) return RECGURU_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int s = 0; s < n_sites; ++s)
-    RG_CHECK_IDS("embedding_bwd_plan (site ids)", sites_host[s].ids, sites_host[s].count, 0, V1, st);
-  int64_t n_rows = 0;
-  const bool by_row = row_mode(sites_host, n_sites, &n_rows);
-  // by_row: one more key value (the sentinel V1) must sort correctly
-  const SortPlan p = make_sort_plan(total, by_row ? V1 + 1 : V1);
-  RG_REQUIRE(workspace && workspace_bytes >= p.end, RECGURU_E_WORKSPACE,
-             "embedding_bwd_plan: workspace %lld < %lld", (long long)workspace_bytes, (long long)p.end);
-  char* ws = static_cast<char*>(workspace);
+namespace rg {
+// RECGURU_BWD_PLAN=2 selects the fused 2 + passes launch plan (plan_count / plan_scatter / radix_pass).
+// It is bit-identical to the default chain but was measured SLOWER on B200 (cfg2 padded batch: 78 us
+// against 65 us; the per-key global histogram atomics cost more than the launches they replace --
+// plan_scatter 20.8 us vs row_scatter 12.5, a radix pass with next-pass counting 31.8 us vs 15.2
+// without), so the default stays the separate histogram / scan / scatter kernels.
+inline bool env_plan_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RECGURU_BWD_PLAN");
+    v = (e && e[0] == '2') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static int plan_v1(const recguru_lookup_site_t* sites_host, int n_sites, const SiteTable& tab, int64_t total,
+                   int64_t V1, int64_t padding_idx, bool by_row, int64_t n_rows, const SortPlan& p, char* ws,
+                   cudaStream_t st) {
   uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(ws + p.off_tilecnt);
   uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + p.off_keys_a);
@@ -915,6 +1212,120 @@ extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_hos
   RG_CHECK_LAUNCH("compact_scatter");
   uint32_t *sk, *sv;
   return run_radix_sort(p, ws, total, n_live, false, st, &sk, &sv, nullptr, nullptr);
+}
+
+// The fused plan: plan_count, plan_scatter, one radix_pass per digit (4 launches for <= 18-bit ids).
+// mask_ids != NULL (row mode only): the shared liveness mask is derived here (mask_out, count3).
+static int plan_v2(const recguru_lookup_site_t* sites_host, int n_sites, const SiteTable& tab, int64_t total,
+                   int64_t V1, int64_t padding_idx, bool by_row, int64_t n_rows, const SortPlan& p, char* ws,
+                   const int64_t* mask_ids, int64_t pad_index, float* mask_out, uint32_t* count3, cudaStream_t st) {
+  uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(ws + p.off_tilecnt);
+  uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
+  uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws + p.off_keys_a), reinterpret_cast<uint32_t*>(ws + p.off_keys_b)};
+  uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(ws + p.off_vals_a), reinterpret_cast<uint32_t*>(ws + p.off_vals_b)};
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + p.off_hist);
+  const int64_t n_units = by_row ? n_rows : total;
+  const unsigned ctiles = static_cast<unsigned>(ceil_div(n_units, kC2Tile));
+  const int64_t rtiles = ceil_div(total, kP2Tile);                     // radix tiles (capacity)
+  const int64_t hist_pass = p2_hist_words(rtiles);                     // words per pass
+  const int64_t hist_words = hist_pass * p.passes;
+  const float* lv = by_row ? (mask_ids ? mask_out : sites_host[0].live) : nullptr;
+  const uint32_t sentinel = static_cast<uint32_t>(V1);
+  const int bits0 = p.bits_per_pass < p.total_bits ? p.bits_per_pass : p.total_bits;
+  const uint32_t mask0 = (1u << bits0) - 1u;
+#define RG_PLAN_LAUNCH(NS)                                                                             \
+  do {                                                                                                 \
+    if (by_row) {                                                                                      \
+      rg::launch_pdl((plan_count_kernel<NS, true>), ctiles, kP2Threads, 0, st, tab, lv, mask_ids, pad_index, \
+                     mask_out, count3, n_units, padding_idx, tile_cnt, hist, hist_words);              \
+      RG_CHECK_LAUNCH("plan_count");                                                                   \
+      rg::launch_pdl((plan_scatter_kernel<NS, true>), ctiles, kP2Threads, 0, st, tab, lv, n_units, padding_idx, \
+                     sentinel, tile_cnt, static_cast<int>(ctiles), n_live, keys[0], vals[0], hist, rtiles, mask0); \
+      RG_CHECK_LAUNCH("plan_scatter");                                                                 \
+    } else {                                                                                           \
+      rg::launch_pdl((plan_count_kernel<NS, false>), ctiles, kP2Threads, 0, st, tab, lv, mask_ids, pad_index, \
+                     mask_out, count3, n_units, padding_idx, tile_cnt, hist, hist_words);              \
+      RG_CHECK_LAUNCH("plan_count");                                                                   \
+      rg::launch_pdl((plan_scatter_kernel<NS, false>), ctiles, kP2Threads, 0, st, tab, lv, n_units, padding_idx, \
+                     sentinel, tile_cnt, static_cast<int>(ctiles), n_live, keys[0], vals[0], hist, rtiles, mask0); \
+      RG_CHECK_LAUNCH("plan_scatter");                                                                 \
+    }                                                                                                  \
+  } while (0)
+  if (n_sites <= 1) RG_PLAN_LAUNCH(1);
+  else if (n_sites <= 3) RG_PLAN_LAUNCH(3);
+  else RG_PLAN_LAUNCH(RECGURU_MAX_SITES);
+#undef RG_PLAN_LAUNCH
+  int cur = 0;
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const int shift = pass * p.bits_per_pass;
+    const int bits = min(p.bits_per_pass, p.total_bits - shift);
+    const bool last = pass == p.passes - 1;
+    const int nshift = shift + p.bits_per_pass;
+    const int nbits = last ? 0 : min(p.bits_per_pass, p.total_bits - nshift);
+    rg::launch_pdl((radix_pass_kernel), static_cast<unsigned>(rtiles), kP2Threads, 0, st, keys[cur], vals[cur],
+                   n_live, shift, bits, hist + pass * hist_pass, last ? nullptr : hist + (pass + 1) * hist_pass,
+                   rtiles, nshift, last ? 0u : (1u << nbits) - 1u, keys[cur ^ 1], vals[cur ^ 1]);
+    RG_CHECK_LAUNCH("radix_pass");
+    cur ^= 1;
+  }
+  return RECGURU_OK;
+}
+
+static int plan_impl(const char* who, const recguru_lookup_site_t* sites_host, int n_sites, int64_t V1,
+                     int64_t padding_idx, void* workspace, int64_t workspace_bytes, const int64_t* mask_ids,
+                     int64_t pad_index, float* mask_out, uint32_t* count3, recguru_stream_t stream) {
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "%s: bad V1", who);
+  SiteTable tab;
+  int64_t total = 0;
+  int rc = build_site_table(who, sites_host, n_sites, false, &tab, &total);
+  if (rc) return rc;
+  if (total == 0) return RECGURU_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int s = 0; s < n_sites; ++s)
+    RG_CHECK_IDS("embedding_bwd_plan (site ids)", sites_host[s].ids, sites_host[s].count, 0, V1, st);
+  int64_t n_rows = 0;
+  const bool by_row = row_mode(sites_host, n_sites, &n_rows);
+  RG_REQUIRE(mask_ids == nullptr || (by_row && mask_out != nullptr && sites_host[0].live == mask_out),
+             RECGURU_E_SHAPE, "%s: deriving the mask here needs every site's live == mask_out (one entry per row)", who);
+  // by_row: one more key value (the sentinel V1) must sort correctly
+  const SortPlan p = make_sort_plan(total, by_row ? V1 + 1 : V1);
+  RG_REQUIRE(workspace && workspace_bytes >= p.end, RECGURU_E_WORKSPACE,
+             "%s: workspace %lld < %lld", who, (long long)workspace_bytes, (long long)p.end);
+  char* ws = static_cast<char*>(workspace);
+  if (env_plan_v1()) {
+    if (mask_ids != nullptr) {
+      rc = count3 ? recguru_pad_mask_count(mask_ids, n_rows, pad_index, mask_out, count3, stream)
+                  : recguru_pad_mask(mask_ids, n_rows, pad_index, mask_out, stream);
+      if (rc) return rc;
+    }
+    return plan_v1(sites_host, n_sites, tab, total, V1, padding_idx, by_row, n_rows, p, ws, st);
+  }
+  return plan_v2(sites_host, n_sites, tab, total, V1, padding_idx, by_row, n_rows, p, ws, mask_ids, pad_index,
+                 mask_out, count3, st);
+}
+}  // namespace rg
+
+// Stage A of the table backward: stable compaction of the live (id, occurrence) pairs and the
+// LSD radix sort.  Reads ids and the liveness source only (site.live, else site.coef).
+extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_host, int n_sites,
+                                          int64_t V1, int64_t padding_idx, void* workspace,
+                                          int64_t workspace_bytes, recguru_stream_t stream) {
+  return rg::plan_impl("embedding_bwd_plan", sites_host, n_sites, V1, padding_idx, workspace, workspace_bytes,
+                       nullptr, 0, nullptr, nullptr, stream);
+}
+
+// Stage A with the shared pad mask derived inside: mask_out[i] = mask_ids[i] != pad_index (one entry
+// per row; every site's `live` must point at mask_out), count3 as in recguru_pad_mask_count (may be
+// NULL).  One launch fewer than recguru_pad_mask_count + recguru_embedding_bwd_plan.
+extern "C" int recguru_embedding_bwd_plan_padmask(const recguru_lookup_site_t* sites_host, int n_sites,
+                                                  int64_t V1, int64_t padding_idx, const int64_t* mask_ids,
+                                                  int64_t pad_index, float* mask_out, uint32_t* count3,
+                                                  void* workspace, int64_t workspace_bytes,
+                                                  recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(mask_ids != nullptr && mask_out != nullptr, RECGURU_E_SHAPE, "embedding_bwd_plan_padmask: null pointer");
+  return rg::plan_impl("embedding_bwd_plan_padmask", sites_host, n_sites, V1, padding_idx, workspace,
+                       workspace_bytes, mask_ids, pad_index, mask_out, count3, stream);
 }
 
 // Stage B: (optional zero fill,) chunked segmented reduce + span fix-up over the plan that

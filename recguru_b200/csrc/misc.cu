@@ -171,6 +171,12 @@ widen_ids_kernel(const int4* __restrict__ in4, const int32_t* __restrict__ in, i
   rg::pdl_trigger();
 }
 
+__global__ void timestamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
 __global__ void zero_u64_kernel(unsigned long long* p, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0ull;
@@ -249,5 +255,13 @@ extern "C" int recguru_widen_ids(const int32_t* ids32_in, int64_t n, int64_t* id
                  reinterpret_cast<const int4*>(ids32_in), ids32_in, n_vec, n,
                  reinterpret_cast<longlong2*>(ids_out), ids_out);
   RG_CHECK_LAUNCH("widen_ids");
+  return RECGURU_OK;
+}
+
+extern "C" int recguru_debug_timestamp(uint64_t* slot, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(slot != nullptr, RECGURU_E_SHAPE, "debug_timestamp: null pointer");
+  timestamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
+  RG_CHECK_LAUNCH("debug_timestamp");
   return RECGURU_OK;
 }

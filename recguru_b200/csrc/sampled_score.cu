@@ -212,6 +212,7 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
   rg::pdl_trigger();
 }
 
+constexpr int kSparseThreadsDefault = 1024;
 // Padding-aware variant (RECGURU_LOSS_SKIP_MASKED): positions under the pad mask are not scored.
 // On a padded batch (cfg2's Amazon-shaped one: 7 % of the positions are live, in runs of ~15 at
 // the tail of each sequence) the dense kernel's layout leaves the live work in a few warps, each
@@ -224,9 +225,10 @@ sampled_score_fwd_kernel(const float4* __restrict__ h, const float4* __restrict_
 //            whole warp per item as in the dense kernel -- every SM has ~100 items for 32 warps;
 //   phase 2  thread = live position: loss + derivatives, outputs scattered to their positions.
 // Loss partials are reduced in a fixed order (lane tree, warps, chunks) => bit-reproducible.
-constexpr int kSparseThreads = 1024;
-template <int VEC>
-__global__ void __launch_bounds__(kSparseThreads, 1)
+// NT = threads per CTA: 1024 (one CTA per SM), 512 or 256 (two / four CTAs per SM: the block-wide
+// phase barriers of one CTA overlap the gathers of its neighbours).
+template <int VEC, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
 sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __restrict__ weight,
                                 const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
                                 int64_t n_pos, int K, const float* __restrict__ mask, int kind,
@@ -240,7 +242,7 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
   constexpr int G = 32 / LANES;
   constexpr int VPL = VEC / LANES;
   constexpr int UN = 8 / G;
-  constexpr int kWarps = kSparseThreads / 32;
+  constexpr int kWarps = NT / 32;
   extern __shared__ float s_dyn[];
   const int C = K + 1;
   const int RS = C | 1;                                       // odd row stride: no bank conflicts
@@ -288,10 +290,12 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
         }
       }
       __syncthreads();
-      // fused dh: the rows of the dead positions are zero (coalesced 16-byte stores)
+      // fused dh: the rows of the dead positions are zero (coalesced 16-byte stores).  (Streaming them
+      // from a side kernel instead was measured: no gain -- this kernel is bound by its barrier-
+      // separated phases of dependent gathers, the 97 MB of zero rows ride along for free.)
       if (dh != nullptr) {
         const int tot4 = n_c * VEC;
-        for (int idx = tid; idx < tot4; idx += kSparseThreads) {
+        for (int idx = tid; idx < tot4; idx += NT) {
           const int q = idx / VEC;
           if (s_rank[q] < 0)
             st_stream_f4(dh + (cb + q) * VEC + (idx - q * VEC), make_float4(0.f, 0.f, 0.f, 0.f));
@@ -299,7 +303,7 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
       }
       // negatives: coalesced sweep over the chunk's [n_c, K] id block
       const int tot = n_c * K;
-      for (int idx = tid; idx < tot; idx += kSparseThreads) {
+      for (int idx = tid; idx < tot; idx += NT) {
         const int q = idx / K, k = idx - q * K;
         const int slot = s_rank[q];
         if (slot >= 0) {
@@ -741,8 +745,25 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
   }
   int64_t blocks = ceil_div(n_pos, kScoreWarps * kDensePW);
   int64_t pos_per_cta = 0;
+  int nt = kSparseThreadsDefault;
   if (skip_masked) {
-    blocks = rg::min64(num_sms(), ceil_div(n_pos, chunk));
+    // RECGURU_SCORE_RESERVE_SMS=<r>: leave r SMs to the kernels of the other branches of a step (the
+    // table-backward plan runs on a side stream while this persistent kernel owns every SM it gets)
+    static int env_reserve = -1;
+    if (env_reserve < 0) {
+      const char* e = getenv("RECGURU_SCORE_RESERVE_SMS");
+      env_reserve = e ? atoi(e) : 0;
+      if (env_reserve < 0 || env_reserve > 64) env_reserve = 0;
+    }
+    static int env_nt = -1;       // RECGURU_SPARSE_THREADS = 1024 | 512 | 256 threads per CTA
+    if (env_nt < 0) {
+      const char* e = getenv("RECGURU_SPARSE_THREADS");
+      env_nt = e ? atoi(e) : kSparseThreadsDefault;
+      if (env_nt != 1024 && env_nt != 512 && env_nt != 256) env_nt = kSparseThreadsDefault;
+    }
+    nt = env_nt;
+    if (chunk > nt) chunk = nt;                                // phase 0 maps one position to one thread
+    blocks = rg::min64(static_cast<int64_t>(num_sms() - env_reserve) * (1024 / nt), ceil_div(n_pos, chunk));
     pos_per_cta = align_up(ceil_div(n_pos, blocks), 32);
     blocks = ceil_div(n_pos, pos_per_cta);
   }
@@ -755,21 +776,33 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
   const float4* h4 = reinterpret_cast<const float4*>(h);
   const float4* w4 = reinterpret_cast<const float4*>(weight);
   const size_t sparse_smem = static_cast<size_t>(chunk) * (2 * RS + 2) * 4;
+#define RG_LAUNCH_SPARSE(V, T)                                                                    \
+  do {                                                                                           \
+    static rg::PerDeviceOnce once;           /* the attribute is per device */                  \
+    const int dev = rg::current_device();                                                        \
+    if (once.need(dev)) {                                                                        \
+      const cudaError_t ea = cudaFuncSetAttribute(sampled_score_fwd_sparse_kernel<V, T>,         \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);              \
+      RG_REQUIRE(ea == cudaSuccess, RECGURU_E_CUDA, "sampled_score_fwd: cudaFuncSetAttribute: %s", \
+                 cudaGetErrorString(ea));                                                        \
+      once.done(dev);                                                                            \
+    }                                                                                            \
+    rg::launch_pdl((sampled_score_fwd_sparse_kernel<V, T>), static_cast<unsigned>(blocks), T, sparse_smem, st,  \
+        h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
+        chunk, pos_per_cta, reinterpret_cast<float4*>(dh), dh_scale, live_count);                \
+  } while (0)
+  // 512 / 256 threads per CTA (2 / 4 CTAs per SM) measured slower (59 / 69 us vs 56 us at cfg2):
+  // compiled only with RECGURU_DEBUG_KNOBS
+#ifdef RECGURU_DEBUG_KNOBS
+#define RG_SPARSE_VARIANTS(V) if (nt == 256) RG_LAUNCH_SPARSE(V, 256); else if (nt == 512) RG_LAUNCH_SPARSE(V, 512); else
+#else
+#define RG_SPARSE_VARIANTS(V)
+#endif
 #define RG_LAUNCH_SCORE(V)                                                                       \
   do {                                                                                           \
     if (skip_masked) {                                                                           \
-      static rg::PerDeviceOnce once;           /* the attribute is per device */                \
-      const int dev = rg::current_device();                                                      \
-      if (once.need(dev)) {                                                                      \
-        const cudaError_t ea = cudaFuncSetAttribute(sampled_score_fwd_sparse_kernel<V>,          \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);           \
-        RG_REQUIRE(ea == cudaSuccess, RECGURU_E_CUDA, "sampled_score_fwd: cudaFuncSetAttribute: %s", \
-                   cudaGetErrorString(ea));                                                      \
-        once.done(dev);                                                                          \
-      }                                                                                          \
-      rg::launch_pdl((sampled_score_fwd_sparse_kernel<V>), static_cast<unsigned>(blocks), kSparseThreads, sparse_smem, st,  \
-          h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
-          chunk, pos_per_cta, reinterpret_cast<float4*>(dh), dh_scale, live_count);              \
+      RG_SPARSE_VARIANTS(V)                                                                      \
+      RG_LAUNCH_SPARSE(V, 1024);                                                                 \
     } else {                                                                                     \
       rg::launch_pdl((sampled_score_fwd_kernel<V>), static_cast<unsigned>(blocks), kScoreWarps * 32, 0, st,    \
           h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part);    \
@@ -782,6 +815,8 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
     default: RG_LAUNCH_SCORE(64); break;
   }
 #undef RG_LAUNCH_SCORE
+#undef RG_LAUNCH_SPARSE
+#undef RG_SPARSE_VARIANTS
   RG_CHECK_LAUNCH("sampled_score_fwd");
   if (kind >= 0) {
     rg::launch_pdl((loss_finalize_kernel), 1, 256, 0, st, part, blocks, loss_out);

@@ -101,6 +101,8 @@ class TrainStep:
         self._zero_done = torch.cuda.Event()
         self._fork = torch.cuda.Event()
         self._join = torch.cuda.Event()
+        self._zero_issued = False
+        self._k1_done = torch.cuda.Event()
         # up to n_inputs + 1 distinct mask sources per step; masks derived on the side stream (plan)
         # and on the main stream (forward) live in separate buffers: no cross-stream hazard
         self._side_masks = [torch.empty(B, L, **f32) for _ in range(n_inputs + 1)]
@@ -118,6 +120,19 @@ class TrainStep:
         self._cnt_ready = torch.cuda.Event()
         self.begin_step()
 
+    # -- step timeline (debug) -----------------------------------------------------------
+    TRACE_POINTS = ("start", "pad_mask", "plan_done", "dw_zero_done", "k1_done", "score_done", "apply_done")
+
+    def enable_trace(self) -> Tensor:
+        """Timestamp kernels (recguru_debug_timestamp) at the ends of the step's branches: they sit in the
+        captured graph too, so a replay yields the real multi-stream timeline (scripts/step_timeline.py)."""
+        self._trace = torch.zeros(len(self.TRACE_POINTS), dtype=torch.int64, device=self.device)
+        return self._trace
+
+    def _stamp(self, name: str) -> None:
+        if getattr(self, "_trace", None) is not None:
+            ops.raw_debug_timestamp(self._trace, self.TRACE_POINTS.index(name))
+
     # -- per-step state -------------------------------------------------------------------
     def begin_step(self) -> None:
         """Forget everything a previous (possibly unfinished: forward-only, failed, skipped) step
@@ -126,6 +141,7 @@ class TrainStep:
         of the previous step), so a validation forward without a backward cannot leak its
         live-count or its plan into the next step."""
         self._planned = False
+        self._zero_issued = False
         self._cnt_state = 0            # 0 = not issued this step, 1 = on the current stream, 2 = on the side stream
         self._dh_done = False
         self._dh_scale = None
@@ -168,6 +184,8 @@ class TrainStep:
             self.in_mask[i] = m
         self._in_done.add(i)
         self._in_ids[i], self._in_src[i] = ids, src
+        if i == self.n_inputs - 1:
+            self._stamp("k1_done")
         return self.x[i]
 
     # -- edge 2: hidden states -> loss ---------------------------------------------------
@@ -192,18 +210,37 @@ class TrainStep:
         self._loss_mask = mask
         # the loss is all this edge exports: positions under the pad mask are not scored
         if self.fuse_dh and not explicit and self._cnt_state != 0:
+            cur = torch.cuda.current_stream()
             if self._cnt_state == 2:
-                torch.cuda.current_stream().wait_event(self._cnt_ready)
+                cur.wait_event(self._cnt_ready)
+            self._issue_zero_fill(cur)
             ops.raw_sampled_score_loss(h, self.weight, pos, neg, mask, self.kind, bufs=self.sbuf,
                                        skip_masked=True, dh_out=self.dh, live_count=self._cnt,
                                        grad_scale=grad_loss)
             self._dh_done = True
             self._dh_scale = grad_loss
         else:
+            self._issue_zero_fill(torch.cuda.current_stream())
             ops.raw_sampled_score_loss(h, self.weight, pos, neg, mask, self.kind, bufs=self.sbuf,
                                        skip_masked=self.skip_masked)
+        self._stamp("score_done")
         self._loss_done = True
         return self.sbuf["aux"][0]
+
+    def _issue_zero_fill(self, cur) -> None:
+        """The dense zero fill of dW (dense-gradient contract) of a planned step, on its own stream,
+        BEHIND the input gathers (bandwidth-bound like them: side by side they stretched the gathers
+        from 29 to 43 us -- scripts/step_timeline.py) and BESIDE the scoring kernel (latency-bound: it
+        leaves the HBM pins idle)."""
+        if not (self._planned and self.dense_grad and self._zero_own and not self._zero_issued):
+            return
+        self._k1_done.record(cur)
+        self._zstream.wait_event(self._k1_done)
+        with torch.cuda.stream(self._zstream):
+            ops.raw_fill_zero(self.dW)
+            self._stamp("dw_zero_done")
+            self._zero_done.record(self._zstream)
+        self._zero_issued = True
 
     # -- table-backward plan: depends on the ids and the pad masks only -----------------------
     def plan_backward(self, in_ids: Sequence[Tensor], pos: Tensor, neg: Tensor,
@@ -224,33 +261,43 @@ class TrainStep:
                 for i in range(self.n_inputs)]
         loss_src = srcs[0] if loss_mask_ids is None else loss_mask_ids
         cur = torch.cuda.current_stream()
+        self._stamp("start")
         self._fork.record(cur)
         self._side.wait_event(self._fork)
-        if self.dense_grad and self._zero_own:
-            self._zstream.wait_event(self._fork)
-            with torch.cuda.stream(self._zstream):
-                ops.raw_fill_zero(self.dW)
-                self._zero_done.record(self._zstream)
+        # (the dense zero fill of dW is bandwidth-bound like the input gathers: it is issued by
+        # forward_loss, behind the gathers and beside the latency-bound scoring kernel)
+        self._zero_issued = False
         with torch.cuda.stream(self._side):
+            fused_src = None
             if mask is None:
-                # the side stream derives the pad masks itself (2 us kernels), so the plan does not
-                # have to wait for K1 and can be issued at the very start of the step
+                # the side stream derives the pad masks itself, so the plan does not have to wait for K1
+                # and can be issued at the very start of the step.  One shared mask source (SASRec): the
+                # plan's first kernel derives mask and count (recguru_embedding_bwd_plan_padmask);
+                # otherwise one 2 us kernel per distinct source.
                 distinct: List[Tensor] = []
-                side = {}
                 for s in [loss_src] + srcs:
-                    if any(s is t for t in distinct):
-                        continue
-                    j = len(distinct)
-                    distinct.append(s)
-                    if s is loss_src and self.fuse_dh and self._cnt_state == 0:
-                        # (state 1: the forward already counted on its stream)
-                        side[id(s)] = ops.raw_pad_mask_count(s, self.pad_index, self._side_masks[j], self._cnt).view(n)
-                        self._cnt_ready.record(self._side)
-                        self._cnt_state = 2
-                    else:
-                        side[id(s)] = ops.raw_pad_mask(s, self.pad_index, out=self._side_masks[j]).view(n)
+                    if not any(s is t for t in distinct):
+                        distinct.append(s)
+                side = {}
+                need_cnt = self.fuse_dh and self._cnt_state == 0
+                if len(distinct) == 1 and not need_cnt and os.environ.get("RECGURU_BWD_PLAN", "1") == "2":
+                    # nobody waits for the population count: the plan's first kernel derives the mask
+                    fused_src = distinct[0]
+                    side[id(fused_src)] = self._side_masks[0].view(n)
+                else:
+                    # (the fused scoring kernel needs sum(mask) early: a 2 us kernel of its own, so that
+                    # the event it waits for sits at the head of the plan branch, not at its end)
+                    for j, s in enumerate(distinct):
+                        if s is loss_src and self.fuse_dh and self._cnt_state == 0:
+                            # (state 1: the forward already counted on its stream)
+                            side[id(s)] = ops.raw_pad_mask_count(s, self.pad_index, self._side_masks[j], self._cnt).view(n)
+                            self._cnt_ready.record(self._side)
+                            self._cnt_state = 2
+                        else:
+                            side[id(s)] = ops.raw_pad_mask(s, self.pad_index, out=self._side_masks[j]).view(n)
                 in_live = [side[id(s)] for s in srcs]
                 loss_live = side[id(loss_src)]
+                self._stamp("pad_mask")
             else:
                 in_live = [mask.view(n)] * self.n_inputs
                 loss_live = mask.view(n)
@@ -258,10 +305,15 @@ class TrainStep:
                 ops.raw_fill_zero(self.dW)
             sites = [Site(in_ids[i], None, live=in_live[i]) for i in range(self.n_inputs)]
             sites += [Site(pos, None, live=loss_live), Site(neg, None, group=self.K, live=loss_live)]
-            ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
+            if fused_src is not None:
+                ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, mask_ids=fused_src,
+                                           pad_index=self.pad_index)
+            else:
+                ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
             if not self.dense_grad:
                 self.epoch += 1
                 ops.raw_embedding_bwd_mark_rows(sites, self.V1, self.ws_bwd, self.row_epoch, self.epoch)
+            self._stamp("plan_done")
             self._join.record(self._side)
         self._planned = True
 
@@ -292,7 +344,10 @@ class TrainStep:
         if self._planned:
             torch.cuda.current_stream().wait_event(self._join)
             if self.dense_grad and self._zero_own:
-                torch.cuda.current_stream().wait_event(self._zero_done)
+                if not self._zero_issued:                  # (forward_loss of this step did not run planned)
+                    ops.raw_fill_zero(self.dW)
+                else:
+                    torch.cuda.current_stream().wait_event(self._zero_done)
             ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
         elif self.dense_grad:
             ops.raw_embedding_bwd(sites, self.V1, self.d, self.padding_idx, out=self.dW, zero_fill=True,
@@ -302,6 +357,7 @@ class TrainStep:
             ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
             self.epoch += 1
             ops.raw_embedding_bwd_mark_rows(sites, self.V1, self.ws_bwd, self.row_epoch, self.epoch)
+        self._stamp("apply_done")
         self.begin_step()
         return self.dh, self.dW
 

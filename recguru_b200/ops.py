@@ -182,13 +182,32 @@ def raw_embedding_bwd(sites: Sequence[Site], V1: int, d: int, padding_idx: int =
     return out
 
 
-def raw_embedding_bwd_plan(sites: Sequence[Site], V1: int, padding_idx: int, workspace: Tensor) -> None:
-    """Stage A (compaction + stable sort) on the current stream; needs ids and live/coef only."""
+def raw_embedding_bwd_plan(sites: Sequence[Site], V1: int, padding_idx: int, workspace: Tensor,
+                           mask_ids: Optional[Tensor] = None, pad_index: int = 0,
+                           count3: Optional[Tensor] = None) -> None:
+    """Stage A (compaction + stable sort) on the current stream; needs ids and live/coef only.
+
+    ``mask_ids``: derive the shared pad mask inside the plan (``recguru_embedding_bwd_plan_padmask``):
+    every site's ``live`` must be the SAME tensor, which is written here as ``mask_ids != pad_index``
+    (and its population count to ``count3``, the int32 ``[3]`` buffer of :func:`raw_pad_mask_count`)."""
     lib = _lib.load()
     arr, keep, total = _marshal_sites(sites, None)
     workspace = _need(workspace, torch.uint8, "workspace")
-    check(lib.recguru_embedding_bwd_plan(arr, len(sites), V1, int(padding_idx), _ptr(workspace),
-                                         workspace.numel(), _stream()), "embedding_bwd_plan")
+    if mask_ids is None:
+        check(lib.recguru_embedding_bwd_plan(arr, len(sites), V1, int(padding_idx), _ptr(workspace),
+                                             workspace.numel(), _stream()), "embedding_bwd_plan")
+        return
+    mask_ids = _need(mask_ids, torch.int64, "mask_ids")
+    mask_out = sites[0].live
+    if mask_out is None or any(s.live is None or s.live.data_ptr() != mask_out.data_ptr() for s in sites):
+        raise RuntimeError("recguru: mask_ids needs every site's live to be one shared mask tensor")
+    if mask_out.numel() != mask_ids.numel() or not mask_out.is_contiguous():
+        raise RuntimeError("recguru: the shared mask must be contiguous with one entry per mask id")
+    if count3 is not None and (count3.dtype != torch.int32 or count3.numel() != 3 or not count3.is_cuda):
+        raise RuntimeError("recguru: count3 must be a CUDA int32 [3] tensor")
+    check(lib.recguru_embedding_bwd_plan_padmask(arr, len(sites), V1, int(padding_idx), _ptr(mask_ids),
+                                                 int(pad_index), _ptr(mask_out), _ptr(count3), _ptr(workspace),
+                                                 workspace.numel(), _stream()), "embedding_bwd_plan_padmask")
 
 
 def raw_embedding_bwd_apply(sites: Sequence[Site], V1: int, d: int, out: Tensor, workspace: Tensor,
@@ -258,6 +277,13 @@ def raw_widen_ids(ids32: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return out
 
 
+def raw_debug_timestamp(slots: Tensor, index: int) -> None:
+    """slots[index] = %globaltimer (ns) when the current stream gets here (int64 CUDA tensor); capturable."""
+    if slots.dtype != torch.int64 or not slots.is_cuda:
+        raise RuntimeError("recguru: slots must be a CUDA int64 tensor")
+    check(_lib.load().recguru_debug_timestamp(slots.data_ptr() + 8 * int(index), _stream()), "debug_timestamp")
+
+
 def raw_fill_zero(x: Tensor) -> Tensor:
     x = _need(x, torch.float32, "x")
     check(_lib.load().recguru_fill_zero(_ptr(x), x.numel(), _stream()), "fill_zero")
@@ -289,6 +315,7 @@ def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
     ``dh_out`` (with ``skip_masked``): also write d loss / d h in the same kernel
     (``recguru_sampled_score_loss_fwd_dh``); ``live_count`` = the int32 ``[3]`` buffer
     :func:`raw_pad_mask_count` filled for this mask, ``grad_scale`` an optional device scalar.
+
 
     Returns (p [..,1], n [..,K], loss_aux [2] or None, dp_unit, dn_unit).  loss_aux[0] is the
     loss, loss_aux[1] = 1/sum(mask)."""

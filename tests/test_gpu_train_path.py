@@ -349,3 +349,104 @@ def test_sce_module_and_cat(ops):
     assert torch.allclose(logits.cpu(), t(r["logits"]), rtol=1e-5, atol=1e-5)
     loss = M.FusedSampledCrossEntropyLoss()(logits, None, K + 1, mask=dev(t(r["mask"])))
     assert torch.allclose(loss.cpu(), t(r["loss"]), rtol=1e-5)
+
+
+# ---------------------------------------------------------------- fused plan (round 2) ---------
+@pytest.mark.parametrize("V1,n_rows,K,frac", [(100_002, 204_800, 5, 0.926), (500_002, 25_600, 30, 0.5),
+                                              (5_002, 3_000, 5, 0.0), (70, 1_000, 3, 0.3), (300_000, 40_000, 5, 1.0)])
+def test_fused_plan_equals_round1_chain(ops, monkeypatch, V1, n_rows, K, frac):
+    """The 2 + passes launch plan (plan_count / plan_scatter / radix_pass) leaves the SAME workspace
+    contents -- live count, sorted keys, sorted occurrence indices -- as the default ten-launch chain,
+    in row mode and in by-index mode, so apply's sums are bit-identical.  Checked through apply: dW from
+    both plans must be bit-equal.  (The switch RECGURU_BWD_PLAN is read once per process: the fused
+    plan runs in a child process.)"""
+    import os
+    import subprocess
+    import sys
+    g = torch.Generator().manual_seed(V1 + n_rows)
+    d = 32
+    mask = (torch.rand(n_rows, generator=g) >= frac).float()
+    ids_in = torch.randint(0, V1, (n_rows,), generator=g)
+    ids_pos = torch.randint(0, V1, (n_rows,), generator=g)
+    ids_neg = torch.randint(0, V1, (n_rows * K,), generator=g)
+    ids_in[torch.rand(n_rows, generator=g) < 0.05] = 0           # padding ids at live rows too
+    X = torch.randn(n_rows, d, generator=g)
+    cp = torch.randn(n_rows, generator=g)
+    cn = torch.randn(n_rows * K, generator=g)
+    dev_ = lambda x: x.cuda()  # noqa: E731
+    m, Xd = dev_(mask), dev_(X)
+
+    def run(row_mode):
+        live2 = m if row_mode else m.clone()                      # a different pointer => by-index compaction
+        sites = [ops.Site(dev_(ids_in), Xd, coef=m, live=m), ops.Site(dev_(ids_pos), Xd, coef=dev_(cp), live=m),
+                 ops.Site(dev_(ids_neg), Xd, coef=dev_(cn), group=K, live=live2)]
+        return ops.raw_embedding_bwd(sites, V1, d, 0)
+
+    # same process, both plans: the switch is read once per process, so the v1 chain runs in a child
+    script = f"""
+import sys, torch, pickle
+sys.path.insert(0, {str(__import__('pathlib').Path(__file__).resolve().parent.parent)!r})
+from recguru_b200 import ops
+g = torch.Generator().manual_seed({V1 + n_rows})
+V1, n_rows, K, frac, d = {V1}, {n_rows}, {K}, {frac}, 32
+mask = (torch.rand(n_rows, generator=g) >= frac).float()
+ids_in = torch.randint(0, V1, (n_rows,), generator=g)
+ids_pos = torch.randint(0, V1, (n_rows,), generator=g)
+ids_neg = torch.randint(0, V1, (n_rows * K,), generator=g)
+ids_in[torch.rand(n_rows, generator=g) < 0.05] = 0
+X = torch.randn(n_rows, d, generator=g); cp = torch.randn(n_rows, generator=g); cn = torch.randn(n_rows * K, generator=g)
+m, Xd = mask.cuda(), X.cuda()
+res = []
+for row_mode in (True, False):
+    live2 = m if row_mode else m.clone()
+    sites = [ops.Site(ids_in.cuda(), Xd, coef=m, live=m), ops.Site(ids_pos.cuda(), Xd, coef=cp.cuda(), live=m),
+             ops.Site(ids_neg.cuda(), Xd, coef=cn.cuda(), group=K, live=live2)]
+    res.append(ops.raw_embedding_bwd(sites, V1, d, 0).cpu())
+torch.save(res, sys.argv[1])
+"""
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        r = subprocess.run([sys.executable, "-c", script, td + "/v1.pt"], env=dict(os.environ, RECGURU_BWD_PLAN="2"),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        v1 = torch.load(td + "/v1.pt")
+    for i, row_mode in enumerate((True, False)):
+        dW = run(row_mode).cpu()
+        assert torch.equal(dW, v1[i]), f"row_mode={row_mode}: fused plan differs from the default chain"
+    assert torch.equal(v1[0], v1[1])                              # by-row == by-index (same order of sums)
+    # and against plain autograd
+    Wr = torch.zeros(V1, d, requires_grad=True)
+    emb = torch.nn.functional.embedding
+    tot = (emb(ids_in, Wr) * X * mask[:, None]).sum() + (emb(ids_pos, Wr) * X * (cp * mask)[:, None]).sum() \
+        + (emb(ids_neg, Wr).view(n_rows, K, d) * X[:, None, :] * (cn.view(n_rows, K) * mask[:, None])[..., None]).sum()
+    tot.backward()
+    ref = Wr.grad.clone(); ref[0] = 0
+    assert torch.allclose(run(True).cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_plan_padmask_entry_point(ops):
+    """recguru_embedding_bwd_plan_padmask: mask (and its count) derived inside the plan == pad mask kernel + plan."""
+    g = torch.Generator().manual_seed(12)
+    V1, n_rows, K, d = 5_002, 6_000, 5, 64
+    src = torch.randint(0, 4, (n_rows,), generator=g)             # 25 % pads
+    ids = [torch.randint(0, V1, (n_rows * gr,), generator=g).cuda() for gr in (1, 1, K)]
+    X = torch.randn(n_rows, d, generator=g).cuda()
+    coefs = [torch.randn(n_rows * gr, generator=g).cuda() for gr in (1, 1, K)]
+    total = n_rows * (2 + K)
+    out = []
+    for fused in (False, True):
+        mask = torch.full((n_rows,), 7.0, device="cuda")
+        cnt = torch.zeros(3, dtype=torch.int32, device="cuda")
+        ws = torch.zeros(ops.embedding_bwd_workspace_bytes(total, V1, d), dtype=torch.uint8, device="cuda")
+        sites = [ops.Site(ids[i], X, coef=coefs[i], group=gr, live=mask) for i, gr in enumerate((1, 1, K))]
+        if fused:
+            ops.raw_embedding_bwd_plan(sites, V1, 0, ws, mask_ids=src.cuda(), pad_index=0, count3=cnt)
+        else:
+            ops.raw_pad_mask_count(src.cuda(), 0, mask, cnt)
+            ops.raw_embedding_bwd_plan(sites, V1, 0, ws)
+        dW = torch.empty(V1, d, device="cuda")
+        ops.raw_embedding_bwd_apply(sites, V1, d, dW, ws, mode=ops.DW_ZERO_FILL)
+        out.append((mask.cpu(), cnt.cpu(), dW.cpu()))
+    assert torch.equal(out[0][0], (src != 0).float()) and torch.equal(out[1][0], out[0][0])
+    assert out[1][1].tolist() == [0, 0, int((src != 0).sum())] == out[0][1].tolist()
+    assert torch.equal(out[0][2], out[1][2])
