@@ -94,6 +94,35 @@ int recguru_pad_mask_count(const int64_t* ids, int64_t n, int64_t pad_index, flo
 int recguru_pe_mask(const float* x, const float* pe, const float* mask, int64_t n_tokens,
                     int64_t L, int64_t d, float* out, recguru_stream_t stream);
 
+/* SURVEY 8f rank 4 -- the nn.Dropout that closes PositionalEncoding.forward
+ * (Transformer/transformer.py:104-106, p = 0.5: config_auto4rec.py:225), fused into K1 and
+ * BIT-COMPATIBLE with torch's own CUDA dropout kernel and generator stream:
+ *   out = dropout((weight[ids] + pe) * mask, p)  ==  torch.nn.functional.dropout(K1_out, p, True)
+ * when torch's CUDA generator holds (seed, philox_offset) and its launch has torch_threads =
+ * 256 * min(SMs * (maxThreadsPerSM / 256), ceil(numel / 256)) threads; the caller then advances the
+ * generator by ((numel - 1) / (torch_threads * 4) + 1) * 4, as torch does (recguru_b200/ops.py:
+ * torch_dropout_state).  recguru_dropout is the same dropout on an existing tensor (rows whose
+ * row_mask entry is 0 pass through untouched; row_mask may be NULL) -- also its own backward:
+ * grad_in = recguru_dropout(grad_out) with the state of the forward call. */
+int recguru_gather_pe_mask_dropout(const float* weight, int64_t V1, int64_t d, const int64_t* ids,
+                                   int64_t n_tokens, int64_t L, const float* pe, const float* mask_in,
+                                   int64_t pad_index, double p_drop, uint64_t seed, uint64_t philox_offset,
+                                   int64_t torch_threads, float* out, float* mask_out,
+                                   recguru_stream_t stream);
+int recguru_dropout(const float* x, const float* row_mask, int64_t n_rows, int64_t d, double p_drop,
+                    uint64_t seed, uint64_t philox_offset, int64_t torch_threads, float* out,
+                    recguru_stream_t stream);
+/* P1' -- gradient of a LEARNED position table (PositionalEncodingM, Transformer/transformer.py:327-342:
+ * x + pos_emb(arange(L)), then the mask):  dP[l,:] (+)= sum_b mask[b,l] * g[b,l,:], fixed summation
+ * order (bit-reproducible).  g [B,L,d], mask [B,L], dP [L,d]. */
+int recguru_pe_grad(const float* g, const float* mask, int64_t B, int64_t L, int64_t d, int accumulate,
+                    float* dP, recguru_stream_t stream);
+/* SURVEY 8f rank 4 -- user representation: u[b,:] = h[b,L-1,:]  (dec_embedding[:, -1, :],
+ * train_auto.py:178,:194; get_user_embed, gan_training.py:152-162), as fp32 (discriminator /
+ * get_scores input) and/or bf16 (operand of the catalog sweep) in one pass; either may be NULL. */
+int recguru_extract_last(const float* h, int64_t B, int64_t L, int64_t d, float* out_f32, void* out_bf16,
+                         recguru_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Piece 2 -- deterministic embedding-table backward                               (K2: B1)
  *   replaces  ATen embedding_dense_backward at every lookup site + the dense add_

@@ -37,6 +37,12 @@ SIGNATURES = {
                                          c_i64, c_ptr, c_ptr, c_ptr]),
     "recguru_pad_mask": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "recguru_pe_mask": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    "recguru_gather_pe_mask_dropout": (C.c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64,
+                                                 C.c_double, C.c_uint64, C.c_uint64, c_i64, c_ptr, c_ptr, c_ptr]),
+    "recguru_dropout": (C.c_int, [c_ptr, c_ptr, c_i64, c_i64, C.c_double, C.c_uint64, C.c_uint64, c_i64, c_ptr,
+                                  c_ptr]),
+    "recguru_pe_grad": (C.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, C.c_int, c_ptr, c_ptr]),
+    "recguru_extract_last": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "recguru_embedding_bwd_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "recguru_embedding_bwd": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_i64, c_i64, c_ptr,
                                         C.c_int, c_ptr, c_i64, c_ptr]),

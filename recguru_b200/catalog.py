@@ -88,6 +88,14 @@ def get_scores_rank(u: Tensor, table_weight: Tensor, target: Tensor, n_items: Te
     return ops.raw_candidate_scores_rank(u, table_weight, target, n_items, want_scores)
 
 
+def user_reps(h: Tensor, bf16: bool = True):
+    """User representations from the recommender's output ``h [B, L, d]``: ``u = h[:, -1, :]``
+    (``dec_embedding[:, -1, :]``, train_auto.py:178,:194; ``get_user_embed``, gan_training.py:152-162)
+    as fp32 -- what ``get_scores`` and the discriminator take -- and, in the same pass, as the bf16
+    operand of the catalog sweep.  Returns ``(u_f32, u_bf16 | None)``."""
+    return ops.raw_extract_last(h, want_f32=True, want_bf16=bf16)
+
+
 # --------------------------------------------------------------------------------------
 # shard arithmetic
 # --------------------------------------------------------------------------------------

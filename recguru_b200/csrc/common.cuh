@@ -123,6 +123,52 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+// Philox4x32-10 (Salmon et al.), the generator of cuRAND's curandStatePhilox4_32_10 and of torch's
+// CUDA generator: counter (c0..c3), key (k0, k1).
+struct Philox4 { uint32_t x, y, z, w; };
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return {c0, c1, c2, c3};
+}
+
+// torch's fused CUDA dropout (ATen/native/cuda/Dropout.cu, fused_dropout_kernel_vec<float, ..., 4>)
+// restated per float4: torch launches T = grid * 256 threads, thread t takes the float4 groups
+// q = t, t + T, t + 2T, ...; for its i-th group it draws curand_uniform4 number i of the Philox
+// stream (seed, subsequence t, offset), keeps element c iff uniform_c < keep_p, and writes
+// (x * keep) * (1 / keep_p).  cuRAND: subsequence -> counter words 2-3, offset / 4 + i -> words 0-1,
+// uniform = u32 * 2^-32 + 2^-33.  So group q needs one Philox block, whoever computes it.
+struct DropoutParams {
+  float keep_p;          // 1 - p; 0 disables
+  float scale;           // 1 / keep_p (fp32, as torch computes it)
+  uint32_t seed_lo, seed_hi;
+  uint64_t offset4;      // philox offset / 4
+  uint32_t T;            // threads of torch's launch
+};
+__device__ __forceinline__ float4 torch_dropout4(float4 v, int64_t q, const DropoutParams& dp) {
+  const uint32_t t = static_cast<uint32_t>(q % dp.T);
+  const uint64_t c = dp.offset4 + static_cast<uint64_t>(q / dp.T);
+  const Philox4 r = philox4x32_10(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), t, 0u, dp.seed_lo, dp.seed_hi);
+  constexpr float kInv = 2.3283064365386963e-10f;             // 2^-32
+  const float u0 = __fmaf_rn(static_cast<float>(r.x), kInv, kInv * 0.5f);
+  const float u1 = __fmaf_rn(static_cast<float>(r.y), kInv, kInv * 0.5f);
+  const float u2 = __fmaf_rn(static_cast<float>(r.z), kInv, kInv * 0.5f);
+  const float u3 = __fmaf_rn(static_cast<float>(r.w), kInv, kInv * 0.5f);
+  v.x = __fmul_rn(__fmul_rn(v.x, u0 < dp.keep_p ? 1.f : 0.f), dp.scale);
+  v.y = __fmul_rn(__fmul_rn(v.y, u1 < dp.keep_p ? 1.f : 0.f), dp.scale);
+  v.z = __fmul_rn(__fmul_rn(v.z, u2 < dp.keep_p ? 1.f : 0.f), dp.scale);
+  v.w = __fmul_rn(__fmul_rn(v.w, u3 < dp.keep_p ? 1.f : 0.f), dp.scale);
+  return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

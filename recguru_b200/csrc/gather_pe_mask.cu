@@ -12,6 +12,7 @@
 // use (memory-level parallelism), adds the PE vector (L2-resident, [L,d]) and streams the
 // result out with 128-bit stores.  Arithmetic is an fp32 add followed by an fp32 multiply
 // by 0/1 (no FMA contraction), i.e. bit-identical to the reference's two ATen kernels.
+#include <cuda_bf16.h>
 #include <limits.h>
 
 #include "common.cuh"
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(kGatherThreads)
 gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restrict__ ids,
                       const float4* __restrict__ pe, const float* __restrict__ mask_in,
                       int64_t pad_index, int64_t n_tokens, int L, int vec_rt,
-                      float4* __restrict__ out, float* __restrict__ mask_out) {
+                      float4* __restrict__ out, float* __restrict__ mask_out, DropoutParams drop) {
   rg::pdl_wait();
   extern __shared__ int smem_raw[];
   const int vec = VEC > 0 ? VEC : vec_rt;
@@ -75,6 +76,9 @@ gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restri
         r.y = __fmul_rn(__fadd_rn(r.y, p.y), m);
         r.z = __fmul_rn(__fadd_rn(r.z, p.z), m);
         r.w = __fmul_rn(__fadd_rn(r.w, p.w), m);
+        // fused nn.Dropout (Transformer/transformer.py:104-106), bit-compatible with torch's kernel and
+        // generator stream; rows under the mask are (signed) zeros whatever is drawn: no Philox there
+        if (drop.keep_p > 0.f && m != 0.f) r = torch_dropout4(r, tok * vec + vv[u], drop);
         st_stream_f4(out + tok * vec + vv[u], r);
       }
     }
@@ -182,10 +186,10 @@ extern "C" int recguru_pad_mask(const int64_t* ids, int64_t n, int64_t pad_index
   return RECGURU_OK;
 }
 
-extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d,
-                                      const int64_t* ids, int64_t n_tokens, int64_t L,
-                                      const float* pe, const float* mask_in, int64_t pad_index,
-                                      float* out, float* mask_out, recguru_stream_t stream) {
+static int gather_pe_mask_impl(const float* weight, int64_t V1, int64_t d,
+                               const int64_t* ids, int64_t n_tokens, int64_t L,
+                               const float* pe, const float* mask_in, int64_t pad_index,
+                               float* out, float* mask_out, rg::DropoutParams drop, recguru_stream_t stream) {
   using namespace rg;
   RG_REQUIRE(weight && (n_tokens == 0 || (ids && out)), RECGURU_E_SHAPE,
              "gather_pe_mask: null pointer");
@@ -208,7 +212,7 @@ extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d
   float4* o4 = reinterpret_cast<float4*>(out);
 #define RG_LAUNCH_GATHER(V)                                                              \
   rg::launch_pdl((gather_pe_mask_kernel<V>), static_cast<unsigned>(blocks), kGatherThreads, smem, st,  \
-      w4, ids, pe4, mask_in, pad_index, n_tokens, static_cast<int>(L), vec, o4, mask_out)
+      w4, ids, pe4, mask_in, pad_index, n_tokens, static_cast<int>(L), vec, o4, mask_out, drop)
   switch (vec) {
     case 8: RG_LAUNCH_GATHER(8); break;
     case 16: RG_LAUNCH_GATHER(16); break;
@@ -218,6 +222,79 @@ extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d
   }
 #undef RG_LAUNCH_GATHER
   RG_CHECK_LAUNCH("gather_pe_mask");
+  return RECGURU_OK;
+}
+
+extern "C" int recguru_gather_pe_mask(const float* weight, int64_t V1, int64_t d,
+                                      const int64_t* ids, int64_t n_tokens, int64_t L,
+                                      const float* pe, const float* mask_in, int64_t pad_index,
+                                      float* out, float* mask_out, recguru_stream_t stream) {
+  rg::DropoutParams none = {};
+  return gather_pe_mask_impl(weight, V1, d, ids, n_tokens, L, pe, mask_in, pad_index, out, mask_out, none, stream);
+}
+
+namespace rg {
+static int make_dropout(const char* who, double p_drop, uint64_t seed, uint64_t offset, int64_t torch_threads,
+                        DropoutParams* dp) {
+  RG_REQUIRE(p_drop >= 0.0 && p_drop < 1.0, RECGURU_E_SHAPE, "%s: dropout p=%g not in [0, 1)", who, p_drop);
+  RG_REQUIRE(offset % 4 == 0 && torch_threads > 0 && torch_threads < (1ll << 32), RECGURU_E_SHAPE,
+             "%s: philox offset must be a multiple of 4 and 0 < torch_threads < 2^32", who);
+  const float keep = static_cast<float>(1.0 - p_drop);       // torch: pa = (float)(1. - p)
+  dp->keep_p = p_drop == 0.0 ? 0.f : keep;
+  dp->scale = 1.0f / keep;
+  dp->seed_lo = static_cast<uint32_t>(seed);
+  dp->seed_hi = static_cast<uint32_t>(seed >> 32);
+  dp->offset4 = offset / 4;
+  dp->T = static_cast<uint32_t>(torch_threads);
+  return RECGURU_OK;
+}
+
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float4* __restrict__ x, const float* __restrict__ row_mask, int vec, int64_t n_vec,
+               float4* __restrict__ out, DropoutParams drop) {
+  rg::pdl_wait();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    float4 v = ld_stream_f4(x + i);
+    // rows whose mask is 0 hold zeros on the forward side and receive no gradient use on the backward
+    // side: they pass through unchanged (sign of zero included)
+    if (row_mask == nullptr || __ldg(row_mask + i / vec) != 0.f) v = torch_dropout4(v, i, drop);
+    st_stream_f4(out + i, v);
+  }
+  rg::pdl_trigger();
+}
+}  // namespace rg
+
+extern "C" int recguru_gather_pe_mask_dropout(const float* weight, int64_t V1, int64_t d,
+                                              const int64_t* ids, int64_t n_tokens, int64_t L,
+                                              const float* pe, const float* mask_in, int64_t pad_index,
+                                              double p_drop, uint64_t seed, uint64_t philox_offset,
+                                              int64_t torch_threads, float* out, float* mask_out,
+                                              recguru_stream_t stream) {
+  rg::DropoutParams dp = {};
+  int rc = rg::make_dropout("gather_pe_mask_dropout", p_drop, seed, philox_offset, torch_threads, &dp);
+  if (rc) return rc;
+  RG_REQUIRE(pe != nullptr, RECGURU_E_SHAPE, "gather_pe_mask_dropout: pe is null (dropout follows the positional add)");
+  return gather_pe_mask_impl(weight, V1, d, ids, n_tokens, L, pe, mask_in, pad_index, out, mask_out, dp, stream);
+}
+
+extern "C" int recguru_dropout(const float* x, const float* row_mask, int64_t n_rows, int64_t d, double p_drop,
+                               uint64_t seed, uint64_t philox_offset, int64_t torch_threads, float* out,
+                               recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(n_rows >= 0 && d > 0 && d % 4 == 0, RECGURU_E_SHAPE, "dropout: bad sizes (d must be a multiple of 4)");
+  if (n_rows == 0) return RECGURU_OK;
+  RG_REQUIRE(x && out && aligned16(x) && aligned16(out), RECGURU_E_SHAPE, "dropout: null or unaligned pointer");
+  DropoutParams dp = {};
+  int rc = make_dropout("dropout", p_drop, seed, philox_offset, torch_threads, &dp);
+  if (rc) return rc;
+  RG_REQUIRE(dp.keep_p > 0.f, RECGURU_E_SHAPE, "dropout: p must be > 0");
+  const int64_t n_vec = n_rows * (d / 4);
+  const int64_t blocks = rg::min64(ceil_div(n_vec, 256 * 4), static_cast<int64_t>(num_sms()) * 16);
+  rg::launch_pdl((dropout_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const float4*>(x), row_mask, static_cast<int>(d / 4), n_vec,
+                 reinterpret_cast<float4*>(out), dp);
+  RG_CHECK_LAUNCH("dropout");
   return RECGURU_OK;
 }
 
@@ -240,5 +317,102 @@ extern "C" int recguru_pe_mask(const float* x, const float* pe, const float* mas
       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pe), mask, n_vec, vec,
       static_cast<int>(L), reinterpret_cast<float4*>(out));
   RG_CHECK_LAUNCH("pe_mask");
+  return RECGURU_OK;
+}
+
+// ---- P1' (learned positions, Transformer/transformer.py:327-342) and user-rep extraction --------
+namespace rg {
+// dP[l, :] = sum_b mask[b, l] * g[b, l, :]  -- the gradient of a LEARNED position table behind
+// x + pos_emb(arange(L)).  One CTA per position l (x one 128-float column block): warp w sums the
+// batch rows b = w, w + 8, ... in ascending order, the eight partial rows are combined in warp order:
+// a fixed summation tree, bit-reproducible.
+__global__ void __launch_bounds__(256)
+pe_grad_kernel(const float4* __restrict__ g, const float* __restrict__ mask, int64_t B, int L, int vec,
+               int accumulate, float4* __restrict__ dP) {
+  rg::pdl_wait();
+  __shared__ float4 s_part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l = blockIdx.x;
+  const int col = blockIdx.y * 32 + lane;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < vec) {
+    for (int64_t b = warp; b < B; b += 8) {
+      const float m = __ldg(mask + b * L + l);
+      if (m != 0.f) {
+        const float4 v = ld_stream_f4(g + (b * L + l) * vec + col);
+        acc.x = fmaf(m, v.x, acc.x); acc.y = fmaf(m, v.y, acc.y);
+        acc.z = fmaf(m, v.z, acc.z); acc.w = fmaf(m, v.w, acc.w);
+      }
+    }
+  }
+  s_part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < vec) {
+    float4 t = s_part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      t.x += s_part[w][lane].x; t.y += s_part[w][lane].y; t.z += s_part[w][lane].z; t.w += s_part[w][lane].w;
+    }
+    float4* dst = dP + static_cast<int64_t>(l) * vec + col;
+    if (accumulate) { const float4 o = *dst; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+    *dst = t;
+  }
+  rg::pdl_trigger();
+}
+
+// u[b, :] = h[b, L-1, :]  (dec_embedding[:, -1, :] / get_seq_embed(...)[:, -1, :]), fp32 and/or bf16
+__global__ void __launch_bounds__(256)
+extract_last_kernel(const float4* __restrict__ h, int64_t B, int L, int vec, float4* __restrict__ out_f32,
+                    uint2* __restrict__ out_bf16) {
+  rg::pdl_wait();
+  const int64_t n = B * vec;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t b = i / vec;
+    const int c = static_cast<int>(i - b * vec);
+    const float4 v = __ldg(h + (b * L + (L - 1)) * vec + c);
+    if (out_f32) out_f32[i] = v;
+    if (out_bf16) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+      const __nv_bfloat162 bb = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&a);
+      o.y = *reinterpret_cast<const uint32_t*>(&bb);
+      out_bf16[i] = o;
+    }
+  }
+  rg::pdl_trigger();
+}
+}  // namespace rg
+
+extern "C" int recguru_pe_grad(const float* g, const float* mask, int64_t B, int64_t L, int64_t d, int accumulate,
+                               float* dP, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(B >= 0 && L > 0 && L < (1 << 30) && d > 0 && d % 4 == 0, RECGURU_E_SHAPE, "pe_grad: bad sizes");
+  RG_REQUIRE(dP && aligned16(dP) && (B == 0 || (g && mask && aligned16(g))), RECGURU_E_SHAPE,
+             "pe_grad: null or unaligned pointer");
+  const int vec = static_cast<int>(d / 4);
+  const dim3 grid(static_cast<unsigned>(L), static_cast<unsigned>(ceil_div(vec, 32)));
+  rg::launch_pdl((pe_grad_kernel), grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const float4*>(g), mask, B, static_cast<int>(L), vec, accumulate,
+                 reinterpret_cast<float4*>(dP));
+  RG_CHECK_LAUNCH("pe_grad");
+  return RECGURU_OK;
+}
+
+extern "C" int recguru_extract_last(const float* h, int64_t B, int64_t L, int64_t d, float* out_f32,
+                                    void* out_bf16, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(B >= 0 && L > 0 && d > 0 && d % 4 == 0, RECGURU_E_SHAPE, "extract_last: bad sizes");
+  if (B == 0) return RECGURU_OK;
+  RG_REQUIRE(h && aligned16(h) && (out_f32 || out_bf16), RECGURU_E_SHAPE, "extract_last: null pointer");
+  RG_REQUIRE((!out_f32 || aligned16(out_f32)) && (reinterpret_cast<uintptr_t>(out_bf16) & 7u) == 0, RECGURU_E_SHAPE,
+             "extract_last: unaligned output");
+  const int vec = static_cast<int>(d / 4);
+  const int64_t blocks = rg::min64(ceil_div(B * vec, 256), static_cast<int64_t>(num_sms()) * 8);
+  rg::launch_pdl((extract_last_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const float4*>(h), B, static_cast<int>(L), vec, reinterpret_cast<float4*>(out_f32),
+                 static_cast<uint2*>(out_bf16));
+  RG_CHECK_LAUNCH("extract_last");
   return RECGURU_OK;
 }

@@ -36,12 +36,19 @@ def _unwrap(model):
     return model.module if hasattr(model, "module") else model
 
 
+def _last_position(h: Tensor) -> Tensor:
+    """``h[:, -1, :]`` -- one small kernel (recguru_extract_last) on the GPU, a view elsewhere."""
+    if h.is_cuda and h.dtype == torch.float32 and h.dim() == 3 and not h.requires_grad:
+        return ops.raw_extract_last(h)[0]
+    return h[:, -1, :]
+
+
 def reference_user_rep(model, sas: bool) -> Callable[[Tensor, Tensor], Tensor]:
     """``u = get_embedding*(...)[:, -1, :]`` exactly as ``get_scores`` takes it (train_auto.py:164-194)."""
     m = _unwrap(model)
     if sas:
-        return lambda enc_in, dec_in: m.get_embedding_sas(dec_in)[:, -1, :]
-    return lambda enc_in, dec_in: m.get_embedding(enc_in, dec_in)[:, -1, :]
+        return lambda enc_in, dec_in: _last_position(m.get_embedding_sas(dec_in))
+    return lambda enc_in, dec_in: _last_position(m.get_embedding(enc_in, dec_in))
 
 
 def reference_item_table(model, sas: bool) -> Tensor:

@@ -74,14 +74,29 @@ class FusedItemEmbedding(nn.Module):
         return torch.ops.recguru.gather_rows(self.weight, ids, pad)
 
     def lookup_pe_mask(self, ids: Tensor, pos_emb: "FusedPositionalEncoding",
-                       pad_index: Optional[int] = 0, mask: Optional[Tensor] = None):
+                       pad_index: Optional[int] = 0, mask: Optional[Tensor] = None,
+                       fused_dropout: Optional[bool] = None):
         """Fused ``pos_emb(src_emb(ids), mask)`` (K1).  With ``mask=None`` the 0/1 mask is derived
-        from ``ids != pad_index`` inside the kernel and returned: ``(out, mask)``."""
+        from ``ids != pad_index`` inside the kernel and returned: ``(out, mask)``.
+
+        In training mode the module's ``nn.Dropout`` is fused into the same kernel
+        (``fused_dropout``, default on): it draws from torch's CUDA generator exactly like
+        ``nn.Dropout`` would -- same kept elements, same generator offset afterwards."""
         self._register()
+        table = pos_emb.table(ids.shape[-1])
+        p = float(pos_emb.dropout.p)
+        if fused_dropout is None:
+            fused_dropout = pos_emb.fused_dropout
+        if fused_dropout and pos_emb.training and 0.0 < p < 1.0 and type(self.weight.data) is Tensor \
+                and self.weight.is_cuda and not torch.cuda.is_current_stream_capturing():
+            seed, off, threads = ops.torch_dropout_state(ids.numel() * self.embedding_dim, self.weight.device)
+            out, m = torch.ops.recguru.gather_pe_mask_dropout(self.weight, ids, table, mask, int(pad_index), p,
+                                                              seed, off, threads)
+            return out, m
         if mask is None:
-            out, m = torch.ops.recguru.gather_pe_mask(self.weight, ids, pos_emb.pe, int(pad_index))
+            out, m = torch.ops.recguru.gather_pe_mask(self.weight, ids, table, int(pad_index))
         else:
-            out = torch.ops.recguru.gather_pe_mask_m(self.weight, ids, pos_emb.pe, mask)
+            out = torch.ops.recguru.gather_pe_mask_m(self.weight, ids, table, mask)
             m = mask
         return pos_emb.dropout(out), m
 
@@ -94,10 +109,15 @@ class FusedPositionalEncoding(nn.Module):
     ``forward(x, mask) = dropout((x + pe[:, :L]) * mask[..., None])``.  The add+mask runs in one
     kernel; dropout stays with torch so the RNG stream matches the reference."""
 
-    def __init__(self, d_model: int, dropout: float, max_len: int = 5000):
+    def __init__(self, d_model: int, dropout: float, max_len: int = 5000, fused_dropout: bool = True):
         super().__init__()
         self.dropout = nn.Dropout(p=dropout)
+        self.fused_dropout = fused_dropout
         self.register_buffer("pe", sinusoid_table(max_len, d_model))
+
+    def table(self, L: int) -> Tensor:
+        """The [>=L, d] position table the kernels add (fixed sinusoid buffer)."""
+        return self.pe
 
     @classmethod
     def from_module(cls, mod: nn.Module) -> "FusedPositionalEncoding":
@@ -107,7 +127,39 @@ class FusedPositionalEncoding(nn.Module):
         return m
 
     def forward(self, x: Tensor, mask: Tensor) -> Tensor:
-        return self.dropout(torch.ops.recguru.pe_mask(x, self.pe, mask))
+        y = torch.ops.recguru.pe_mask(x, self.table(x.shape[-2]), mask)
+        p = float(self.dropout.p)
+        if self.fused_dropout and self.training and 0.0 < p < 1.0 and x.is_cuda and x.shape[-1] % 4 == 0 \
+                and type(x.data) is Tensor and not torch.cuda.is_current_stream_capturing():
+            # same kept elements and same generator consumption as self.dropout(y), without the byte mask
+            seed, off, threads = ops.torch_dropout_state(y.numel(), y.device)
+            return torch.ops.recguru.dropout(y, None, p, seed, off, threads)
+        return self.dropout(y)
+
+
+class FusedPositionalEncodingM(FusedPositionalEncoding):
+    """``PositionalEncodingM(d_model, dropout, max_len, device)`` (Transformer/transformer.py:327-342):
+    LEARNED positions -- ``forward(x, mask) = dropout((x + pos_emb(arange(L))) * mask[..., None])``.
+    Same kernels as the sinusoid module (they add any ``[L, d]`` table); the table's gradient
+    ``dP[l] = sum_b mask[b,l] * g[b,l]`` comes from ``recguru_pe_grad`` (fixed summation order).
+    ``pos_emb`` keeps its name, so ``state_dict()`` keys match the reference (``pos_emb.weight``)."""
+
+    def __init__(self, d_model: int, dropout: float, max_len: int = 5000, device=None, fused_dropout: bool = True):
+        nn.Module.__init__(self)
+        self.dropout = nn.Dropout(p=dropout)
+        self.fused_dropout = fused_dropout
+        self.device = device
+        self.pos_emb = nn.Embedding(max_len, d_model)
+
+    @classmethod
+    def from_module(cls, mod: nn.Module) -> "FusedPositionalEncodingM":
+        w = mod.pos_emb.weight
+        m = cls(w.shape[1], mod.dropout.p, max_len=w.shape[0], device=getattr(mod, "device", None))
+        m.pos_emb.weight = w                          # shares the Parameter
+        return m
+
+    def table(self, L: int) -> Tensor:
+        return self.pos_emb.weight[:L]
 
 
 class _FusedLogitLoss(nn.Module):

@@ -86,6 +86,100 @@ def raw_gather_pe_mask(weight: Tensor, ids: Tensor, pe: Optional[Tensor], pad_in
     return out, mask_out
 
 
+def torch_dropout_state(numel: int, device) -> Tuple[int, int, int]:
+    """Consume torch's CUDA generator exactly as ``torch.nn.functional.dropout`` would for a fp32
+    tensor of ``numel`` elements (ATen/native/cuda/Dropout.cu: dropout_cuda): returns
+    ``(seed, philox_offset, torch_threads)`` and advances the generator's offset by
+    ``((numel - 1) // (torch_threads * 4) + 1) * 4``.  Host-side bookkeeping: not for use inside a
+    CUDA-graph capture."""
+    torch.cuda.init()                                   # default_generators is empty before the lazy init
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    prop = torch.cuda.get_device_properties(idx)
+    block = 256
+    grid = min(prop.multi_processor_count * (prop.max_threads_per_multi_processor // block), (numel + block - 1) // block)
+    threads = grid * block
+    inc = ((numel - 1) // (threads * 4) + 1) * 4
+    gen = torch.cuda.default_generators[idx]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(off + inc)
+    return int(seed), int(off), int(threads)
+
+
+def raw_gather_pe_mask_dropout(weight: Tensor, ids: Tensor, pe: Tensor, pad_index: int, p: float, seed: int,
+                               offset: int, threads: int, mask_in: Optional[Tensor] = None,
+                               out: Optional[Tensor] = None, mask_out: Optional[Tensor] = None
+                               ) -> Tuple[Tensor, Optional[Tensor]]:
+    """K1 with the nn.Dropout of PositionalEncoding.forward fused in (Transformer/transformer.py:104-106):
+    ``dropout((weight[ids] + pe) * mask, p)``, bit-identical to torch's dropout kernel for the generator
+    state ``(seed, offset)`` (see :func:`torch_dropout_state`)."""
+    lib = _lib.load()
+    weight = _need(weight, torch.float32, "weight")
+    ids = _need(ids, torch.int64, "ids")
+    pe = _need(pe, torch.float32, "pe")
+    if pe.dim() == 3:
+        pe = pe[0]
+    V1, d = weight.shape
+    L = ids.shape[-1]
+    if pe.shape[0] < L or pe.shape[1] != d:
+        raise RuntimeError(f"recguru: pe shape {tuple(pe.shape)} incompatible with L={L}, d={d}")
+    if mask_in is not None:
+        mask_in = _need(mask_in, torch.float32, "mask")
+    if out is None:
+        out = torch.empty(*ids.shape, d, dtype=torch.float32, device=weight.device)
+    if mask_out is None and mask_in is None:
+        mask_out = torch.empty(ids.shape, dtype=torch.float32, device=weight.device)
+    check(lib.recguru_gather_pe_mask_dropout(_ptr(weight), V1, d, _ptr(ids), ids.numel(), max(L, 1), _ptr(pe),
+                                             _ptr(mask_in), int(pad_index), float(p), int(seed), int(offset),
+                                             int(threads), _ptr(out), _ptr(mask_out), _stream()),
+          "gather_pe_mask_dropout")
+    return out, mask_out
+
+
+def raw_dropout(x: Tensor, p: float, seed: int, offset: int, threads: int, row_mask: Optional[Tensor] = None,
+                out: Optional[Tensor] = None) -> Tensor:
+    """``torch.nn.functional.dropout(x, p, True)`` for the generator state ``(seed, offset)``, bit-identical
+    to torch's kernel; rows with ``row_mask == 0`` pass through.  Its own backward (same state)."""
+    x = _need(x, torch.float32, "x")
+    d = x.shape[-1]
+    n_rows = x.numel() // d
+    if row_mask is not None:
+        row_mask = _need(row_mask, torch.float32, "row_mask")
+        if row_mask.numel() != n_rows:
+            raise RuntimeError("recguru: row_mask must have one entry per row of x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().recguru_dropout(_ptr(x), _ptr(row_mask), n_rows, d, float(p), int(seed), int(offset),
+                                      int(threads), _ptr(out), _stream()), "dropout")
+    return out
+
+
+def raw_pe_grad(g: Tensor, mask: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """dP[l,:] = sum_b mask[b,l] * g[b,l,:]: gradient of a learned position table (P1')."""
+    g = _need(g, torch.float32, "g")
+    mask = _need(mask, torch.float32, "mask")
+    B, L, d = g.shape
+    if mask.numel() != B * L:
+        raise RuntimeError("recguru: mask must be [B, L]")
+    if out is None:
+        out = torch.empty(L, d, dtype=torch.float32, device=g.device)
+        accumulate = False
+    check(_lib.load().recguru_pe_grad(_ptr(g), _ptr(mask), B, L, d, 1 if accumulate else 0, _ptr(out), _stream()),
+          "pe_grad")
+    return out
+
+
+def raw_extract_last(h: Tensor, want_f32: bool = True, want_bf16: bool = False):
+    """u = h[:, -1, :] (dec_embedding[:, -1, :], train_auto.py:178; get_user_embed, gan_training.py:152-162)
+    as fp32 and/or bf16 (the catalog sweep's operand) in one pass.  Returns (u_f32 | None, u_bf16 | None)."""
+    h = _need(h, torch.float32, "h")
+    B, L, d = h.shape
+    u32 = torch.empty(B, d, dtype=torch.float32, device=h.device) if want_f32 else None
+    u16 = torch.empty(B, d, dtype=torch.bfloat16, device=h.device) if want_bf16 else None
+    check(_lib.load().recguru_extract_last(_ptr(h), B, L, d, _ptr(u32), _ptr(u16), _stream()), "extract_last")
+    return u32, u16
+
+
 def raw_pe_mask(x: Tensor, pe: Tensor, mask: Tensor, out: Optional[Tensor] = None) -> Tensor:
     """PositionalEncoding.forward before dropout (Transformer/transformer.py:104-106)."""
     lib = _lib.load()
@@ -623,6 +717,11 @@ _lib_def.define("gather_pe_mask(Tensor weight, Tensor ids, Tensor pe, int pad_in
 _lib_def.define("gather_pe_mask_m(Tensor weight, Tensor ids, Tensor pe, Tensor mask) -> Tensor")
 _lib_def.define("gather_rows(Tensor weight, Tensor ids, int padding_idx) -> Tensor")
 _lib_def.define("pe_mask(Tensor x, Tensor pe, Tensor mask) -> Tensor")
+_lib_def.define("gather_pe_mask_dropout(Tensor weight, Tensor ids, Tensor pe, Tensor? mask, int pad_index, float p,"
+                " int seed, int offset, int threads) -> (Tensor, Tensor)")
+_lib_def.define("dropout(Tensor x, Tensor? row_mask, float p, int seed, int offset, int threads) -> Tensor")
+_lib_def.define("pe_grad(Tensor g, Tensor mask) -> Tensor")
+_lib_def.define("extract_last(Tensor h) -> Tensor")
 _lib_def.define("embedding_bwd(Tensor grad, Tensor ids, Tensor? coef, int V1, int padding_idx) -> Tensor")
 _lib_def.define("sort_ids(Tensor ids, int V1) -> (Tensor, Tensor)")
 _lib_def.define("sampled_scores(Tensor h, Tensor weight, Tensor pos, Tensor neg, int padding_idx) -> (Tensor, Tensor)")
@@ -667,6 +766,27 @@ def _gather_rows(weight, ids, padding_idx):
 @_impl("pe_mask")
 def _pe_mask(x, pe, mask):
     return raw_pe_mask(x, pe, mask)
+
+
+@_impl("gather_pe_mask_dropout")
+def _gather_pe_mask_dropout(weight, ids, pe, mask, pad_index, p, seed, offset, threads):
+    out, m = raw_gather_pe_mask_dropout(weight, ids, pe, pad_index, p, seed, offset, threads, mask_in=mask)
+    return out, (mask if mask is not None else m)
+
+
+@_impl("dropout")
+def _dropout(x, row_mask, p, seed, offset, threads):
+    return raw_dropout(x, p, seed, offset, threads, row_mask=row_mask)
+
+
+@_impl("pe_grad")
+def _pe_grad(g, mask):
+    return raw_pe_grad(g, mask)
+
+
+@_impl("extract_last")
+def _extract_last(h):
+    return raw_extract_last(h)[0]
 
 
 @_impl("embedding_bwd")
@@ -764,6 +884,26 @@ def _(weight, ids, padding_idx):
 @_fake("pe_mask")
 def _(x, pe, mask):
     return torch.empty_like(x)
+
+
+@_fake("gather_pe_mask_dropout")
+def _(weight, ids, pe, mask, pad_index, p, seed, offset, threads):
+    return weight.new_empty(*ids.shape, weight.shape[1]), weight.new_empty(ids.shape)
+
+
+@_fake("dropout")
+def _(x, row_mask, p, seed, offset, threads):
+    return torch.empty_like(x)
+
+
+@_fake("pe_grad")
+def _(g, mask):
+    return g.new_empty(g.shape[-2], g.shape[-1])
+
+
+@_fake("extract_last")
+def _(h):
+    return h.new_empty(h.shape[0], h.shape[-1])
 
 
 @_fake("embedding_bwd")
@@ -899,18 +1039,40 @@ def _setup_gather_pe_mask(ctx, inputs, output):
     ctx.mark_non_differentiable(mask)   # a 0/1 function of the ids: keep it out of the graph
     ctx.V1 = weight.shape[0]
     ctx.wref = weight.detach()          # same storage, no graph: identifies the table in backward
+    ctx.pe_needs_grad = pe.requires_grad   # learned positions (PositionalEncodingM, transformer.py:327-342)
+    ctx.pe_shape = tuple(pe.shape)
+
+
+def _fit_pe_grad(d_pe: Tensor, pe_shape) -> Tensor:
+    """[L, d] gradient -> the shape of the position table the op was given ([>=L, d] or [1, >=L, d])."""
+    L, d = d_pe.shape
+    rows = pe_shape[-2]
+    if rows != L:
+        full = d_pe.new_zeros(rows, d)
+        full[:L] = d_pe
+        d_pe = full
+    return d_pe.reshape(pe_shape)
+
+
+def _pe_grad_of(ctx, g_out, ids, mask):
+    if not ctx.pe_needs_grad:
+        return None
+    L, d = ids.shape[-1], g_out.shape[-1]
+    return _fit_pe_grad(torch.ops.recguru.pe_grad(g_out.reshape(-1, L, d).contiguous(), mask.reshape(-1, L)),
+                        ctx.pe_shape)
 
 
 def _bwd_gather_pe_mask(ctx, g_out, g_mask):
     ids, mask = ctx.saved_tensors
     d = g_out.shape[-1]
+    d_pe = _pe_grad_of(ctx, g_out, ids, mask)
     if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g_out.reshape(-1, d), coef=mask.reshape(-1))]):
-        return None, None, None, None
+        return None, None, d_pe, None
     # d out / d W[id] = mask ; pad rows get coef 0 (== the reference: x*mask kills their grad,
     # and nn.Embedding(padding_idx) would skip them anyway)
     dW = torch.ops.recguru.embedding_bwd(g_out.reshape(-1, d), ids.reshape(-1), mask.reshape(-1),
                                          ctx.V1, -1)
-    return dW, None, None, None
+    return dW, None, d_pe, None
 
 
 torch.library.register_autograd("recguru::gather_pe_mask", _bwd_gather_pe_mask,
@@ -922,30 +1084,103 @@ def _setup_gather_pe_mask_m(ctx, inputs, output):
     ctx.save_for_backward(ids, mask)
     ctx.V1 = weight.shape[0]
     ctx.wref = weight.detach()
+    ctx.pe_needs_grad = pe.requires_grad
+    ctx.pe_shape = tuple(pe.shape)
 
 
 def _bwd_gather_pe_mask_m(ctx, g_out):
     ids, mask = ctx.saved_tensors
     d = g_out.shape[-1]
+    d_pe = _pe_grad_of(ctx, g_out, ids, mask)
     if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g_out.reshape(-1, d), coef=mask.reshape(-1))]):
-        return None, None, None, None
+        return None, None, d_pe, None
     dW = torch.ops.recguru.embedding_bwd(g_out.reshape(-1, d), ids.reshape(-1), mask.reshape(-1),
                                          ctx.V1, -1)
-    return dW, None, None, None
+    return dW, None, d_pe, None
 
 
 torch.library.register_autograd("recguru::gather_pe_mask_m", _bwd_gather_pe_mask_m,
                                 setup_context=_setup_gather_pe_mask_m)
 
 
+def _setup_gather_pe_mask_dropout(ctx, inputs, output):
+    weight, ids, pe, mask_in, pad_index, p, seed, offset, threads = inputs
+    _, mask = output
+    ctx.save_for_backward(ids, mask)
+    ctx.mark_non_differentiable(mask)
+    ctx.V1 = weight.shape[0]
+    ctx.wref = weight.detach()
+    ctx.drop = (p, seed, offset, threads)
+    ctx.pe_needs_grad = pe.requires_grad
+    ctx.pe_shape = tuple(pe.shape)
+
+
+def _bwd_gather_pe_mask_dropout(ctx, g_out, g_mask):
+    ids, mask = ctx.saved_tensors
+    d = g_out.shape[-1]
+    # through the dropout first (same Philox state => same keep pattern), then as gather_pe_mask
+    p, seed, offset, threads = ctx.drop
+    g = g_out.contiguous()
+    if p > 0:
+        g = torch.ops.recguru.dropout(g, mask, p, seed, offset, threads)
+    d_pe = _pe_grad_of(ctx, g, ids, mask)
+    if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g.reshape(-1, d), coef=mask.reshape(-1))]):
+        dW = None
+    else:
+        dW = torch.ops.recguru.embedding_bwd(g.reshape(-1, d), ids.reshape(-1), mask.reshape(-1), ctx.V1, -1)
+    return dW, None, d_pe, None, None, None, None, None, None
+
+
+torch.library.register_autograd("recguru::gather_pe_mask_dropout", _bwd_gather_pe_mask_dropout,
+                                setup_context=_setup_gather_pe_mask_dropout)
+
+
+def _setup_dropout(ctx, inputs, output):
+    x, row_mask, p, seed, offset, threads = inputs
+    if row_mask is not None:
+        ctx.save_for_backward(row_mask)
+    ctx.has_mask = row_mask is not None
+    ctx.drop = (p, seed, offset, threads)
+
+
+def _bwd_dropout(ctx, g):
+    row_mask = ctx.saved_tensors[0] if ctx.has_mask else None
+    p, seed, offset, threads = ctx.drop
+    return torch.ops.recguru.dropout(g.contiguous(), row_mask, p, seed, offset, threads), None, None, None, None, None
+
+
+torch.library.register_autograd("recguru::dropout", _bwd_dropout, setup_context=_setup_dropout)
+
+
+def _setup_extract_last(ctx, inputs, output):
+    (h,) = inputs
+    ctx.shape = h.shape
+
+
+def _bwd_extract_last(ctx, g):
+    dh = g.new_zeros(ctx.shape)
+    dh[:, -1, :] = g
+    return dh
+
+
+torch.library.register_autograd("recguru::extract_last", _bwd_extract_last, setup_context=_setup_extract_last)
+
+
 def _setup_pe_mask(ctx, inputs, output):
-    _, _, mask = inputs
+    _, pe, mask = inputs
     ctx.save_for_backward(mask)
+    ctx.pe_needs_grad = pe.requires_grad
+    ctx.pe_shape = tuple(pe.shape)
 
 
 def _bwd_pe_mask(ctx, g):
     (mask,) = ctx.saved_tensors
-    return g * mask.reshape(*g.shape[:-1], 1), None, None
+    d_pe = None
+    if ctx.pe_needs_grad:
+        L, d = g.shape[-2], g.shape[-1]
+        d_pe = _fit_pe_grad(torch.ops.recguru.pe_grad(g.reshape(-1, L, d).contiguous(), mask.reshape(-1, L)),
+                            ctx.pe_shape)
+    return g * mask.reshape(*g.shape[:-1], 1), d_pe, None
 
 
 torch.library.register_autograd("recguru::pe_mask", _bwd_pe_mask, setup_context=_setup_pe_mask)
