@@ -375,6 +375,71 @@ def bench_train(D: Dist, args, peaks):
                     "with the kernels serialised on one stream; whole_step = all algorithmic bytes of a step "
                     "over the timed step"}
 
+    # ---- the same step on a NON-padded batch: every position live, so nothing is
+    # skipped or compacted away -- the seqs/s figure that does not depend on the batch's sparsity, and
+    # the table backward (K2) against the HBM roofline where it actually moves its bytes
+    gd = torch.Generator().manual_seed(4321)
+    dense_tb = batches[0]["tb"]
+    dense = dict(dec_in=torch.randint(1, cfg["n_items"] + 1, (cfg["B"], cfg["L"]), generator=gd).to(dev),
+                 dec_out=torch.randint(1, cfg["n_items"] + 1, (cfg["B"], cfg["L"]), generator=gd).to(dev),
+                 n_items=dense_tb.n_items, h=batches[0]["h"], g=batches[0]["g"])
+    if args.no_graph:
+        def dense_fn(i):
+            hp.step(dense["dec_in"], dense["dec_out"], dense["n_items"], dense["h"], dense["g"])
+    else:
+        dense_graph = hp.capture_step(dense["dec_in"], dense["dec_out"], dense["n_items"], dense["h"], dense["g"])
+
+        def dense_fn(i):
+            dense_graph.replay()
+    ms_dense = timed_loop(D, dense_fn, K, Wm) / K
+    dm = torch.ones(n, device=dev)
+    d_sites_plan = [ops.Site(dense["dec_in"], None, live=dm), ops.Site(dense["dec_out"], None, live=dm),
+                    ops.Site(dense["n_items"], None, group=cfg["K"], live=dm)]
+    d_sites = [ops.Site(dense["dec_in"], dense["g"].view(n, cfg["d"]), coef=dm, live=dm),
+               ops.Site(dense["dec_out"], dense["h"].view(n, cfg["d"]), coef=hp.sbuf["dp"], scale=hp.one,
+                        scale2=hp.sbuf["aux"][1:2], live=dm),
+               ops.Site(dense["n_items"], dense["h"].view(n, cfg["d"]), coef=hp.sbuf["dn"].view(-1), scale=hp.one,
+                        scale2=hp.sbuf["aux"][1:2], group=cfg["K"], live=dm)]
+    ms_dplan = timed_loop(D, lambda i: ops.raw_embedding_bwd_plan(d_sites_plan, hp.V1, 0, hp.ws_bwd), max(K, 10), Wm) / max(K, 10)
+    ms_dapply = timed_loop(D, lambda i: ops.raw_embedding_bwd_apply(d_sites, hp.V1, hp.d, hp.dW, hp.ws_bwd,
+                                                                    mode=ops.DW_PREZEROED), max(K, 10), Wm) / max(K, 10)
+    d_live_ids = torch.cat([dense["dec_in"].view(-1), dense["dec_out"].view(-1), dense["n_items"].view(-1)])
+    d_distinct = int(torch.unique(d_live_ids).numel())
+    ab_dense = hp.algorithmic_bytes(d_distinct, None, None)
+    k2_mb = (ab_dense["embedding_bwd_plan"] - 4 * hp.V1 * hp.d + ab_dense["embedding_bwd_apply"]) / 1e6
+    dense_batch = {
+        "ms_per_step": ms_dense, "value": cfg["B"] * D.world / (ms_dense * 1e-3), "unit": "seqs/s",
+        "algorithmic_mb": round(ab_dense["total"] / 1e6, 1),
+        "frac_of_hbm_peak": round(ab_dense["total"] / 1e6 / ms_dense / peaks["hbm"], 3),
+        "k2_table_backward": {"plan_ms": round(ms_dplan, 4), "apply_ms": round(ms_dapply, 4),
+                              "gathered_indices": int(d_live_ids.numel()), "distinct_rows": d_distinct,
+                              "algorithmic_mb": round(k2_mb, 1),
+                              "frac_of_hbm_peak": round(k2_mb / (ms_dplan + ms_dapply) / peaks["hbm"], 3),
+                              "note": "plan + apply launched back to back on one stream (no overlap), "
+                                      "zero fill of dW not included in either the bytes or the time"},
+        "note": "no pad positions: all 1.43 M gathered indices carry gradient (uniform ids)"}
+    del dm, d_sites, d_sites_plan
+
+    # ---- fused dropout: K1 with torch-compatible Philox dropout vs K1 + torch's dropout
+    b0 = batches[0]["tb"]
+    xd = torch.empty(cfg["B"], cfg["L"], cfg["d"], device=dev)
+
+    def k1_fused(i):
+        seed, off, thr = ops.torch_dropout_state(xd.numel(), dev)
+        ops.raw_gather_pe_mask_dropout(hp.weight, b0.dec_in, hp.pe, hp.pad_index, 0.5, seed, off, thr, out=xd,
+                                       mask_out=hp._main_masks[0])
+
+    def k1_then_torch(i):
+        ops.raw_gather_pe_mask(hp.weight, b0.dec_in, hp.pe, hp.pad_index, out=xd, mask_out=hp._main_masks[0])
+        torch.nn.functional.dropout(xd, 0.5, True)
+    nd = max(K, 20)
+    ms_k1f = timed_loop(D, k1_fused, nd, Wm) / nd
+    ms_k1t = timed_loop(D, k1_then_torch, nd, Wm) / nd
+    fused_dropout = {"k1_with_fused_dropout_ms": round(ms_k1f, 4), "k1_then_torch_dropout_ms": round(ms_k1t, 4),
+                     "note": "p = 0.5 (config_auto4rec.py:225); same kept elements and generator offsets as nn.Dropout "
+                             "(tests/test_gpu_dropout.py); padded cfg2 batch; not part of the timed step"}
+    del xd
+
     # ---- the drop-in surface: what the reference's UNCHANGED call sites execute --
     # FusedItemEmbedding.lookup_pe_mask + sampled_loss_fused + loss.backward() through
     # torch.ops.recguru.* and torch autograd, eager launches; the table gradient of all lookup sites is
@@ -395,13 +460,45 @@ def bench_train(D: Dist, args, peaks):
             loss_, _, _ = sampled_loss_fused(h_, emb, b["tb"].dec_out, b["tb"].n_items, m_.view(-1), cfg["kind"])
             torch.autograd.backward([loss_, x_], [None, b["g"]])
         ms_d = timed_loop(D, dropin_step, K, Wm) / K
-        dropin["one_pass_backward" if one_pass else "per_site_dense_gradients"] = {
-            "ms_per_step": round(ms_d, 4), "seqs_per_s": round(cfg["B"] * D.world / (ms_d * 1e-3))}
+        rec = {"ms_per_step": round(ms_d, 4), "seqs_per_s": round(cfg["B"] * D.world / (ms_d * 1e-3))}
+        if one_pass and not args.no_graph:
+            # the same forward + backward() captured as ONE CUDA graph (autograd inside the capture): what
+            # the drop-in path costs on the device once the Python / dispatcher / autograd-engine time of
+            # the eager loop (several hundred us per step on this host) is out of the picture
+            try:
+                warm = torch.cuda.Stream()
+                warm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(warm):
+                    for w_ in range(3):
+                        dropin_step(w_)
+                torch.cuda.current_stream().wait_stream(warm)
+                dgs = []
+                for bi in range(n_batches):
+                    gph = torch.cuda.CUDAGraph()
+                    emb.weight.grad = None
+                    hs[bi].grad = None
+                    with torch.cuda.graph(gph):
+                        b = batches[bi]
+                        x_, m_ = emb.lookup_pe_mask(b["tb"].dec_in, posm, pad_index=0)
+                        loss_, _, _ = sampled_loss_fused(hs[bi], emb, b["tb"].dec_out, b["tb"].n_items, m_.view(-1),
+                                                         cfg["kind"])
+                        torch.autograd.backward([loss_, x_], [None, b["g"]])
+                    dgs.append(gph)
+                ms_g = timed_loop(D, lambda i: dgs[i % n_batches].replay(), K, Wm) / K
+                rec["cuda_graph_ms_per_step"] = round(ms_g, 4)
+                rec["cuda_graph_seqs_per_s"] = round(cfg["B"] * D.world / (ms_g * 1e-3))
+                del dgs
+            except Exception as e:  # noqa: BLE001  (a capture that torch refuses must not kill the bench line)
+                rec["cuda_graph_error"] = repr(e)[:200]
+                torch.cuda.synchronize()
+        dropin["one_pass_backward" if one_pass else "per_site_dense_gradients"] = rec
         del emb, posm, hs
     dropin["ratio_vs_hotpath_eager"] = round(dropin["one_pass_backward"]["ms_per_step"] / (ms_eager / K), 3)
+    if "cuda_graph_ms_per_step" in dropin["one_pass_backward"]:
+        dropin["ratio_graph_vs_hotpath_graph"] = round(dropin["one_pass_backward"]["cuda_graph_ms_per_step"] / (ms / K), 3)
     dropin["note"] = ("eager launches through torch.ops.recguru.* + autograd (no CUDA graph, no side-stream plan, "
-                      "allocations by torch's caching allocator); dense scoring kernel (every position scored, "
-                      "the logits are returned to the caller as MyRec.forward does)")
+                      "allocations by torch's caching allocator); padding-aware scoring kernel; all lookup sites of "
+                      "the step reduced in one row-compacted K2 pass when backward() ends")
 
     # ---- next row: the optimizer step of the table, timed on its own (NOT part of
     # the step above: north_star stops at the dense gradient)
@@ -652,7 +749,7 @@ def bench_train(D: Dist, args, peaks):
         "gpu_launches": int(launches), "clocks": cs.summary(), "loss": float(loss_host.item()),
         "launch_mode": "eager" if args.no_graph else "cuda_graph (one graph per rotating batch)",
         "table_adam": table_adam, "e2e_device_negatives": e2e_sampler, "e2e_device_batches": e2e_builder,
-        "dropin_surface": dropin,
+        "dropin_surface": dropin, "dense_batch": dense_batch, "fused_dropout": fused_dropout,
         "ms_per_step_eager": ms_eager / K, "ms_per_step_serialised_stages": ms_serial / K,
         "algorithmic_mb_per_step": round(abytes["total"] / 1e6, 1),
         "table_backward": {"gathered_indices": cfg["B"] * cfg["L"] * (2 + cfg["K"]), "live_indices": live,
@@ -1210,6 +1307,7 @@ def main():
                     "ms_per_step_eager": train["ms_per_step_eager"],
                     "ms_per_step_serialised_stages": train["ms_per_step_serialised_stages"],
                     "sustained": train["sustained"], "dropin_surface": train["dropin_surface"],
+                    "dense_batch": train["dense_batch"], "fused_dropout": train["fused_dropout"],
                     "table_adam": train["table_adam"], "e2e_device_negatives": train["e2e_device_negatives"],
                     "e2e_device_batches": train["e2e_device_batches"]}
             if gather is not None:

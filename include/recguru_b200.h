@@ -277,6 +277,24 @@ int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, const void* ite
                               const float* target_score, int64_t k, float* topk_val,
                               int64_t* topk_id, int64_t* rank_count, void* workspace,
                               int64_t workspace_bytes, recguru_stream_t stream);
+/* recguru_catalog_topk_rank with an explicit rule for items whose score EQUALS the target's
+ * (a collapsed model or low-precision scores make exact ties common, and the reference's
+ * argsort leaves their order unspecified):
+ *   RECGURU_TIE_LOWER_ID     rank = #{s > t} + #{j < target : s_j == t}   (stable descending sort; default)
+ *   RECGURU_TIE_TARGET_FIRST rank = #{s > t}            -- the target wins every tie (what the reference's
+ *                                                          target-in-column-0 layout yields on CPU)
+ *   RECGURU_TIE_TARGET_LAST  rank = #{s >= t} - 1       -- the pessimistic rank
+ * TARGET_LAST - TARGET_FIRST = the number of items tied with the target (degenerate-evaluation check).
+ * The top-k lists do not depend on the mode.  k <= 16. */
+#define RECGURU_TIE_LOWER_ID 0
+#define RECGURU_TIE_TARGET_FIRST 1
+#define RECGURU_TIE_TARGET_LAST 2
+int recguru_catalog_topk_rank_ties(const void* users_bf16, int64_t U, const void* items_bf16,
+                                   int64_t id_lo, int64_t n_items, int64_t d, const int64_t* target,
+                                   const float* target_score, int64_t k, int tie_mode, float* topk_val,
+                                   int64_t* topk_id, int64_t* rank_count, void* workspace,
+                                   int64_t workspace_bytes, recguru_stream_t stream);
+
 /* Debug/parity only: dense scores [U, n_items] fp32 through the same tcgen05 path. */
 int recguru_catalog_scores_dense(const void* users_bf16, int64_t U, const void* items_bf16,
                                  int64_t n_items, int64_t d, float* scores,

@@ -256,3 +256,23 @@ def test_seq_gen(seq, length_enc, len_dec, eos, val):
 
 
 test_seq_gen.__test__ = False  # not a pytest test
+
+
+def sampling_weights(seq, val, test, v_size, item_freq=None, exclude_val=False):
+    """The weight vector ``pickle_loader.__getitem__`` hands to ``torch.multinomial``
+    (data/data_loader.py:289-314), restated.  The loop ``for val in seq: weights[seq] = 0`` rebinds
+    ``val`` to ``seq[-1]`` (:291-292,:303-304), so the following ``weights[val] = 0`` does NOT zero the
+    validation item; in the ``item_freq`` branch (:289-295) ``weights[0]`` keeps ``wf[0]**0.75 / sum``.
+    ``exclude_val=True`` is the repaired law (validation item excluded) that NegativeSampler defaults to."""
+    import numpy as np
+    seq = np.asarray(seq, dtype=np.int64)
+    if item_freq is not None:
+        w = np.power(np.asarray(item_freq, dtype=np.float64), 0.75)
+        w = (w / w.sum()).astype(np.float32).astype(np.float64)       # FT(wf): a float32 tensor (:252-254)
+    else:
+        w = np.ones(v_size, dtype=np.float64)
+        w[0] = 0
+    w[seq] = 0
+    w[seq[-1] if (len(seq) and not exclude_val) else val] = 0
+    w[test] = 0
+    return w

@@ -15,6 +15,7 @@ ABI_VERSION = 4
 MAX_SITES = 8
 LOSS_KINDS = {"bpr": 0, "bpr_sas": 1, "sce": 2}
 LOSS_SKIP_MASKED = 0x100
+TIE_MODES = {"id": 0, "target_first": 1, "target_last": 2}
 
 c_i64 = C.c_int64
 c_ptr = C.c_void_p
@@ -71,6 +72,8 @@ SIGNATURES = {
     "recguru_catalog_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "recguru_catalog_topk_rank": (C.c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr,
                                             c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "recguru_catalog_topk_rank_ties": (C.c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr,
+                                                 c_i64, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "recguru_catalog_scores_dense": (C.c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "recguru_topk_merge": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
                                      c_ptr]),

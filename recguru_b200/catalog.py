@@ -121,10 +121,21 @@ class CatalogEvaluator:
     """
 
     def __init__(self, weight: Tensor, k: int = 10, id_lo: int = 1, n_items: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None, sharded: Optional[bool] = None):
+                 group: Optional[dist.ProcessGroup] = None, sharded: Optional[bool] = None, tie: str = "id"):
         if n_items is None:
             n_items = weight.shape[0] - 2
         self.k = int(k)
+        # Tie rule for the target's rank (top-k lists are always score desc, id asc):
+        #   "id"           lower id first -- the stable descending sort (default; shard-count independent)
+        #   "target_first" rank = #{s > t}: the target wins every tie.  This is what the reference's own
+        #                  protocol yields on CPU (target in column 0 of a stable argsort, train_auto.py:234-237);
+        #                  on degenerate scores (collapsed / untrained model, bf16 ties) it is optimistic:
+        #                  an all-equal score row gives rank 0.
+        #   "target_last"  rank = #{s >= t} - 1: the pessimistic rank.
+        # :meth:`tie_bracket` returns both ends; their difference is the number of items tied with the target.
+        if tie not in ("id", "target_first", "target_last"):
+            raise ValueError(f"recguru: unknown tie rule {tie!r}")
+        self.tie = tie
         self.group = group
         self.world = dist.get_world_size(group) if (sharded or (sharded is None and group is not None)) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -151,7 +162,8 @@ class CatalogEvaluator:
         return ops.raw_catalog_target_scores(users_bf16, self.items, target, self.id_lo)
 
     def _local_topk_rank(self, users_bf16: Tensor, target: Tensor, tscore: Tensor):
-        return ops.raw_catalog_topk_rank(users_bf16, self.items, target, tscore, self.k, self.id_lo)
+        return ops.raw_catalog_topk_rank(users_bf16, self.items, target, tscore, self.k, self.id_lo,
+                                         tie=getattr(self, "tie", "id"))
 
     def _merge(self, vals: Tensor, ids: Tensor, counts: Tensor):
         return ops.raw_topk_merge(vals, ids, counts)
@@ -230,7 +242,22 @@ class CatalogEvaluator:
         return v[:U_loc], i[:U_loc], r[:U_loc]
 
     def _local_rank(self, users_bf16: Tensor, target: Tensor, tscore: Tensor) -> Tensor:
-        return ops.raw_catalog_topk_rank(users_bf16, self.items, target, tscore, 0, self.id_lo)[2]
+        return ops.raw_catalog_topk_rank(users_bf16, self.items, target, tscore, 0, self.id_lo,
+                                         tie=getattr(self, "tie", "id"))[2]
+
+    def tie_bracket(self, users: Tensor, target: Tensor, u_max: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+        """``(best, worst)`` rank of every target: ``best = #{s > t}`` (target wins all ties), ``worst =
+        #{s >= t} - 1``.  ``worst - best`` items tie with the target; a large value flags a degenerate
+        evaluation (collapsed model, bf16 score collisions) where HR/NDCG depend on the tie rule."""
+        keep = getattr(self, "tie", "id")
+        try:
+            self.tie = "target_first"
+            best = self.target_rank(users, target, u_max=u_max)
+            self.tie = "target_last"
+            worst = self.target_rank(users, target, u_max=u_max)
+        finally:
+            self.tie = keep
+        return best, worst
 
     def target_rank(self, users: Tensor, target: Tensor, u_max: Optional[int] = None) -> Tensor:
         """Target ranks only (what HR/NDCG/MRR need): the sweep runs in its rank-only mode -- no

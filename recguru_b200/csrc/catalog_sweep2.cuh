@@ -205,7 +205,13 @@ catalog_sweep2_kernel(const __grid_constant__ CUtensorMap map_users,
       if (t == 0.f) t = 0.f;                  // -0 -> +0 (the sign-bit count relies on it)
       tgt_local = p.target[u] - p.id_lo;
     }
+    // ties: an item that scores exactly t counts towards the rank iff ... its id is lower (default: the
+    // stable descending sort), never (RECGURU_TIE_TARGET_FIRST: the target wins every tie, what the
+    // reference's column-0 layout gives it), always (RECGURU_TIE_TARGET_LAST: the pessimistic rank).
+    // "counts" = compare >= t, done as > against the next float below t.
     const float t_below = next_below(t);
+    const float t_left = p.tie_mode == RECGURU_TIE_TARGET_FIRST ? t : t_below;    // items left of the target
+    const float t_right = p.tie_mode == RECGURU_TIE_TARGET_LAST ? t_below : t;    // items right of it
     int tgt_tile, tgt_col = -1;               // tile relative to this device's slice
     if (tgt_local < 0) tgt_tile = -1;
     else if (tgt_local >= p.n_items) tgt_tile = INT_MAX;
@@ -312,10 +318,10 @@ catalog_sweep2_kernel(const __grid_constant__ CUtensorMap map_users,
             const float v = __uint_as_float(w[c]);
             if (col < valid) {
               if (j == tgt_j) {
-                if (col < tgt_col) cnt += (v >= t) ? 1 : 0;
-                else if (col > tgt_col) cnt += (v > t) ? 1 : 0;
+                if (col < tgt_col) cnt += (v > t_left) ? 1 : 0;
+                else if (col > tgt_col) cnt += (v > t_right) ? 1 : 0;
               } else {
-                cnt += (v > (j < tgt_j ? t_below : t)) ? 1 : 0;
+                cnt += (v > (j < tgt_j ? t_left : t_right)) ? 1 : 0;
               }
             }
           }
@@ -334,7 +340,7 @@ catalog_sweep2_kernel(const __grid_constant__ CUtensorMap map_users,
 
       // fast tile: the accumulator row in BN/CH TMEM loads; after the last one the scores live in
       // registers only, so the accumulator goes back to the MMA warps before its arithmetic
-      const float tcmp = j < tgt_j ? t_below : t;
+      const float tcmp = j < tgt_j ? t_left : t_right;
       uint64_t tt;
       asm("mov.b64 %0, {%1, %1};" : "=l"(tt) : "f"(tcmp));
 #pragma unroll 1

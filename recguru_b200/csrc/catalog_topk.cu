@@ -84,6 +84,7 @@ struct CatalogParams {
   int64_t* out_cnt;      // [n_splits, U]
   float* dense;          // kModeDense: [U, n_items]
   const __nv_bfloat16* users;  // [U, d] (TS mode reads the user tile directly)
+  int tie_mode;          // RECGURU_TIE_*: how items that tie with the target count towards its rank
   uint32_t two;          // the constant 2, opaque to the compiler (keeps IMAD.HI on the FMA pipe)
   uint32_t debug_flags;  // bit 0: TMEM-load-only epilogue (timing floor experiments; wrong results)
 };
@@ -1161,13 +1162,15 @@ extern "C" int recguru_catalog_target_scores(const void* users_bf16, int64_t U,
   return RECGURU_OK;
 }
 
-extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, const void* items_bf16,
-                                         int64_t id_lo, int64_t n_items, int64_t d,
-                                         const int64_t* target, const float* target_score,
-                                         int64_t k, float* topk_val, int64_t* topk_id,
-                                         int64_t* rank_count, void* workspace,
-                                         int64_t workspace_bytes, recguru_stream_t stream) {
+static int catalog_topk_rank_impl(const void* users_bf16, int64_t U, const void* items_bf16,
+                                  int64_t id_lo, int64_t n_items, int64_t d,
+                                  const int64_t* target, const float* target_score,
+                                  int64_t k, int tie_mode, float* topk_val, int64_t* topk_id,
+                                  int64_t* rank_count, void* workspace,
+                                  int64_t workspace_bytes, recguru_stream_t stream) {
   using namespace rg;
+  RG_REQUIRE(tie_mode >= RECGURU_TIE_LOWER_ID && tie_mode <= RECGURU_TIE_TARGET_LAST, RECGURU_E_SHAPE,
+             "catalog_topk_rank: tie_mode=%d", tie_mode);
   int rc = check_catalog("catalog_topk_rank", users_bf16, U, items_bf16, n_items, d);
   if (rc) return rc;
   RG_REQUIRE(target && target_score && rank_count && (k == 0 || (topk_val && topk_id)), RECGURU_E_SHAPE,
@@ -1180,7 +1183,7 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CatalogParams p;
   p.U = U; p.n_items = n_items; p.id_lo = id_lo; p.target = target; p.tscore = target_score;
-  p.k = static_cast<int>(k); p.dense = nullptr; p.two = 2u;
+  p.k = static_cast<int>(k); p.dense = nullptr; p.two = 2u; p.tie_mode = tie_mode;
   p.users = static_cast<const __nv_bfloat16*>(users_bf16);
   const int bn = catalog_bn();
   p.n_splits = pick_splits(U, n_items, bn);
@@ -1199,6 +1202,8 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
   }
   // RECGURU_CATALOG_V=1: the round-1 kernel (A/B measurements); k > 16 (shared-memory lists) always uses it
   const bool v2 = k <= 16 && env_int("RECGURU_CATALOG_V", 2) != 1 && env_int("RECGURU_CATALOG_DEBUG", 0) == 0;
+  RG_REQUIRE(v2 || tie_mode == RECGURU_TIE_LOWER_ID, RECGURU_E_UNSUPPORTED,
+             "catalog_topk_rank: tie modes other than lower-id-first need k <= 16 (the round-2 sweep)");
   if (v2 && k == 0)
     rc = d == 64 ? launch_sweep2<64, kModeRank>(items_bf16, mu, p, st) : launch_sweep2<128, kModeRank>(items_bf16, mu, p, st);
   else if (v2)
@@ -1214,6 +1219,27 @@ extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, cons
   return RECGURU_OK;
 }
 
+extern "C" int recguru_catalog_topk_rank(const void* users_bf16, int64_t U, const void* items_bf16,
+                                         int64_t id_lo, int64_t n_items, int64_t d,
+                                         const int64_t* target, const float* target_score,
+                                         int64_t k, float* topk_val, int64_t* topk_id,
+                                         int64_t* rank_count, void* workspace,
+                                         int64_t workspace_bytes, recguru_stream_t stream) {
+  return catalog_topk_rank_impl(users_bf16, U, items_bf16, id_lo, n_items, d, target, target_score, k,
+                                RECGURU_TIE_LOWER_ID, topk_val, topk_id, rank_count, workspace, workspace_bytes,
+                                stream);
+}
+
+extern "C" int recguru_catalog_topk_rank_ties(const void* users_bf16, int64_t U, const void* items_bf16,
+                                              int64_t id_lo, int64_t n_items, int64_t d,
+                                              const int64_t* target, const float* target_score,
+                                              int64_t k, int tie_mode, float* topk_val, int64_t* topk_id,
+                                              int64_t* rank_count, void* workspace,
+                                              int64_t workspace_bytes, recguru_stream_t stream) {
+  return catalog_topk_rank_impl(users_bf16, U, items_bf16, id_lo, n_items, d, target, target_score, k, tie_mode,
+                                topk_val, topk_id, rank_count, workspace, workspace_bytes, stream);
+}
+
 extern "C" int recguru_catalog_scores_dense(const void* users_bf16, int64_t U,
                                             const void* items_bf16, int64_t n_items, int64_t d,
                                             float* scores, recguru_stream_t stream) {
@@ -1226,7 +1252,7 @@ extern "C" int recguru_catalog_scores_dense(const void* users_bf16, int64_t U,
   if (rc) return rc;
   CatalogParams p;
   memset(&p, 0, sizeof(p));
-  p.U = U; p.n_items = n_items; p.k = 1; p.dense = scores; p.two = 2u;
+  p.U = U; p.n_items = n_items; p.k = 1; p.dense = scores; p.two = 2u; p.tie_mode = 0;
   p.users = static_cast<const __nv_bfloat16*>(users_bf16);
   p.n_splits = pick_splits(U, n_items, 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

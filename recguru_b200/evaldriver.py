@@ -144,11 +144,21 @@ class EvalDriver:
 
 
 def evaluation(model_train, data_loader: Iterable, de, param_config=None, k_val: Optional[Sequence[int]] = None,
-               sas: bool = False, full_catalog: bool = False):
-    """Same call as the reference's ``evaluation`` (train_auto.py:202); see the module docstring."""
+               sas: bool = False, full_catalog: bool = False, tie: str = "id"):
+    """Same call as the reference's ``evaluation`` (train_auto.py:202); see the module docstring.
+
+    Protocol notes.  Default (``full_catalog=False``): the reference's own protocol -- the target against
+    the loader's sampled candidates, the target winning ties (its column-0 position under a stable
+    argsort; the reference's CUDA argsort leaves tie order unspecified).  ``full_catalog=True`` is a
+    DIFFERENT protocol and its numbers are not comparable with the reference's: every user is ranked
+    against all items, including the items of the user's own history, so ``result_freq`` and
+    ``result_rand`` (which differ only in how candidates were sampled) come out identical; ties are
+    resolved by ``tie`` ("id": lower id first, "target_first", "target_last" -- see
+    :class:`recguru_b200.catalog.CatalogEvaluator`; ``CatalogEvaluator.tie_bracket`` measures how many
+    items tie with each target, the check for a degenerate evaluation)."""
     model_train.eval()
     weight = reference_item_table(model_train, sas).detach()
-    ev = catalog.CatalogEvaluator(weight, k=10) if full_catalog else None
+    ev = catalog.CatalogEvaluator(weight, k=10, tie=tie) if full_catalog else None
     drv = EvalDriver(reference_user_rep(model_train, sas), weight, de, k_val, evaluator=ev)
     for data_batch in data_loader:
         drv.add_batch(data_batch)

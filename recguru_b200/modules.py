@@ -210,11 +210,17 @@ def sampled_logits_cat(h: Tensor, table: FusedItemEmbedding, dec_out: Tensor, n_
 
 
 def sampled_loss_fused(h: Tensor, table: FusedItemEmbedding, dec_out: Tensor, n_items: Tensor,
-                       mask: Optional[Tensor], kind: str):
+                       mask: Optional[Tensor], kind: str, skip_masked: bool = True):
     """Scores + loss in one kernel (K3).  ``kind`` in {"bpr", "bpr_sas", "sce"}.
-    Returns ``(loss, p_logits, n_logits)``; backward produces dh and the dense table grad."""
+    Returns ``(loss, p_logits, n_logits)``; backward produces dh and the dense table grad.
+
+    ``skip_masked`` (default): positions with ``mask == 0`` are not scored -- the reference scores them and
+    multiplies their loss term by 0 (tools/lossfunctions.py:44-48,:66-71,:90-95), so the loss and every
+    gradient are unchanged; only the returned logits of those positions are 0 instead of values nothing
+    downstream may use.  Pass ``skip_masked=False`` to get every logit."""
     pad = -1 if table.padding_idx is None else int(table.padding_idx)
     table._register()
     aux, p, n, _, _ = torch.ops.recguru.sampled_score_loss(h, table.weight, dec_out, n_items, mask,
-                                                           kind, pad)
+                                                           kind + "/skip" if (skip_masked and mask is not None) else kind,
+                                                           pad)
     return aux[0], p, n

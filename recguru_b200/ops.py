@@ -556,8 +556,11 @@ def raw_catalog_target_scores(users_bf16: Tensor, items_bf16: Tensor, target: Te
 
 
 def raw_catalog_topk_rank(users_bf16: Tensor, items_bf16: Tensor, target: Tensor,
-                          target_score: Tensor, k: int, id_lo: int, bufs: Optional[dict] = None):
-    """Fused scoring GEMM + running top-k + rank count over items [id_lo, id_lo+n_items)."""
+                          target_score: Tensor, k: int, id_lo: int, bufs: Optional[dict] = None,
+                          tie: str = "id"):
+    """Fused scoring GEMM + running top-k + rank count over items [id_lo, id_lo+n_items).
+    ``tie``: how items scoring exactly the target's score count -- ``"id"`` (lower id first: the stable
+    sort, default), ``"target_first"`` (rank = #{s > t}), ``"target_last"`` (rank = #{s >= t} - 1)."""
     lib = _lib.load()
     users_bf16 = _need(users_bf16, torch.bfloat16, "users")
     items_bf16 = _need(items_bf16, torch.bfloat16, "items")
@@ -576,10 +579,16 @@ def raw_catalog_topk_rank(users_bf16: Tensor, items_bf16: Tensor, target: Tensor
     if need < 0:
         raise _lib.RecGuruError(f"catalog_workspace_bytes rejected U={U} n_items={n_items} k={k}")
     ws = b.get("ws") if "ws" in b and b["ws"].numel() >= need else _workspace(need, dev)
-    check(lib.recguru_catalog_topk_rank(_ptr(users_bf16), U, _ptr(items_bf16), int(id_lo), n_items, d,
-                                        _ptr(target), _ptr(target_score), k, _ptr(val), _ptr(idx),
-                                        _ptr(cnt), _ptr(ws), ws.numel(), _stream()),
-          "catalog_topk_rank")
+    if tie == "id":
+        check(lib.recguru_catalog_topk_rank(_ptr(users_bf16), U, _ptr(items_bf16), int(id_lo), n_items, d,
+                                            _ptr(target), _ptr(target_score), k, _ptr(val), _ptr(idx),
+                                            _ptr(cnt), _ptr(ws), ws.numel(), _stream()),
+              "catalog_topk_rank")
+    else:
+        check(lib.recguru_catalog_topk_rank_ties(_ptr(users_bf16), U, _ptr(items_bf16), int(id_lo), n_items, d,
+                                                 _ptr(target), _ptr(target_score), k, _lib.TIE_MODES[tie],
+                                                 _ptr(val), _ptr(idx), _ptr(cnt), _ptr(ws), ws.numel(), _stream()),
+              "catalog_topk_rank_ties")
     return val, idx, cnt
 
 
@@ -814,7 +823,10 @@ def _sampled_loss(p, n, mask, kind):
 
 @_impl("sampled_score_loss")
 def _sampled_score_loss(h, weight, pos, neg, mask, kind, padding_idx):
-    p, n, aux, dp, dn = raw_sampled_score_loss(h, weight, pos, neg, mask, kind)
+    # kind "bpr_sas/skip": positions under the mask are not scored (padding-aware kernel)
+    base, _, flag = kind.partition("/")
+    p, n, aux, dp, dn = raw_sampled_score_loss(h, weight, pos, neg, mask, base,
+                                               skip_masked=flag == "skip" and mask is not None)
     return aux, p, n, dp, dn
 
 
@@ -1124,7 +1136,8 @@ def _bwd_gather_pe_mask_dropout(ctx, g_out, g_mask):
     if p > 0:
         g = torch.ops.recguru.dropout(g, mask, p, seed, offset, threads)
     d_pe = _pe_grad_of(ctx, g, ids, mask)
-    if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g.reshape(-1, d), coef=mask.reshape(-1))]):
+    m1 = mask.reshape(-1)
+    if _defer_sites(ctx.wref, [Site(ids.reshape(-1), g.reshape(-1, d), coef=m1, live=m1)]):
         dW = None
     else:
         dW = torch.ops.recguru.embedding_bwd(g.reshape(-1, d), ids.reshape(-1), mask.reshape(-1), ctx.V1, -1)
@@ -1233,14 +1246,21 @@ torch.library.register_autograd("recguru::sampled_loss", _bwd_sampled_loss,
 def _setup_sampled_score_loss(ctx, inputs, output):
     h, weight, pos, neg, mask, kind, padding_idx = inputs
     aux, p, n, dp, dn = output
-    ctx.save_for_backward(h, weight, pos, neg, aux, dp, dn)
+    if mask is not None:
+        ctx.save_for_backward(h, weight, pos, neg, aux, dp, dn, mask)
+    else:
+        ctx.save_for_backward(h, weight, pos, neg, aux, dp, dn)
+    ctx.has_mask = mask is not None
     ctx.padding_idx = padding_idx
     ctx.mark_non_differentiable(dp, dn)
     ctx.set_materialize_grads(False)  # g_p / g_n stay None unless p / n are used downstream
 
 
 def _bwd_sampled_score_loss(ctx, g_aux, g_p, g_n, g_dp, g_dn):
-    h, weight, pos, neg, aux, dp, dn = ctx.saved_tensors
+    h, weight, pos, neg, aux, dp, dn = ctx.saved_tensors[:7]
+    # the loss mask doubles as the sites' liveness mask: when the input lookup of the same step hangs off
+    # the SAME mask tensor, the one-pass table backward compacts by row (7x less to scan at cfg2)
+    live = ctx.saved_tensors[7].reshape(-1) if ctx.has_mask else None
     n_pos = pos.numel()
     K = neg.numel() // n_pos
     inv_m = aux[1:2]                      # 1/sum(mask), still missing from dp/dn
@@ -1249,8 +1269,8 @@ def _bwd_sampled_score_loss(ctx, g_aux, g_p, g_n, g_dp, g_dn):
         if weight.data_ptr() in _one_pass:
             dh = raw_sampled_score_bwd_dh(dp, dn, weight, pos, neg, go, inv_m).view(h.shape)
             h2 = h.reshape(n_pos, h.shape[-1])
-            if _defer_sites(weight, [Site(pos.reshape(-1), h2, dp, go, inv_m),
-                                     Site(neg.reshape(-1), h2, dn.view(-1), go, inv_m, group=K)]):
+            if _defer_sites(weight, [Site(pos.reshape(-1), h2, dp, go, inv_m, live=live),
+                                     Site(neg.reshape(-1), h2, dn.view(-1), go, inv_m, group=K, live=live)]):
                 return dh, None, None, None, None, None, None
         dh, dW = torch.ops.recguru.sampled_score_bwd(dp, dn, go, inv_m, h, weight, pos, neg,
                                                      ctx.padding_idx)

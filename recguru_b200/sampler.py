@@ -10,6 +10,18 @@ counter-based Philox: reproducible from ``(seed, step)``); only the id sequences
 
 The random stream differs from ``torch.multinomial``'s, the distribution does not
 (``tests/test_gpu_sampler.py``: exclusions never drawn, chi-square against the reference weights).
+
+Two quirks of the reference loader decide what "the reference's distribution" is (pinned by
+``tests/golden/sampler_weights.npz``, generated from ``pickle_loader.__getitem__`` itself):
+
+* ``for val in seq: weights[seq] = 0`` (data_loader.py:291-292,:303-304) REBINDS ``val`` to the last
+  history item, so ``weights[val] = 0`` zeroes ``seq[-1]`` a second time and the user's true
+  validation item stays a legal negative.  ``exclude_val=True``
+  (default) fixes that -- the validation item is excluded, as the code plainly intends;
+  ``exclude_val=False`` reproduces the reference's law exactly.
+* with ``item_freq`` the reference does not zero ``weights[0]`` (:289-295 vs :301-302): the pad id can be
+  drawn if ``wf[0] > 0``.  Here id 0 is never a negative; pass frequencies with ``wf[0] == 0`` (item counts
+  never include the pad id) and the two laws coincide.
 """
 from __future__ import annotations
 
@@ -51,8 +63,9 @@ class NegativeSampler:
     here, data_loader.py:251-254); ``None`` = uniform."""
 
     def __init__(self, v_size: int, num_n: int, seed: int = 0, item_freq: Optional[np.ndarray] = None,
-                 device="cuda"):
+                 device="cuda", exclude_val: bool = True):
         self.v_size, self.num_n, self.seed, self.step = int(v_size), int(num_n), int(seed), 0
+        self.exclude_val = bool(exclude_val)       # False: the reference's law (its val exclusion is a no-op)
         self.device = torch.device(device)
         self.alias_prob = self.alias_idx = None
         if item_freq is not None:
@@ -71,6 +84,8 @@ class NegativeSampler:
         (CUDA graphs: bump it inside the graph with :meth:`advance`)."""
         history = _need(history, torch.int64, "history")
         B, H = history.shape
+        if not self.exclude_val:
+            val = None
         val = None if val is None else _need(val.view(-1), torch.int64, "val")
         test = None if test is None else _need(test.view(-1), torch.int64, "test")
         if out is None:
@@ -112,7 +127,8 @@ class NegativeSampler:
             step = self.step
             self.step += 1
         check(_lib.load().recguru_sample_negatives_csr(
-            _ptr(store.items), _ptr(store.offsets), _ptr(user_idx), B, max(int(store.max_len), 1), _ptr(store.val),
+            _ptr(store.items), _ptr(store.offsets), _ptr(user_idx), B, max(int(store.max_len), 1),
+            _ptr(store.val if self.exclude_val else None),
             _ptr(store.test), self.v_size, _ptr(self.alias_prob), _ptr(self.alias_idx), self.num_n, self.seed,
             int(step), _ptr(step_dev), _ptr(out), _stream()), "sample_negatives_csr")
         return out

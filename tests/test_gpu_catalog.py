@@ -231,3 +231,34 @@ def test_catalog_evaluator_single_gpu(ops):
     # the torch.library op
     v2, i2, r2 = torch.ops.recguru.catalog_topk_rank(users.cuda(), ev.items, target.cuda(), k, 1)
     assert torch.equal(r2, rank) and torch.equal(i2, idx)
+
+
+def test_tie_modes_and_bracket(ops):
+    """explicit tie rules for the target's rank.  Degenerate scores (few distinct values, an
+    all-equal row) on grid data: target_first = #{s > t}, target_last = #{s >= t} - 1, id = the stable
+    sort; the bracket's width is the number of items tied with the target."""
+    from recguru_b200 import catalog
+    d, n_items, U = 64, 3000, 260
+    g = torch.Generator().manual_seed(5)
+    W = torch.randint(-1, 2, (n_items + 2, d), generator=g).float()      # scores collide massively
+    W[0] = 0
+    users = torch.randint(-1, 2, (U, d), generator=g).float()
+    users[7] = 0                                                         # an all-equal score row (all zeros)
+    target = torch.randint(1, n_items + 1, (U,), generator=g)
+    s = O.catalog_scores(users, W[1:n_items + 1])
+    t = s.gather(1, (target - 1)[:, None])
+    best_ref = (s > t).sum(1)
+    worst_ref = (s >= t).sum(1) - 1
+    id_ref = O.catalog_rank(s, target - 1)
+    ev = catalog.CatalogEvaluator(W.cuda(), k=10)
+    assert torch.equal(ev.target_rank(users.cuda(), target.cuda()).cpu(), id_ref)
+    best, worst = ev.tie_bracket(users.cuda(), target.cuda())
+    assert torch.equal(best.cpu(), best_ref) and torch.equal(worst.cpu(), worst_ref)
+    assert int(best[7]) == 0 and int(worst[7]) == n_items - 1            # the degenerate row: rank 0 .. N-1
+    assert bool(((best.cpu() <= id_ref) & (id_ref <= worst.cpu())).all())
+    for tie, ref in (("target_first", best_ref), ("target_last", worst_ref)):
+        e2 = catalog.CatalogEvaluator(W.cuda(), k=10, tie=tie)
+        val, idx, rk = e2.rank_topk(users.cuda(), target.cuda())
+        assert torch.equal(rk.cpu(), ref)
+        rv, ri = O.catalog_topk(s, 10)
+        assert torch.equal(idx.cpu(), ri + 1) and torch.equal(val.cpu(), rv)   # lists do not depend on the rule

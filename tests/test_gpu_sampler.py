@@ -9,13 +9,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def reference_weights(v_size, seq, val, test, item_freq=None):
-    """The weight vector the reference hands to torch.multinomial."""
-    w = np.ones(v_size) if item_freq is None else np.power(item_freq[:v_size].astype(np.float64), 0.75)
-    w[0] = 0
-    w[np.asarray(seq)] = 0
-    w[val] = 0
-    w[test] = 0
+def reference_weights(v_size, seq, val, test, item_freq=None, exclude_val=True):
+    """The weight vector the reference hands to torch.multinomial: oracle.sampling_weights, pinned to the
+    unmodified loader by tests/golden/sampler_weights.npz (test_oracle_golden.py).  exclude_val=True is
+    the repaired law NegativeSampler defaults to; False the reference's own (its val exclusion is a no-op)."""
+    from oracle import ref_path as O
+    w = O.sampling_weights(seq, val, test, v_size, item_freq=None if item_freq is None else item_freq[:v_size],
+                           exclude_val=exclude_val)
+    w[0] = 0                                      # id 0 is never a negative here (wf[0] == 0 in the tests)
     return w / w.sum()
 
 
@@ -54,6 +55,31 @@ def test_sampler_distribution_and_exclusions(built_lib, weighted):
         chi2 = (((cnt - exp) ** 2)[p > 0] / exp[p > 0]).sum()
         dof = int((p > 0).sum()) - 1
         assert chi2 < dof + 6 * np.sqrt(2 * dof)                         # chi-square within 6 sigma
+
+
+def test_sampler_reference_law_keeps_validation_item(built_lib):
+    """exclude_val=False: the reference's exact law (data_loader.py:291-295: `for val in seq` rebinds val, the
+    validation item stays a legal negative) -- chi-square against the loader-pinned oracle weights."""
+    from recguru_b200.sampler import NegativeSampler
+    B, H, v_size, num_n = 6, 40, 300, 200_000
+    hist, seqs, val, test = make_batch(B, H, v_size, 21)
+    for b in range(B):                                                   # make sure val is not excluded by accident
+        while val[b] in set(seqs[b].tolist()) | {int(test[b])}:
+            val[b] = val[b] % (v_size - 1) + 1
+    smp = NegativeSampler(v_size, num_n, seed=5, exclude_val=False)
+    out = smp.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(val).cuda(), torch.from_numpy(test).cuda()).cpu().numpy()
+    fixed = NegativeSampler(v_size, num_n, seed=5).sample(torch.from_numpy(hist).cuda(), torch.from_numpy(val).cuda(),
+                                                          torch.from_numpy(test).cuda()).cpu().numpy()
+    for b in range(B):
+        p = reference_weights(v_size, seqs[b], val[b], test[b], exclude_val=False)
+        assert p[val[b]] > 0
+        cnt = np.bincount(out[b], minlength=v_size).astype(np.float64)
+        assert cnt[p == 0].sum() == 0 and cnt[val[b]] > 0               # val IS drawn under the reference's law
+        exp = p * num_n
+        chi2 = (((cnt - exp) ** 2)[p > 0] / exp[p > 0]).sum()
+        dof = int((p > 0).sum()) - 1
+        assert chi2 < dof + 6 * np.sqrt(2 * dof)
+        assert np.bincount(fixed[b], minlength=v_size)[val[b]] == 0     # ... and never under the repaired one
 
 
 def test_sampler_is_deterministic_in_seed_and_step(built_lib):

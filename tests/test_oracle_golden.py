@@ -272,3 +272,26 @@ def test_survey_kats_metrics_and_pad_mask():
     want = [[1, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0], [1, 1, 1, 1, 0, 0]]
     mask = O.pad_mask(ids, 0)
     assert mask.dtype == torch.float32 and mask.tolist() == want
+
+
+def test_sampling_weights_match_reference_loader():
+    """oracle.sampling_weights == the weight vectors pickle_loader.__getitem__ hands to torch.multinomial
+    (captured from the unmodified reference by oracle/make_golden_sampler.py), including the reference's
+    `for val in seq` rebinding: the true validation item is NOT excluded (ADVICE r1 / SURVEY 5 quirk 1)."""
+    g = load_golden("sampler_weights.npz")
+    v_size = int(g["v_size"])
+    off = np.concatenate([[0], np.cumsum(g["seq_len"])])
+    n_val_kept = 0
+    for i in range(len(g["seq_len"])):
+        seq = g["seq_flat"][off[i]:off[i + 1]]
+        val, test = int(g["val"][i]), int(g["test"][i])
+        w = O.sampling_weights(seq, val, test, v_size)
+        assert np.array_equal(w, g["weights_uniform"][i])
+        wf = O.sampling_weights(seq, val, test, v_size, item_freq=g["wf"])
+        assert np.allclose(wf, g["weights_freq"][i], rtol=1e-6, atol=0)
+        if val not in set(seq.tolist()) | {test}:
+            assert g["weights_uniform"][i][val] == 1.0          # the quirk: val stays a legal negative
+            n_val_kept += 1
+            assert O.sampling_weights(seq, val, test, v_size, exclude_val=True)[val] == 0.0
+        assert g["weights_uniform"][i][seq].sum() == 0 and g["weights_uniform"][i][test] == 0
+    assert n_val_kept > 0
