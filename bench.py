@@ -794,7 +794,8 @@ def bench_gather(D: Dist, args, peaks, W, pe, batches):
                    "batch: 93% pad tokens hit one row; dense_ids: a no-padding batch); 4 rotating out buffers "
                    "= 420 MB > L2.  The HBM figures are in `hbm_table`."}
     del outs, masks, ids
-    out["hbm_table"] = bench_gather_hbm(D, args, peaks)
+    if D.world == 1:
+        out["hbm_table"] = bench_gather_hbm(D, args, peaks)
     return out
 
 
@@ -1258,7 +1259,7 @@ def main():
         torch.cuda.empty_cache()
     topo = {}
     for which in ("cfg1", "cfg3"):
-        if want(which):
+        if want(which) and (D.world == 1 or which in only):   # replicas only: measured at N = 1 unless asked for
             topo[which] = bench_topology(D, args, peaks, which)
             torch.cuda.empty_cache()
     cat = {}

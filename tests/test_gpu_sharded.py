@@ -33,7 +33,7 @@ def _data(n_items, U, d):
     return W, users, target
 
 
-def _worker(rank, world, port, n_items, U, d, k, out):
+def _worker(rank, world, port, n_items, U, d, k, out, counts=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -43,7 +43,8 @@ def _worker(rank, world, port, n_items, U, d, k, out):
         W, users, target = _data(n_items, U, d)
         ev = CatalogEvaluator(W.cuda(), k=k, group=dist.group.WORLD)
         per = U // world
-        sl = slice(rank * per, (rank + 1) * per)
+        sl = slice(rank * per, (rank + 1) * per) if counts is None else \
+            slice(sum(counts[:rank]), sum(counts[:rank + 1]))
         val, idx, rk = ev.rank_topk(users[sl].cuda(), target[sl].cuda())
         met = ev.evaluate_global(users[sl].cuda(), target[sl].cuda(), ks=(5, 10))
         out[rank] = (val.cpu(), idx.cpu(), rk.cpu(), met)
@@ -70,3 +71,25 @@ def test_sharded_catalog_nccl_matches_oracle(built_lib, n_items, U, d, k):
         assert torch.equal(idx, ri[sl] + 1) and torch.equal(val, rv[sl])
         assert abs(met[10]["hr"] - O.hit_at_k_batch(ref_rank.tolist(), 10)) < 1e-12
         assert abs(met[5]["ndcg"] - O.NDCG_at_k_batch(ref_rank.tolist(), 5)) < 1e-9
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_catalog_nccl_ragged_users(built_lib):
+    """Ranks holding different numbers of users (a last partial batch): padded to the maximum
+    inside rank_topk, results sliced back -- bit-equal to the single-shard oracle."""
+    world, n_items, d, k = 2, 3000, 128, 10
+    counts = [300, 77]
+    U = sum(counts)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_items, U, d, k, out, counts), nprocs=world, join=True)
+    W, users, target = _data(n_items, U, d)
+    s = O.catalog_scores(users, W[1:n_items + 1])
+    ref_rank = O.catalog_rank(s, target - 1)
+    rv, ri = O.catalog_topk(s, k)
+    for r in range(world):
+        val, idx, rk, met = out[r]
+        sl = slice(sum(counts[:r]), sum(counts[:r + 1]))
+        assert rk.shape[0] == counts[r]
+        assert torch.equal(rk, ref_rank[sl]) and torch.equal(idx, ri[sl] + 1) and torch.equal(val, rv[sl])
+        assert abs(met[10]["hr"] - O.hit_at_k_batch(ref_rank.tolist(), 10)) < 1e-12
