@@ -1040,9 +1040,14 @@ static int launch_sweep2(const void* items, const CUtensorMap& mu, CatalogParams
   CUtensorMap mi;
   const int rc = make_rowmajor_map(&mi, items, p.n_items, D, 128);
   if (rc) return rc;
+#ifdef RECGURU_DEBUG_KNOBS
+  // 3 / 4 epilogue warps per lane quarter (64- / 32-column TMEM loads): measured SLOWER than 2 (cfg4: 24.4 /
+  // 26.3 ms against 22.7; profiles/r02_catalog_warps_per_quarter.log) -- the sweep is bound by board power,
+  // not by latency hiding, and the extra chunk loops are extra instructions.  Debug builds only.
   const int nw = env_int("RECGURU_CATALOG_WARPS", kSweepWarpsDefault);
   if (nw == 3) return launch_sweep2_k<D, MODE, 3, 64>(mu, mi, p, st);
   if (nw == 4) return launch_sweep2_k<D, MODE, 4, 32>(mu, mi, p, st);
+#endif
   return launch_sweep2_k<D, MODE, 2, 128>(mu, mi, p, st);
 }
 

@@ -316,10 +316,15 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total_host,
   rg::pdl_wait();
   __shared__ uint32_t s_hist[kMaxBins];
   const int64_t total = n_live ? static_cast<int64_t>(*n_live) : total_host;
+  const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kSortTile;
+  // The grid is sized for the CAPACITY (all gathered indices); after compaction only the first
+  // ceil(total / tile) tiles hold keys.  The others used to store 512 zeros each into the digit-major
+  // histogram (stride = grid: one sector per word) for the scan to read back -- on cfg2's padded batch
+  // 648 of 700 tiles.  The scan and the scatter now look at the live tiles only, so dead tiles leave.
+  if (tile0 >= total) return;
   const int bins = 1 << bits;
   for (int b = threadIdx.x; b < bins; b += kSortThreads) s_hist[b] = 0;
   __syncthreads();
-  const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kSortTile;
   const uint32_t mask = bins - 1;
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
@@ -335,12 +340,15 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t total_host,
 // Exclusive scan of one digit's row of the digit-major histogram (CTA b <-> digit b); the row
 // total goes to totals[b].  The scatter kernel adds the digit base (scan over totals) itself.
 __global__ void __launch_bounds__(256)
-radix_scan_rows_kernel(uint32_t* __restrict__ hist, int n_tiles, uint32_t* __restrict__ totals) {
+radix_scan_rows_kernel(uint32_t* __restrict__ hist, int n_tiles_cap, int64_t total_host,
+                       const uint32_t* __restrict__ n_live, uint32_t* __restrict__ totals) {
   rg::pdl_wait();
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* row = hist + static_cast<int64_t>(blockIdx.x) * n_tiles;
+  uint32_t* row = hist + static_cast<int64_t>(blockIdx.x) * n_tiles_cap;   // row stride = capacity
+  const int64_t total = n_live ? static_cast<int64_t>(*n_live) : total_host;
+  const int n_tiles = static_cast<int>((total + kSortTile - 1) / kSortTile);   // live tiles only
   if (tid == 0) s_carry = 0;
   __syncthreads();
   for (int t0 = 0; t0 < n_tiles; t0 += 256) {
@@ -1045,7 +1053,7 @@ static int run_radix_sort(const SortPlan& p, char* ws, int64_t count, const uint
     const int bits = min(p.bits_per_pass, p.total_bits - shift);
     rg::launch_pdl((radix_hist_kernel), grid, kSortThreads, 0, st, keys[cur], count, n_live, shift, bits, hist);
     RG_CHECK_LAUNCH("radix_hist");
-    rg::launch_pdl((radix_scan_rows_kernel), 1u << bits, 256, 0, st, hist, static_cast<int>(p.n_tiles), totals);
+    rg::launch_pdl((radix_scan_rows_kernel), 1u << bits, 256, 0, st, hist, static_cast<int>(p.n_tiles), count, n_live, totals);
     RG_CHECK_LAUNCH("radix_scan_rows");
     const bool last = pass == p.passes - 1;
     if (last && out_perm64) {

@@ -1,0 +1,26 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m recguru_b200.build > /dev/null
+echo "== whole gpu suite"
+timeout 900 python -m pytest tests -m gpu -q --no-header 2>&1 | tail -8 | tee gpurun_out/r2_tests_all.log
+echo "== plan only"
+timeout 60 python scripts/plan_only.py
+timeout 60 python scripts/plan_only.py dense
+echo "== timeline"
+timeout 100 python scripts/step_timeline.py
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -3 | tee gpurun_out/r2_smoke.log
+echo "== bench"
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_h.json 2> gpurun_out/r2_bench_h.err; echo "rc=$?"
+tail -3 gpurun_out/r2_bench_h.err
+python - <<'PY'
+import json
+j=json.loads(open("gpurun_out/r2_bench_h.json").read().strip().splitlines()[-1])
+print("train", round(j["value"]), "seqs/s", round(j["ms_per_step"],4), "ms; eager", round(j["ms_per_step_eager"],4), "e2e", round(j["e2e"]["value"]), "roof", j["roofline"]["frac"], j["roofline"]["whole_step"])
+for k,v in j["stages"].items(): print("  ", k, v["ms"], v["frac_of_hbm_peak"])
+print("dropin", j["dropin_surface"])
+print("dense", j["dense_batch"]["ms_per_step"], j["dense_batch"]["frac_of_hbm_peak"], j["dense_batch"]["k2_table_backward"])
+for k,c in j["catalog"].items(): print(k, round(c["value"]), "users/s", c["roofline"]["frac"], "rank-only", c["rank_only"]["users_per_s"], "cpu", c.get("cpu_baseline",{}).get("value"))
+print("topo", {k: {vk: (round(vv["value"]), vv["roofline"]["frac"]) for vk, vv in v["variants"].items()} for k, v in j["train_topologies"].items()})
+print("cpu", j["cpu_baseline"])
+PY
