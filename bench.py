@@ -543,9 +543,20 @@ def bench_train(D: Dist, args, peaks):
     # replicas share the host links); recguru_widen_ids restores the int64 layout the ops take, on the
     # copy stream.  The int64-over-PCIe form (what default_collate hands over, data_loader.py:418-421)
     # is timed beside it.
-    pin32 = [{k: v.to(torch.int32).pin_memory() for k, v in pb.items()} for pb in pin]
-    d_in = [{k: torch.empty_like(v, device=dev) for k, v in pin[0].items()} for _ in range(2)]
-    d_in32 = [{k: torch.empty_like(v, device=dev) for k, v in pin32[0].items()} for _ in range(2)]
+    # ... and into ONE pinned block per step ([dec_in | dec_out | n_items], int32): one H2D copy and one
+    # widen kernel instead of three of each
+    keys3 = ("dec_in", "dec_out", "n_items")
+    sizes3 = [pin[0][k].numel() for k in keys3]
+    pin32 = [torch.cat([pb[k].reshape(-1).to(torch.int32) for k in keys3]).pin_memory() for pb in pin]
+    d_blk64 = [torch.empty(sum(sizes3), dtype=torch.int64, device=dev) for _ in range(2)]
+    d_blk32 = [torch.empty(sum(sizes3), dtype=torch.int32, device=dev) for _ in range(2)]
+    d_in = []
+    for slot in range(2):                                   # the int64 views the step's kernels read
+        o, views = 0, {}
+        for k, sz in zip(keys3, sizes3):
+            views[k] = d_blk64[slot][o:o + sz].view(pin[0][k].shape)
+            o += sz
+        d_in.append(views)
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream()
     copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -556,11 +567,11 @@ def bench_train(D: Dist, args, peaks):
         slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # buffer free (its previous step finished)
-            for k in d_in[slot]:
-                if state["ids32"]:
-                    d_in32[slot][k].copy_(pin32[i % n_batches][k], non_blocking=True)
-                    ops.raw_widen_ids(d_in32[slot][k], out=d_in[slot][k])
-                else:
+            if state["ids32"]:
+                d_blk32[slot].copy_(pin32[i % n_batches], non_blocking=True)
+                ops.raw_widen_ids(d_blk32[slot], out=d_blk64[slot])
+            else:
+                for k in keys3:
                     d_in[slot][k].copy_(pin[i % n_batches][k], non_blocking=True)
             copied[slot].record(copy_stream)
 
@@ -725,7 +736,7 @@ def bench_train(D: Dist, args, peaks):
                            "device; only the batch's user indices cross PCIe; value = the faster of eager launches and one "
                            "CUDA graph per batch (sampler step read from a device counter the graph advances)"}
     e2e_mode = "eager (TrainHotPath.step)" if ms_e2e == ms_e2e_eager else "cuda_graph (TrainHotPath.capture_step)"
-    h2d = sum(v.numel() * v.element_size() for v in pin32[0].values())
+    h2d = pin32[0].numel() * pin32[0].element_size()
     h2d_i64 = sum(v.numel() * v.element_size() for v in pin[0].values())
     seqs = cfg["B"] * D.world
     out = {
@@ -738,8 +749,8 @@ def bench_train(D: Dist, args, peaks):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
                 "launch_mode": e2e_mode, "ms_per_step_eager": ms_e2e_eager / K,
                 "ms_per_step_graph": None if ms_e2e_graph is None else ms_e2e_graph / K,
-                "ids_on_host": "int32 (collated into pinned int32 by the loader; widened to int64 on the device "
-                               "by recguru_widen_ids on the copy stream)",
+                "ids_on_host": "int32, one pinned block per step [dec_in | dec_out | n_items] (the loader's collate); one "
+                               "H2D copy, widened to int64 on the device by recguru_widen_ids on the copy stream",
                 "int64_ids": {"value": seqs * K / (ms_e2e_i64 / 1e3), "ms_per_step": ms_e2e_i64 / K,
                               "h2d_bytes_per_step": h2d_i64,
                               "note": "same loop with int64 ids over PCIe (what default_collate hands over)"},

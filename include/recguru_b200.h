@@ -180,6 +180,23 @@ int recguru_embedding_bwd_plan_padmask(const recguru_lookup_site_t* sites, int n
                                        int64_t padding_idx, const int64_t* mask_ids, int64_t pad_index,
                                        float* mask_out, uint32_t* count3, void* workspace,
                                        int64_t workspace_bytes, recguru_stream_t stream);
+/* The plan in two calls, so that a caller can record an event between the compaction and the sort:
+ * RECGURU_PLAN_COMPACT (stable compaction; in row mode it also leaves the ascending list of live rows
+ * that recguru_embedding_bwd_plan_live_rows points at) then RECGURU_PLAN_SORT (the radix sort) on the
+ * same stream == RECGURU_PLAN_ALL == recguru_embedding_bwd_plan. */
+#define RECGURU_PLAN_ALL 0
+#define RECGURU_PLAN_COMPACT 1
+#define RECGURU_PLAN_SORT 2
+int recguru_embedding_bwd_plan_stage(const recguru_lookup_site_t* sites, int n_sites, int64_t V1,
+                                     int64_t padding_idx, void* workspace, int64_t workspace_bytes,
+                                     int stage, recguru_stream_t stream);
+/* Host-only: device pointers (into `workspace`) of the live-row list the row-mode compaction of these
+ * sites writes -- *live_rows[0 .. **n_live_rows) ascending rows with live != 0.  It is the list of
+ * positions the loss keeps (train_auto.py:124 tgt_padding_mask), consumed by
+ * recguru_sampled_score_loss_fwd_dh_rows.  RECGURU_E_UNSUPPORTED if the sites are not in row mode. */
+int recguru_embedding_bwd_plan_live_rows(const recguru_lookup_site_t* sites, int n_sites, int64_t V1,
+                                         void* workspace, int64_t workspace_bytes,
+                                         const uint32_t** live_rows, const uint32_t** n_live_rows);
 int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_host, int n_sites, int64_t d,
                                 int64_t V1, float* dW, int zero_fill, void* workspace,
                                 int64_t workspace_bytes, recguru_stream_t stream);
@@ -228,6 +245,19 @@ int recguru_sampled_score_loss_fwd_dh(const float* h, const float* weight, int64
                                       float* dn_unit, void* workspace, int64_t workspace_bytes,
                                       const float* grad_scale, const uint32_t* live_count,
                                       float* dh, recguru_stream_t stream);
+/* The same with the live positions given as a list: live_rows[0 .. *n_live_rows) = the ascending
+ * indices i with mask[i] != 0 (device pointers; the row-mode compaction of the table-backward plan
+ * leaves exactly this list, recguru_embedding_bwd_plan_live_rows).  One warp per live position and no
+ * compaction inside the kernel; outputs bit-identical to recguru_sampled_score_loss_fwd_dh.  dh may
+ * be NULL (forward only). */
+int recguru_sampled_score_loss_fwd_dh_rows(const float* h, const float* weight, int64_t V1, int64_t d,
+                                           const int64_t* pos, const int64_t* neg, int64_t n_pos,
+                                           int64_t K, const float* mask, int kind, float* p_out,
+                                           float* n_out, float* loss_out, float* dp_unit,
+                                           float* dn_unit, void* workspace, int64_t workspace_bytes,
+                                           const float* grad_scale, const uint32_t* live_count,
+                                           const uint32_t* live_rows, const uint32_t* n_live_rows,
+                                           float* dh, recguru_stream_t stream);
 /* Loss only, from logits (drop-in for loss_bpr(p,n,mask) / loss_s_ce(logits,...)). */
 int recguru_sampled_loss_fwd(const float* p, const float* n, int64_t n_pos, int64_t K,
                              const float* mask, int kind, float* loss_out, float* dp_unit,

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kSortThreads)
 row_scatter_kernel(SiteTable st, const float* __restrict__ live, int64_t n_rows, int64_t padding_idx,
                    uint32_t sentinel, const uint32_t* __restrict__ tile_offset,
                    const uint32_t* __restrict__ n_live_rows, uint32_t* __restrict__ n_live_occ,
-                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ live_rows) {
   rg::pdl_wait();
   __shared__ uint32_t s_w[kSortThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,6 +276,7 @@ row_scatter_kernel(SiteTable st, const float* __restrict__ live, int64_t n_rows,
     if (rank[j] == 0xffffffffu) continue;
     const int64_t row = warp0 + j * 32 + lane;
     const uint32_t r = base + rank[j];
+    live_rows[r] = static_cast<uint32_t>(row);      // the step's live positions, ascending (scoring kernel)
     uint32_t gpre = 0;
 #pragma unroll
     for (int s2 = 0; s2 < NS; ++s2) {
@@ -1002,7 +1003,7 @@ struct SortPlan {
   int total_bits, passes, bits_per_pass;
   int64_t n_tiles;
   // workspace carve-up (bytes, 256-aligned)
-  int64_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_hist, off_totals, off_tilecnt, off_nlive, end;
+  int64_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_hist, off_totals, off_tilecnt, off_nlive, off_rows, end;
 };
 
 static SortPlan make_sort_plan(int64_t count, int64_t V1) {
@@ -1029,6 +1030,7 @@ static SortPlan make_sort_plan(int64_t count, int64_t V1) {
   p.off_totals = o; o += align_up(kMaxBins * 4, 256);
   p.off_tilecnt = o; o += align_up(ceil_div(count > 0 ? count : 1, kCompactTile) * 4, 256);
   p.off_nlive = o; o += 256;
+  p.off_rows = o; o += kb;                 // compacted list of live rows (row mode; rows <= count)
   p.end = o;
   return p;
 }
@@ -1187,12 +1189,17 @@ inline bool env_plan_v1() {
 
 static int plan_v1(const recguru_lookup_site_t* sites_host, int n_sites, const SiteTable& tab, int64_t total,
                    int64_t V1, int64_t padding_idx, bool by_row, int64_t n_rows, const SortPlan& p, char* ws,
-                   cudaStream_t st) {
+                   int stage, cudaStream_t st) {
   uint32_t* tile_cnt = reinterpret_cast<uint32_t*>(ws + p.off_tilecnt);
   uint32_t* n_live = reinterpret_cast<uint32_t*>(ws + p.off_nlive);
   uint32_t* ka = reinterpret_cast<uint32_t*>(ws + p.off_keys_a);
   uint32_t* va = reinterpret_cast<uint32_t*>(ws + p.off_vals_a);
+  if (stage == RECGURU_PLAN_SORT) {
+    uint32_t *sk0, *sv0;
+    return run_radix_sort(p, ws, total, n_live, false, st, &sk0, &sv0, nullptr, nullptr);
+  }
   if (by_row) {
+    uint32_t* rows = reinterpret_cast<uint32_t*>(ws + p.off_rows);
     const unsigned rtiles = static_cast<unsigned>(ceil_div(n_rows, kCompactTile));
     const float* lv = sites_host[0].live;
     rg::launch_pdl((row_count_kernel), rtiles, kSortThreads, 0, st, lv, n_rows, tile_cnt);
@@ -1200,10 +1207,11 @@ static int plan_v1(const recguru_lookup_site_t* sites_host, int n_sites, const S
     rg::launch_pdl((compact_scan_kernel), 1, 1024, 0, st, tile_cnt, static_cast<int>(rtiles), n_live + 1);
     RG_CHECK_LAUNCH("compact_scan");
     const uint32_t sentinel = static_cast<uint32_t>(V1);
-    if (n_sites <= 1) rg::launch_pdl((row_scatter_kernel<1>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va);
-    else if (n_sites <= 3) rg::launch_pdl((row_scatter_kernel<3>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va);
-    else rg::launch_pdl((row_scatter_kernel<RECGURU_MAX_SITES>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va);
+    if (n_sites <= 1) rg::launch_pdl((row_scatter_kernel<1>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va, rows);
+    else if (n_sites <= 3) rg::launch_pdl((row_scatter_kernel<3>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va, rows);
+    else rg::launch_pdl((row_scatter_kernel<RECGURU_MAX_SITES>), rtiles, kSortThreads, 0, st, tab, lv, n_rows, padding_idx, sentinel, tile_cnt, n_live + 1, n_live, ka, va, rows);
     RG_CHECK_LAUNCH("row_scatter");
+    if (stage == RECGURU_PLAN_COMPACT) return RECGURU_OK;
     uint32_t *sk2, *sv2;
     return run_radix_sort(p, ws, total, n_live, false, st, &sk2, &sv2, nullptr, nullptr);
   }
@@ -1218,6 +1226,7 @@ static int plan_v1(const recguru_lookup_site_t* sites_host, int n_sites, const S
   else if (n_sites <= 3) rg::launch_pdl((compact_scatter_kernel<3>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt, ka, va);
   else rg::launch_pdl((compact_scatter_kernel<RECGURU_MAX_SITES>), tiles, kSortThreads, 0, st, tab, total, padding_idx, tile_cnt, ka, va);
   RG_CHECK_LAUNCH("compact_scatter");
+  if (stage == RECGURU_PLAN_COMPACT) return RECGURU_OK;
   uint32_t *sk, *sv;
   return run_radix_sort(p, ws, total, n_live, false, st, &sk, &sv, nullptr, nullptr);
 }
@@ -1281,16 +1290,18 @@ static int plan_v2(const recguru_lookup_site_t* sites_host, int n_sites, const S
 
 static int plan_impl(const char* who, const recguru_lookup_site_t* sites_host, int n_sites, int64_t V1,
                      int64_t padding_idx, void* workspace, int64_t workspace_bytes, const int64_t* mask_ids,
-                     int64_t pad_index, float* mask_out, uint32_t* count3, recguru_stream_t stream) {
+                     int64_t pad_index, float* mask_out, uint32_t* count3, int stage, recguru_stream_t stream) {
   RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "%s: bad V1", who);
+  RG_REQUIRE(stage >= RECGURU_PLAN_ALL && stage <= RECGURU_PLAN_SORT, RECGURU_E_SHAPE, "%s: stage=%d", who, stage);
   SiteTable tab;
   int64_t total = 0;
   int rc = build_site_table(who, sites_host, n_sites, false, &tab, &total);
   if (rc) return rc;
   if (total == 0) return RECGURU_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int s = 0; s < n_sites; ++s)
-    RG_CHECK_IDS("embedding_bwd_plan (site ids)", sites_host[s].ids, sites_host[s].count, 0, V1, st);
+  if (stage != RECGURU_PLAN_SORT)
+    for (int s = 0; s < n_sites; ++s)
+      RG_CHECK_IDS("embedding_bwd_plan (site ids)", sites_host[s].ids, sites_host[s].count, 0, V1, st);
   int64_t n_rows = 0;
   const bool by_row = row_mode(sites_host, n_sites, &n_rows);
   RG_REQUIRE(mask_ids == nullptr || (by_row && mask_out != nullptr && sites_host[0].live == mask_out),
@@ -1301,13 +1312,15 @@ static int plan_impl(const char* who, const recguru_lookup_site_t* sites_host, i
              "%s: workspace %lld < %lld", who, (long long)workspace_bytes, (long long)p.end);
   char* ws = static_cast<char*>(workspace);
   if (env_plan_v1()) {
-    if (mask_ids != nullptr) {
+    if (mask_ids != nullptr && stage != RECGURU_PLAN_SORT) {
       rc = count3 ? recguru_pad_mask_count(mask_ids, n_rows, pad_index, mask_out, count3, stream)
                   : recguru_pad_mask(mask_ids, n_rows, pad_index, mask_out, stream);
       if (rc) return rc;
     }
-    return plan_v1(sites_host, n_sites, tab, total, V1, padding_idx, by_row, n_rows, p, ws, st);
+    return plan_v1(sites_host, n_sites, tab, total, V1, padding_idx, by_row, n_rows, p, ws, stage, st);
   }
+  RG_REQUIRE(stage == RECGURU_PLAN_ALL, RECGURU_E_UNSUPPORTED,
+             "%s: the two-stage plan needs the default plan (unset RECGURU_BWD_PLAN)", who);
   return plan_v2(sites_host, n_sites, tab, total, V1, padding_idx, by_row, n_rows, p, ws, mask_ids, pad_index,
                  mask_out, count3, st);
 }
@@ -1319,7 +1332,43 @@ extern "C" int recguru_embedding_bwd_plan(const recguru_lookup_site_t* sites_hos
                                           int64_t V1, int64_t padding_idx, void* workspace,
                                           int64_t workspace_bytes, recguru_stream_t stream) {
   return rg::plan_impl("embedding_bwd_plan", sites_host, n_sites, V1, padding_idx, workspace, workspace_bytes,
-                       nullptr, 0, nullptr, nullptr, stream);
+                       nullptr, 0, nullptr, nullptr, RECGURU_PLAN_ALL, stream);
+}
+
+// Stage A in two calls, so that a caller can hang an event between them: RECGURU_PLAN_COMPACT runs
+// the stable compaction (in row mode it also leaves the ascending list of live rows, see
+// recguru_embedding_bwd_plan_live_rows), RECGURU_PLAN_SORT the radix sort over it.  COMPACT then
+// SORT on one stream == RECGURU_PLAN_ALL == recguru_embedding_bwd_plan.
+extern "C" int recguru_embedding_bwd_plan_stage(const recguru_lookup_site_t* sites_host, int n_sites,
+                                                int64_t V1, int64_t padding_idx, void* workspace,
+                                                int64_t workspace_bytes, int stage, recguru_stream_t stream) {
+  return rg::plan_impl("embedding_bwd_plan_stage", sites_host, n_sites, V1, padding_idx, workspace,
+                       workspace_bytes, nullptr, 0, nullptr, nullptr, stage, stream);
+}
+
+// Where the row-mode compaction leaves the live rows: *live_rows -> ascending row indices,
+// *n_live_rows -> their count (both device pointers into `workspace`, valid once the compaction of
+// the same sites has run on the stream).  RECGURU_E_UNSUPPORTED when the sites are not in row mode.
+extern "C" int recguru_embedding_bwd_plan_live_rows(const recguru_lookup_site_t* sites_host, int n_sites,
+                                                    int64_t V1, void* workspace, int64_t workspace_bytes,
+                                                    const uint32_t** live_rows, const uint32_t** n_live_rows) {
+  using namespace rg;
+  RG_REQUIRE(live_rows && n_live_rows, RECGURU_E_SHAPE, "embedding_bwd_plan_live_rows: null pointer");
+  RG_REQUIRE(V1 > 0 && V1 < (1ll << 31), RECGURU_E_SHAPE, "embedding_bwd_plan_live_rows: bad V1");
+  SiteTable tab;
+  int64_t total = 0;
+  int rc = build_site_table("embedding_bwd_plan_live_rows", sites_host, n_sites, false, &tab, &total);
+  if (rc) return rc;
+  int64_t n_rows = 0;
+  RG_REQUIRE(total > 0 && row_mode(sites_host, n_sites, &n_rows) && env_plan_v1(), RECGURU_E_UNSUPPORTED,
+             "embedding_bwd_plan_live_rows: the sites do not share one per-row liveness mask");
+  const SortPlan p = make_sort_plan(total, V1 + 1);
+  RG_REQUIRE(workspace && workspace_bytes >= p.end, RECGURU_E_WORKSPACE,
+             "embedding_bwd_plan_live_rows: workspace %lld < %lld", (long long)workspace_bytes, (long long)p.end);
+  char* ws = static_cast<char*>(workspace);
+  *live_rows = reinterpret_cast<const uint32_t*>(ws + p.off_rows);
+  *n_live_rows = reinterpret_cast<const uint32_t*>(ws + p.off_nlive) + 1;
+  return RECGURU_OK;
 }
 
 // Stage A with the shared pad mask derived inside: mask_out[i] = mask_ids[i] != pad_index (one entry
@@ -1333,7 +1382,7 @@ extern "C" int recguru_embedding_bwd_plan_padmask(const recguru_lookup_site_t* s
   using namespace rg;
   RG_REQUIRE(mask_ids != nullptr && mask_out != nullptr, RECGURU_E_SHAPE, "embedding_bwd_plan_padmask: null pointer");
   return rg::plan_impl("embedding_bwd_plan_padmask", sites_host, n_sites, V1, padding_idx, workspace,
-                       workspace_bytes, mask_ids, pad_index, mask_out, count3, stream);
+                       workspace_bytes, mask_ids, pad_index, mask_out, count3, RECGURU_PLAN_ALL, stream);
 }
 
 // Stage B: (optional zero fill,) chunked segmented reduce + span fix-up over the plan that

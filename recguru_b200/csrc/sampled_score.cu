@@ -290,17 +290,6 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
         }
       }
       __syncthreads();
-      // fused dh: the rows of the dead positions are zero (coalesced 16-byte stores).  (Streaming them
-      // from a side kernel instead was measured: no gain -- this kernel is bound by its barrier-
-      // separated phases of dependent gathers, the 97 MB of zero rows ride along for free.)
-      if (dh != nullptr) {
-        const int tot4 = n_c * VEC;
-        for (int idx = tid; idx < tot4; idx += NT) {
-          const int q = idx / VEC;
-          if (s_rank[q] < 0)
-            st_stream_f4(dh + (cb + q) * VEC + (idx - q * VEC), make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-      }
       // negatives: coalesced sweep over the chunk's [n_c, K] id block
       const int tot = n_c * K;
       for (int idx = tid; idx < tot; idx += NT) {
@@ -336,6 +325,19 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
           w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       score_item<VEC>(hv, w, c0, C, g, sub, s_sc + slot * RS);
+    }
+    // fused dh: the rows of the dead positions are zero (coalesced 16-byte streaming stores).  Issued
+    // HERE, behind this warp's gathers: ahead of them (where they sat in round 1) the 32 stores per
+    // thread filled the load/store queue in front of the dependent row gathers of phase 1; now the
+    // warps that drew few or no work items stream zeros while the others wait for their rows.
+    // (Streaming them from a side kernel instead was also measured: no gain.)
+    if (dh != nullptr) {
+      const int tot4 = n_c * VEC;
+      for (int idx = tid; idx < tot4; idx += NT) {
+        const int q = idx / VEC;
+        if (s_rank[q] < 0)
+          st_stream_f4(dh + (cb + q) * VEC + (idx - q * VEC), make_float4(0.f, 0.f, 0.f, 0.f));
+      }
     }
     __syncthreads();
     // ---- phase 2: thread = live position ---------------------------------------------------
@@ -422,6 +424,154 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
     }
   }
   if (kind >= 0 && tid == 0) block_partial[blockIdx.x] = make_float2(tot_l, tot_m);
+  rg::pdl_trigger();
+}
+
+// The padding-aware scoring when the step already owns the list of live positions (the row-mode
+// compaction of the table-backward plan, recguru_embedding_bwd_plan_live_rows): no per-CTA
+// compaction and no block-wide phase.  One warp per live position, start to finish: ids, the h row
+// and the 1+K table rows (8 rows in flight), scores, loss + unit derivatives (lane 0; a handful of
+// transcendentals), dh from the table rows still in registers (1+K <= 8) or re-read from L1.  Same
+// dot-product tree, same loss routine, same coefficient products and fma chain as the compacting
+// kernel above => bit-identical outputs.  After its live positions every thread streams zeros into
+// the outputs of the dead ones.  The loss partials are per warp (positions t = warp, warp + W, ..),
+// reduced in a fixed order.
+constexpr int kRowsWarps = 8;
+template <int VEC>
+__global__ void __launch_bounds__(kRowsWarps * 32)
+sampled_score_rows_kernel(const float4* __restrict__ h, const float4* __restrict__ weight,
+                          const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+                          int64_t n_pos, int K, const float* __restrict__ mask, int kind,
+                          float* __restrict__ p_out, float* __restrict__ n_out,
+                          float* __restrict__ dp_unit, float* __restrict__ dn_unit,
+                          float2* __restrict__ block_partial, float4* __restrict__ dh,
+                          const float* __restrict__ dh_scale, const uint32_t* __restrict__ live_count,
+                          const uint32_t* __restrict__ live_rows, const uint32_t* __restrict__ n_live_rows) {
+  rg::pdl_wait();
+  constexpr int LANES = VEC < 32 ? VEC : 32;
+  constexpr int G = 32 / LANES;
+  constexpr int VPL = VEC / LANES;
+  constexpr int UN = 8 / G;
+  __shared__ float s_sc[kRowsWarps][kRowPad];
+  __shared__ float2 s_part[kRowsWarps];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane / LANES, sub = lane % LANES;
+  const int C = K + 1;
+  const bool one_step = C <= 8;
+  const uint32_t n_live = __ldg(n_live_rows);
+  const uint32_t gw = blockIdx.x * kRowsWarps + warp, nw = gridDim.x * kRowsWarps;
+  float sc = dh_scale ? __ldg(dh_scale) : 1.f;
+  sc *= 1.f / static_cast<float>(__ldg(live_count));         // == loss_out[1] of loss_finalize_kernel
+  float* row = s_sc[warp];
+  float tl = 0.f, tm = 0.f;                                   // lane 0: this warp's loss partial
+  for (uint32_t t = gw; t < n_live; t += nw) {
+    const int64_t i = __ldg(live_rows + t);
+    const int64_t my_id = lane == 0 ? __ldg(pos + i) : (lane < C ? __ldg(neg + i * K + (lane - 1)) : 0);
+    const float m = __ldg(mask + i);
+    float4 hv[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) hv[v] = ld_stream_f4(h + i * VEC + v * LANES + sub);
+    float4 w[UN][VPL];
+    for (int c0 = 0; c0 < C; c0 += 8) {
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int c = c0 + u * G + g;
+        const int64_t id = __shfl_sync(0xffffffffu, my_id, c < C ? c : 0);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+          w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      score_item<VEC>(hv, w, c0, C, g, sub, row);
+    }
+    __syncwarp();
+    const float sv = lane < C ? row[lane] : 0.f;
+    if (lane == 0) { if (p_out) p_out[i] = sv; }
+    else if (lane < C && n_out) n_out[i * K + (lane - 1)] = sv;
+    __syncwarp();
+    if (lane == 0) {
+      const float l = position_loss(kind, row, K);
+      tl += l * m;
+      tm += m;
+    }
+    __syncwarp();
+    const float dv = lane < C ? row[lane] * m : 0.f;           // unit derivative of candidate `lane`
+    if (lane == 0) { if (dp_unit) dp_unit[i] = dv; }
+    else if (lane < C && dn_unit) dn_unit[i * K + (lane - 1)] = dv;
+    if (dh != nullptr) {
+      const float my_c = dv * sc;
+      float4 acc[VPL];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        float cf[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int c = c0 + u * G + g;
+          const int src = c < C ? c : 0;
+          cf[u] = __shfl_sync(0xffffffffu, my_c, src);
+          if (c >= C) cf[u] = 0.f;
+          if (!one_step) {
+            const int64_t id = __shfl_sync(0xffffffffu, my_id, src);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+              w[u][v] = c < C ? __ldg(weight + id * VEC + v * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            acc[v].x = fmaf(cf[u], w[u][v].x, acc[v].x);
+            acc[v].y = fmaf(cf[u], w[u][v].y, acc[v].y);
+            acc[v].z = fmaf(cf[u], w[u][v].z, acc[v].z);
+            acc[v].w = fmaf(cf[u], w[u][v].w, acc[v].w);
+          }
+      }
+#pragma unroll
+      for (int o = 16; o >= LANES; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+          acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+          acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+          acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+        }
+      if (g == 0) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) st_stream_f4(dh + i * VEC + v * LANES + sub, acc[v]);
+      }
+    }
+    __syncwarp();                                             // `row` is rewritten by the next position
+  }
+  if (lane == 0) s_part[warp] = make_float2(tl, tm);
+  // ---- the dead positions: every output is zero (coalesced streaming stores) ----
+  const int64_t gt = static_cast<int64_t>(blockIdx.x) * (kRowsWarps * 32) + tid;
+  const int64_t nt = static_cast<int64_t>(gridDim.x) * (kRowsWarps * 32);
+  if (dh != nullptr) {
+    const int64_t tot4 = n_pos * VEC;
+    for (int64_t idx = gt; idx < tot4; idx += nt)
+      if (__ldg(mask + idx / VEC) == 0.f) st_stream_f4(dh + idx, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  for (int64_t idx = gt; idx < n_pos; idx += nt)
+    if (__ldg(mask + idx) == 0.f) {
+      if (p_out) p_out[idx] = 0.f;
+      if (dp_unit) dp_unit[idx] = 0.f;
+    }
+  if (n_out != nullptr || dn_unit != nullptr) {
+    const int64_t totk = n_pos * K;
+    for (int64_t idx = gt; idx < totk; idx += nt)
+      if (__ldg(mask + idx / K) == 0.f) {
+        if (n_out) n_out[idx] = 0.f;
+        if (dn_unit) dn_unit[idx] = 0.f;
+      }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float2 t2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int w2 = 0; w2 < kRowsWarps; ++w2) { t2.x += s_part[w2].x; t2.y += s_part[w2].y; }
+    block_partial[blockIdx.x] = t2;
+  }
   rg::pdl_trigger();
 }
 
@@ -710,7 +860,8 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
                                        float* p_out, float* n_out, float* loss_out,
                                        float* dp_unit, float* dn_unit, void* workspace,
                                        int64_t workspace_bytes, float* dh, const float* dh_scale,
-                                       const uint32_t* live_count, recguru_stream_t stream) {
+                                       const uint32_t* live_count, const uint32_t* live_rows,
+                                       const uint32_t* n_live_rows, recguru_stream_t stream) {
   using namespace rg;
   const bool skip_masked = kind >= 0 && (kind & RECGURU_LOSS_SKIP_MASKED) && mask != nullptr;
   if (dh != nullptr) {
@@ -719,6 +870,9 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
     RG_REQUIRE(live_count != nullptr && aligned16(dh), RECGURU_E_SHAPE,
                "sampled_score_loss_fwd_dh: live_count is null or dh is not 16-byte aligned");
   }
+  if (live_rows != nullptr)
+    RG_REQUIRE(skip_masked && n_live_rows != nullptr && live_count != nullptr && (dh == nullptr || aligned16(dh)),
+               RECGURU_E_SHAPE, "sampled_score_loss_fwd_dh_rows: needs a SKIP_MASKED kind, a mask, live_count and n_live_rows");
   if (kind >= 0) kind &= ~RECGURU_LOSS_SKIP_MASKED;
   int rc = check_common("sampled_score_loss_fwd", V1, d, n_pos, K);
   if (rc) return rc;
@@ -766,6 +920,8 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
     blocks = rg::min64(static_cast<int64_t>(num_sms() - env_reserve) * (1024 / nt), ceil_div(n_pos, chunk));
     pos_per_cta = align_up(ceil_div(n_pos, blocks), 32);
     blocks = ceil_div(n_pos, pos_per_cta);
+    // live-row list given: 4 CTAs of 8 warps per SM, one warp per live position
+    if (live_rows != nullptr) blocks = rg::min64(static_cast<int64_t>(num_sms()) * 4, ceil_div(n_pos, 32));
   }
   if (kind >= 0)
     RG_REQUIRE(workspace && workspace_bytes >= blocks * 8, RECGURU_E_WORKSPACE,
@@ -800,7 +956,11 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
 #endif
 #define RG_LAUNCH_SCORE(V)                                                                       \
   do {                                                                                           \
-    if (skip_masked) {                                                                           \
+    if (live_rows != nullptr) {                                                                  \
+      rg::launch_pdl((sampled_score_rows_kernel<V>), static_cast<unsigned>(blocks), kRowsWarps * 32, 0, st,   \
+          h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
+          reinterpret_cast<float4*>(dh), dh_scale, live_count, live_rows, n_live_rows);            \
+    } else if (skip_masked) {                                                                    \
       RG_SPARSE_VARIANTS(V)                                                                      \
       RG_LAUNCH_SPARSE(V, 1024);                                                                 \
     } else {                                                                                     \
@@ -833,7 +993,7 @@ extern "C" int recguru_sampled_score_loss_fwd(const float* h, const float* weigh
                                               int64_t workspace_bytes, recguru_stream_t stream) {
   return sampled_score_loss_fwd_impl(h, weight, V1, d, pos, neg, n_pos, K, mask, kind, p_out, n_out, loss_out,
                                      dp_unit, dn_unit, workspace, workspace_bytes, nullptr, nullptr, nullptr,
-                                     stream);
+                                     nullptr, nullptr, stream);
 }
 
 extern "C" int recguru_sampled_score_loss_fwd_dh(const float* h, const float* weight, int64_t V1,
@@ -848,7 +1008,26 @@ extern "C" int recguru_sampled_score_loss_fwd_dh(const float* h, const float* we
   RG_REQUIRE(dh != nullptr, RECGURU_E_SHAPE, "sampled_score_loss_fwd_dh: dh is null");
   return sampled_score_loss_fwd_impl(h, weight, V1, d, pos, neg, n_pos, K, mask, kind, p_out, n_out, loss_out,
                                      dp_unit, dn_unit, workspace, workspace_bytes, dh, grad_scale, live_count,
-                                     stream);
+                                     nullptr, nullptr, stream);
+}
+
+// The same, given the ascending list of live positions (mask[i] != 0 <=> i in live_rows[0 .. *n_live_rows)):
+// one warp per live position, no compaction inside.  dh may be NULL (forward only).
+extern "C" int recguru_sampled_score_loss_fwd_dh_rows(const float* h, const float* weight, int64_t V1,
+                                                      int64_t d, const int64_t* pos, const int64_t* neg,
+                                                      int64_t n_pos, int64_t K, const float* mask, int kind,
+                                                      float* p_out, float* n_out, float* loss_out,
+                                                      float* dp_unit, float* dn_unit, void* workspace,
+                                                      int64_t workspace_bytes, const float* grad_scale,
+                                                      const uint32_t* live_count, const uint32_t* live_rows,
+                                                      const uint32_t* n_live_rows, float* dh,
+                                                      recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(live_rows != nullptr && n_live_rows != nullptr, RECGURU_E_SHAPE,
+             "sampled_score_loss_fwd_dh_rows: live_rows is null");
+  return sampled_score_loss_fwd_impl(h, weight, V1, d, pos, neg, n_pos, K, mask, kind, p_out, n_out, loss_out,
+                                     dp_unit, dn_unit, workspace, workspace_bytes, dh, grad_scale, live_count,
+                                     live_rows, n_live_rows, stream);
 }
 
 extern "C" int recguru_sampled_loss_fwd(const float* p, const float* n, int64_t n_pos, int64_t K,

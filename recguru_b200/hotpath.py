@@ -118,10 +118,16 @@ class TrainStep:
             raise RuntimeError("recguru: fuse_dh needs the padding-aware scoring kernel (skip_masked=True)")
         self._cnt = torch.zeros(3, dtype=torch.int32, device=dev)
         self._cnt_ready = torch.cuda.Event()
+        # score_rows: when every lookup site of the step shares one pad mask (SASRec), the plan's row
+        # compaction yields the list of live positions anyway: the scoring kernel walks that list, one warp
+        # per live position, instead of compacting the mask per CTA (RECGURU_SCORE_ROWS=0: A/B timing)
+        self.score_rows = self.fuse_dh and os.environ.get("RECGURU_SCORE_ROWS", "1") != "0"
+        self._rows_ready = torch.cuda.Event()
         self.begin_step()
 
     # -- step timeline (debug) -----------------------------------------------------------
-    TRACE_POINTS = ("start", "pad_mask", "plan_done", "dw_zero_done", "k1_done", "score_done", "apply_done")
+    TRACE_POINTS = ("start", "pad_mask", "plan_done", "dw_zero_done", "k1_done", "score_done", "apply_done",
+                    "rows_ready")
 
     def enable_trace(self) -> Tensor:
         """Timestamp kernels (recguru_debug_timestamp) at the ends of the step's branches: they sit in the
@@ -152,6 +158,8 @@ class TrainStep:
         self._main_src: List[Tensor] = []      # mask sources whose mask exists on the main stream (index = buffer)
         self._main_ext = {}                    # id(source) -> mask tensor produced by K1 itself
         self._loss_mask = None
+        self._live_rows = None                 # (rows, n_rows) device addresses once the plan compacted by row
+        self._rows_src = None
 
     # -- mask plumbing --------------------------------------------------------------------
     def _mask_on_main(self, src: Tensor) -> Tensor:
@@ -214,9 +222,13 @@ class TrainStep:
             if self._cnt_state == 2:
                 cur.wait_event(self._cnt_ready)
             self._issue_zero_fill(cur)
+            rows = None
+            if self._live_rows is not None and src is self._rows_src:
+                cur.wait_event(self._rows_ready)           # the plan's compaction: the live-position list
+                rows = self._live_rows
             ops.raw_sampled_score_loss(h, self.weight, pos, neg, mask, self.kind, bufs=self.sbuf,
                                        skip_masked=True, dh_out=self.dh, live_count=self._cnt,
-                                       grad_scale=grad_loss)
+                                       grad_scale=grad_loss, live_rows=rows)
             self._dh_done = True
             self._dh_scale = grad_loss
         else:
@@ -305,9 +317,18 @@ class TrainStep:
                 ops.raw_fill_zero(self.dW)
             sites = [Site(in_ids[i], None, live=in_live[i]) for i in range(self.n_inputs)]
             sites += [Site(pos, None, live=loss_live), Site(neg, None, group=self.K, live=loss_live)]
+            one_mask = all(t is loss_live for t in in_live)
             if fused_src is not None:
                 ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, mask_ids=fused_src,
                                            pad_index=self.pad_index)
+            elif self.score_rows and one_mask and mask is None and self._cnt_state != 0:
+                # compaction | event | sort: the scoring kernel of the main stream consumes the live rows
+                ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, stage=ops.PLAN_COMPACT)
+                self._stamp("rows_ready")
+                self._rows_ready.record(self._side)
+                self._live_rows = ops.raw_embedding_bwd_plan_live_rows(sites, self.V1, self.ws_bwd)
+                self._rows_src = loss_src
+                ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, stage=ops.PLAN_SORT)
             else:
                 ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
             if not self.dense_grad:

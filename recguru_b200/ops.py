@@ -276,10 +276,28 @@ def raw_embedding_bwd(sites: Sequence[Site], V1: int, d: int, padding_idx: int =
     return out
 
 
+PLAN_ALL, PLAN_COMPACT, PLAN_SORT = 0, 1, 2
+
+
+def raw_embedding_bwd_plan_live_rows(sites: Sequence[Site], V1: int, workspace: Tensor) -> Tuple[int, int]:
+    """Device addresses ``(live_rows, n_live_rows)`` inside ``workspace`` of the ascending live-row list
+    the row-mode compaction of these sites writes (every site shares one per-row ``live`` mask).
+    Host-only; the list is valid once the compaction has run on the stream."""
+    lib = _lib.load()
+    arr, keep, total = _marshal_sites(sites, None)
+    workspace = _need(workspace, torch.uint8, "workspace")
+    rows, n_rows = C.c_void_p(), C.c_void_p()
+    check(lib.recguru_embedding_bwd_plan_live_rows(arr, len(sites), V1, _ptr(workspace), workspace.numel(),
+                                                   C.byref(rows), C.byref(n_rows)), "embedding_bwd_plan_live_rows")
+    return int(rows.value), int(n_rows.value)
+
+
 def raw_embedding_bwd_plan(sites: Sequence[Site], V1: int, padding_idx: int, workspace: Tensor,
                            mask_ids: Optional[Tensor] = None, pad_index: int = 0,
-                           count3: Optional[Tensor] = None) -> None:
+                           count3: Optional[Tensor] = None, stage: int = PLAN_ALL) -> None:
     """Stage A (compaction + stable sort) on the current stream; needs ids and live/coef only.
+    ``stage``: ``PLAN_COMPACT`` then ``PLAN_SORT`` = the same work in two calls (an event can be
+    recorded between them: the live-row list of the compaction feeds the scoring kernel).
 
     ``mask_ids``: derive the shared pad mask inside the plan (``recguru_embedding_bwd_plan_padmask``):
     every site's ``live`` must be the SAME tensor, which is written here as ``mask_ids != pad_index``
@@ -287,6 +305,13 @@ def raw_embedding_bwd_plan(sites: Sequence[Site], V1: int, padding_idx: int, wor
     lib = _lib.load()
     arr, keep, total = _marshal_sites(sites, None)
     workspace = _need(workspace, torch.uint8, "workspace")
+    if stage != PLAN_ALL:
+        if mask_ids is not None:
+            raise RuntimeError("recguru: the two-stage plan takes a ready mask (mask_ids must be None)")
+        check(lib.recguru_embedding_bwd_plan_stage(arr, len(sites), V1, int(padding_idx), _ptr(workspace),
+                                                   workspace.numel(), int(stage), _stream()),
+              "embedding_bwd_plan_stage")
+        return
     if mask_ids is None:
         check(lib.recguru_embedding_bwd_plan(arr, len(sites), V1, int(padding_idx), _ptr(workspace),
                                              workspace.numel(), _stream()), "embedding_bwd_plan")
@@ -401,7 +426,8 @@ def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
                            mask: Optional[Tensor], kind: Optional[str], want_grads: bool = True,
                            bufs: Optional[dict] = None, skip_masked: bool = False,
                            dh_out: Optional[Tensor] = None, live_count: Optional[Tensor] = None,
-                           grad_scale: Optional[Tensor] = None):
+                           grad_scale: Optional[Tensor] = None,
+                           live_rows: Optional[Tuple[int, int]] = None):
     """p = h.W[pos], n = h.W[neg]; loss per tools/lossfunctions.py:36-49,:56-72,:79-96.
     ``skip_masked``: do not score positions with mask == 0 (loss and derivatives unchanged, the
     logits of those positions are reported as 0 instead of the values nobody consumes).
@@ -409,7 +435,9 @@ def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
     ``dh_out`` (with ``skip_masked``): also write d loss / d h in the same kernel
     (``recguru_sampled_score_loss_fwd_dh``); ``live_count`` = the int32 ``[3]`` buffer
     :func:`raw_pad_mask_count` filled for this mask, ``grad_scale`` an optional device scalar.
-
+    ``live_rows`` (with ``skip_masked`` and ``live_count``): the pair of device addresses
+    :func:`raw_embedding_bwd_plan_live_rows` returns -- the kernel walks that list of live positions
+    instead of compacting the mask itself (``recguru_sampled_score_loss_fwd_dh_rows``; same bits).
 
     Returns (p [..,1], n [..,K], loss_aux [2] or None, dp_unit, dn_unit).  loss_aux[0] is the
     loss, loss_aux[1] = 1/sum(mask)."""
@@ -443,13 +471,22 @@ def raw_sampled_score_loss(h: Tensor, weight: Tensor, pos: Tensor, neg: Tensor,
             dp = b.get("dp") if "dp" in b else torch.empty(n_pos, dtype=torch.float32, device=dev)
             dn = b.get("dn") if "dn" in b else torch.empty(n_pos, K, dtype=torch.float32, device=dev)
         ws = b.get("ws") if "ws" in b else _workspace(lib.recguru_sampled_workspace_bytes(n_pos, K), dev)
-    if dh_out is not None:
-        dh_out = _need(dh_out, torch.float32, "dh_out")
-        if dh_out.numel() != n_pos * d or not dh_out.is_contiguous():
-            raise RuntimeError("recguru: dh_out must be a contiguous [n_pos, d] tensor")
+    if dh_out is not None or live_rows is not None:
+        if dh_out is not None:
+            dh_out = _need(dh_out, torch.float32, "dh_out")
+            if dh_out.numel() != n_pos * d or not dh_out.is_contiguous():
+                raise RuntimeError("recguru: dh_out must be a contiguous [n_pos, d] tensor")
         if live_count is None or live_count.dtype != torch.int32 or live_count.numel() != 3 or not live_count.is_cuda:
             raise RuntimeError("recguru: live_count must be the CUDA int32 [3] buffer of raw_pad_mask_count")
         gs = None if grad_scale is None else _need(grad_scale, torch.float32, "grad_scale")
+        if live_rows is not None:
+            rows_ptr, n_rows_ptr = live_rows
+            check(lib.recguru_sampled_score_loss_fwd_dh_rows(
+                _ptr(h), _ptr(weight), V1, d, _ptr(pos), _ptr(neg), n_pos, K, _ptr(mask), kind_i, _ptr(p), _ptr(n),
+                _ptr(aux), _ptr(dp), _ptr(dn), _ptr(ws), 0 if ws is None else ws.numel(), _ptr(gs),
+                live_count.data_ptr() + 8, rows_ptr, n_rows_ptr, _ptr(dh_out), _stream()),
+                "sampled_score_loss_fwd_dh_rows")
+            return p, n, aux, dp, dn
         check(lib.recguru_sampled_score_loss_fwd_dh(_ptr(h), _ptr(weight), V1, d, _ptr(pos), _ptr(neg), n_pos,
                                                     K, _ptr(mask), kind_i, _ptr(p), _ptr(n), _ptr(aux),
                                                     _ptr(dp), _ptr(dn), _ptr(ws), 0 if ws is None else ws.numel(),

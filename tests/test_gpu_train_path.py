@@ -304,6 +304,70 @@ def test_fused_forward_dh_bit_identical_to_two_kernels(ops, kind, d, K):
         ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=False, dh_out=dh1, live_count=count3)
 
 
+@pytest.mark.parametrize("kind", ["bpr", "bpr_sas", "sce"])
+@pytest.mark.parametrize("d,K,frac", [(32, 5, 0.7), (64, 5, 0.93), (64, 30, 0.5), (128, 8, 0.2), (256, 3, 0.99),
+                                      (64, 1, 0.0), (128, 31, 1.0)])
+def test_score_over_live_row_list_bit_identical(ops, kind, d, K, frac):
+    """recguru_sampled_score_loss_fwd_dh_rows (one warp per live position, the list coming from the row-mode
+    compaction of the table-backward plan) == the compacting kernel: logits, derivatives and dh bit for bit,
+    the loss up to the order of its fp32 partial sums.  frac = share of padded positions (0 and 1 included)."""
+    torch.manual_seed(7 * d + K)
+    B, L, V1 = 41, 53, 1201
+    n = B * L
+    W = dev(torch.randn(V1, d) * 0.3)
+    h = dev(torch.randn(B, L, d) * 0.3)
+    pos = dev(torch.randint(1, V1, (B, L)))
+    neg = dev(torch.randint(1, V1, (B, L * K)))
+    ids = torch.randint(1, V1, (B, L))
+    ids[torch.rand(B, L) < frac] = 0
+    if frac >= 1.0:
+        ids[:] = 0
+        ids[3, 5] = 9                                     # one live position (a loss over none is 0/0)
+    idc = dev(ids)
+    mask = torch.empty(B, L, device="cuda")
+    count3 = torch.zeros(3, dtype=torch.int32, device="cuda")
+    ops.raw_pad_mask_count(idc, 0, mask, count3)
+    m = mask.view(-1)
+    go = dev(torch.tensor([1.25]))
+    # the live-row list: compaction stage of the plan over (in, pos, neg) sharing the one mask
+    sites = [ops.Site(idc, None, live=m), ops.Site(pos, None, live=m), ops.Site(neg, None, group=K, live=m)]
+    ws = torch.zeros(ops.embedding_bwd_workspace_bytes(n * (2 + K), V1, d), dtype=torch.uint8, device="cuda")
+    ops.raw_embedding_bwd_plan(sites, V1, 0, ws, stage=ops.PLAN_COMPACT)
+    rows = ops.raw_embedding_bwd_plan_live_rows(sites, V1, ws)
+    # the list itself: ascending live rows
+    base = ws.data_ptr()
+    n_live = int(ws[rows[1] - base: rows[1] - base + 4].view(torch.int32).item())
+    got_rows = ws[rows[0] - base: rows[0] - base + 4 * n_live].view(torch.int32).cpu()
+    assert torch.equal(got_rows.long(), torch.nonzero(ids.view(-1) != 0).view(-1))
+    dh1 = torch.full((n, d), float("nan"), device="cuda")
+    p1, n1, aux1, dp1, dn1 = ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=True, dh_out=dh1,
+                                                        live_count=count3, grad_scale=go)
+    dh2 = torch.full((n, d), float("nan"), device="cuda")
+    bufs = {k: torch.full_like(v, float("nan")) for k, v in (("p", p1), ("n", n1), ("dp", dp1), ("dn", dn1))}
+    p2, n2, aux2, dp2, dn2 = ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=True, dh_out=dh2,
+                                                        live_count=count3, grad_scale=go, live_rows=rows, bufs=bufs)
+    assert torch.equal(p1, p2) and torch.equal(n1, n2) and torch.equal(dp1, dp2) and torch.equal(dn1, dn2)
+    assert torch.equal(dh1, dh2)
+    assert torch.equal(aux1[1], aux2[1])
+    torch.testing.assert_close(aux2[0], aux1[0], rtol=2e-6, atol=0)
+    # bit-reproducible run to run
+    p3, n3, aux3, dp3, dn3 = ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=True, dh_out=dh2,
+                                                        live_count=count3, grad_scale=go, live_rows=rows)
+    assert torch.equal(aux3, aux2)
+    # the sort stage after the compaction == the one-call plan
+    ops.raw_embedding_bwd_plan(sites, V1, 0, ws, stage=ops.PLAN_SORT)
+    X = dev(torch.randn(n, d))
+    full = [ops.Site(idc, X, coef=m, live=m), ops.Site(pos, X, coef=dp1, live=m),
+            ops.Site(neg, X, coef=dn1.view(-1), group=K, live=m)]
+    dWa = torch.empty(V1, d, device="cuda")
+    ops.raw_embedding_bwd_apply(full, V1, d, dWa, ws, mode=ops.DW_ZERO_FILL)
+    ws2 = torch.zeros_like(ws)
+    ops.raw_embedding_bwd_plan(sites, V1, 0, ws2)
+    dWb = torch.empty(V1, d, device="cuda")
+    ops.raw_embedding_bwd_apply(full, V1, d, dWb, ws2, mode=ops.DW_ZERO_FILL)
+    assert torch.equal(dWa, dWb)
+
+
 # ---------------------------------------------------------------- op layer / autograd --------
 def test_modules_autograd_end_to_end_golden(ops):
     """FusedItemEmbedding + FusedPositionalEncoding + fused loss reproduce the reference's loss
