@@ -238,10 +238,15 @@ def bench_train(D: Dist, args, peaks):
         def f_gather():
             ops.raw_gather_pe_mask(hp.weight, tb.dec_in, hp.pe, hp.pad_index, out=hp.x0, mask_out=hp.mask)
 
+        sm = hp._side_mask.view(n)
+        plan_sites = [ops.Site(tb.dec_in, None, live=sm), ops.Site(tb.dec_out, None, live=sm),
+                      ops.Site(tb.n_items, None, group=cfg["K"], live=sm)]
+        rows = ops.raw_embedding_bwd_plan_live_rows(plan_sites, hp.V1, hp.ws_bwd) if hp.score_rows else None
+
         def f_fwd():
-            if hp.fuse_dh:       # forward + dh in one kernel; sum(mask) comes from the plan stage's pad-mask kernel
+            if hp.fuse_dh:       # forward + dh in one kernel; sum(mask) and the live-row list come from the plan stage
                 ops.raw_sampled_score_loss(b["h"], hp.weight, tb.dec_out, tb.n_items, hp.mask, hp.kind, bufs=hp.sbuf,
-                                           skip_masked=True, dh_out=hp.dh, live_count=hp._cnt)
+                                           skip_masked=True, dh_out=hp.dh, live_count=hp._cnt, live_rows=rows)
             else:
                 ops.raw_sampled_score_loss(b["h"], hp.weight, tb.dec_out, tb.n_items, hp.mask, hp.kind, bufs=hp.sbuf,
                                            skip_masked=hp.skip_masked)
@@ -256,8 +261,8 @@ def bench_train(D: Dist, args, peaks):
             else:
                 ops.raw_pad_mask(tb.dec_in, hp.pad_index, out=hp._side_mask)
             ops.raw_fill_zero(hp.dW)
-            ops.raw_embedding_bwd_plan([ops.Site(tb.dec_in, None, live=m), ops.Site(tb.dec_out, None, live=m),
-                                        ops.Site(tb.n_items, None, group=cfg["K"], live=m)], hp.V1, 0, hp.ws_bwd)
+            ops.raw_embedding_bwd_plan(plan_sites, hp.V1, 0, hp.ws_bwd, stage=ops.PLAN_COMPACT)
+            ops.raw_embedding_bwd_plan(plan_sites, hp.V1, 0, hp.ws_bwd, stage=ops.PLAN_SORT)
 
         def f_apply():
             sites = [ops.Site(tb.dec_in, b["g"].view(n, cfg["d"]), coef=m, live=m),
@@ -354,19 +359,21 @@ def bench_train(D: Dist, args, peaks):
                                                 "the start of the step (own pad-mask kernel), runs under the "
                                                 "gather and scoring kernels")
     if hp.fuse_dh:
-        stages["sampled_score_loss_fwd"]["fused"] = ("forward + d loss/d h in one kernel "
-                                                      "(recguru_sampled_score_loss_fwd_dh)")
+        stages["sampled_score_loss_fwd"]["fused"] = (
+            "forward + d loss/d h in one kernel over the plan's live-row list (recguru_sampled_score_loss_fwd_dh_rows)"
+            if hp.score_rows else "forward + d loss/d h in one kernel (recguru_sampled_score_loss_fwd_dh)")
         stages[dh_name]["schedule"] = "NOT launched by the timed step (dh is fused into the forward); timed for reference"
     # roofline: the longest stage ON the critical path of the timed schedule
     critical = [s_ for s_ in stage_names if s_ not in ("embedding_bwd_plan", "sampled_score_bwd_dh_standalone")]
     dom = max(critical, key=lambda s_: stage_ms[s_])
-    stage_kernels = {"gather_pe_mask": ("gather_pe_mask_kernel",), "sampled_score_loss_fwd": ("sampled_score_fwd",),
+    stage_kernels = {"gather_pe_mask": ("gather_pe_mask_kernel",),
+                     "sampled_score_loss_fwd": ("sampled_score_rows_kernel" if hp.score_rows else "sampled_score_fwd",),
                      "sampled_score_bwd_dh": ("sampled_score_bwd_dh",),
                      "sampled_score_bwd_dh_standalone": ("sampled_score_bwd_dh",),
                      "embedding_bwd_apply": ("chunk_reduce_kernel", "span_fixup_kernel")}
     roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
             "frac": stages[dom]["frac_of_hbm_peak"], "traffic": ncu_traffic(*stage_kernels[dom]),
-            "traffic_source": "profiles/r01_traffic.json (ncu --set full, DRAM read+write per launch)",
+            "traffic_source": "profiles/r02_traffic.json (ncu --set full, DRAM read+write per launch)",
             "peak_source": peaks["src"],
             "whole_step": {"algorithmic_mb": round(abytes["total"] / 1e6, 1),
                            "gbs": round(abytes["total"] / 1e6 / (ms / K), 1),

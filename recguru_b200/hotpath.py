@@ -98,6 +98,8 @@ class TrainStep:
         # chain: its own branch (RECGURU_ZERO_STREAM=0 puts it back at the head of the plan stream)
         self._zero_own = os.environ.get("RECGURU_ZERO_STREAM", "1") != "0"
         self._zstream = torch.cuda.Stream(device=dev)
+        # RECGURU_ZERO_AFTER=score: start the fill behind the scoring kernel instead of behind K1 (A/B knob)
+        self._zero_late = os.environ.get("RECGURU_ZERO_AFTER", "k1") == "score"
         self._zero_done = torch.cuda.Event()
         self._fork = torch.cuda.Event()
         self._join = torch.cuda.Event()
@@ -160,6 +162,7 @@ class TrainStep:
         self._loss_mask = None
         self._live_rows = None                 # (rows, n_rows) device addresses once the plan compacted by row
         self._rows_src = None
+        self._compacted = None                 # (pos, neg) when forward_loss ran the compaction itself
 
     # -- mask plumbing --------------------------------------------------------------------
     def _mask_on_main(self, src: Tensor) -> Tensor:
@@ -226,6 +229,17 @@ class TrainStep:
             if self._live_rows is not None and src is self._rows_src:
                 cur.wait_event(self._rows_ready)           # the plan's compaction: the live-position list
                 rows = self._live_rows
+            elif self.score_rows and not self._planned and self._cnt_state == 1 and \
+                    len(self._in_done) == self.n_inputs and all(s_ is src for s_ in self._in_src):
+                # no plan forked (serial schedule): the compaction the table backward needs anyway runs
+                # here, ahead of the scoring kernel, so that the same kernel scores in every schedule
+                n_ = self.B * self.L
+                m_ = mask.view(n_)
+                sites = [Site(self._in_ids[i], None, live=m_) for i in range(self.n_inputs)]
+                sites += [Site(pos, None, live=m_), Site(neg, None, group=self.K, live=m_)]
+                ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, stage=ops.PLAN_COMPACT)
+                rows = ops.raw_embedding_bwd_plan_live_rows(sites, self.V1, self.ws_bwd)
+                self._compacted = (pos, neg)
             ops.raw_sampled_score_loss(h, self.weight, pos, neg, mask, self.kind, bufs=self.sbuf,
                                        skip_masked=True, dh_out=self.dh, live_count=self._cnt,
                                        grad_scale=grad_loss, live_rows=rows)
@@ -235,16 +249,20 @@ class TrainStep:
             self._issue_zero_fill(torch.cuda.current_stream())
             ops.raw_sampled_score_loss(h, self.weight, pos, neg, mask, self.kind, bufs=self.sbuf,
                                        skip_masked=self.skip_masked)
+        if self._zero_late:
+            self._issue_zero_fill(torch.cuda.current_stream(), late=True)
         self._stamp("score_done")
         self._loss_done = True
         return self.sbuf["aux"][0]
 
-    def _issue_zero_fill(self, cur) -> None:
+    def _issue_zero_fill(self, cur, late: bool = False) -> None:
         """The dense zero fill of dW (dense-gradient contract) of a planned step, on its own stream,
         BEHIND the input gathers (bandwidth-bound like them: side by side they stretched the gathers
         from 29 to 43 us -- scripts/step_timeline.py) and BESIDE the scoring kernel (latency-bound: it
         leaves the HBM pins idle)."""
         if not (self._planned and self.dense_grad and self._zero_own and not self._zero_issued):
+            return
+        if self._zero_late != late:
             return
         self._k1_done.record(cur)
         self._zstream.wait_event(self._k1_done)
@@ -371,8 +389,19 @@ class TrainStep:
                     torch.cuda.current_stream().wait_event(self._zero_done)
             ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
         elif self.dense_grad:
-            ops.raw_embedding_bwd(sites, self.V1, self.d, self.padding_idx, out=self.dW, zero_fill=True,
-                                  workspace=self.ws_bwd)
+            if self._compacted is not None and self._compacted[0] is pos and self._compacted[1] is neg:
+                # forward_loss compacted these sites already: sort + reduce
+                ops.raw_fill_zero(self.dW)
+                ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, stage=ops.PLAN_SORT)
+                ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
+            else:
+                ops.raw_embedding_bwd(sites, self.V1, self.d, self.padding_idx, out=self.dW, zero_fill=True,
+                                      workspace=self.ws_bwd)
+        elif self._compacted is not None and self._compacted[0] is pos and self._compacted[1] is neg:
+            ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, stage=ops.PLAN_SORT)
+            ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
+            self.epoch += 1
+            ops.raw_embedding_bwd_mark_rows(sites, self.V1, self.ws_bwd, self.row_epoch, self.epoch)
         else:
             ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
             ops.raw_embedding_bwd_apply(sites, self.V1, self.d, self.dW, self.ws_bwd, mode=ops.DW_PREZEROED)
