@@ -23,6 +23,7 @@
 // HBM roofline: per occurrence 8 B id + 4d B source row read; 4d B per distinct row
 // written; + 4*V1*d B for the zero fill.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace rg {
 
@@ -922,6 +923,161 @@ chunk_reduce_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
   rg::pdl_trigger();
 }
 
+// ---- 4b. the same reduce with the source rows staged through shared memory by TMA --------
+// chunk_reduce_kernel keeps 8 rows per warp in flight in REGISTERS (124 of them): at 11 resident
+// warps per SM that is 45 KB in flight, and a chunk is eight dependent load round trips -- a
+// latency-bound gather (0.3 of the HBM roofline).  Here every lane issues ONE 1-D bulk copy
+// (cp.async.bulk, completing on the warp's mbarrier) for its own occurrence's row straight from the
+// lane-parallel decode -- up to 32 rows = 16 KB per warp in flight, no registers, no shuffles to
+// issue -- and the warp then adds the rows out of shared memory in sorted order.  Same additions in
+// the same order as chunk_reduce_kernel => bit-identical dW and partial rows.
+constexpr int kCrWarps = 4;                   // warps per CTA (16 KB of staging each)
+constexpr int kCrStageBytes = 16384;
+template <int VPL, int NS>
+__global__ void __launch_bounds__(kCrWarps * 32)
+chunk_reduce_tma_kernel(SiteTable st, const uint32_t* __restrict__ skeys,
+                        const uint32_t* __restrict__ svals, const uint32_t* __restrict__ n_live,
+                        int vec /* d/4 */, int group_rows /* rows staged at once: min(32, 1024/vec) */,
+                        int64_t padding_idx, int accumulate, float4* __restrict__ dW,
+                        float4* __restrict__ partial /* [n_chunks][2][vec] */) {
+  rg::pdl_wait();
+  extern __shared__ __align__(128) unsigned char cr_smem[];
+  __shared__ __align__(8) uint64_t s_bar[kCrWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total = *n_live;
+  const int64_t chunk = static_cast<int64_t>(blockIdx.x) * kCrWarps + warp;
+  const int64_t c0 = chunk * kChunk;
+  if (c0 >= total) return;
+  const int n = static_cast<int>(rg::min64(kChunk, total - c0));
+  float4* buf = reinterpret_cast<float4*>(cr_smem + warp * kCrStageBytes);
+  uint64_t* bar = &s_bar[warp];
+  if (lane == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::mbar_fence_init();
+  }
+  __syncwarp();
+
+  constexpr int kPer = kChunk / 32;
+  uint32_t l_key[kPer];
+  const float4* l_src[kPer];
+  float l_coef[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int i = q * 32 + lane;
+    l_key[q] = 0xffffffffu;
+    l_src[q] = nullptr;
+    l_coef[q] = 0.f;
+    if (i < n) {
+      l_key[q] = skeys[c0 + i];
+      const int64_t occ = svals[c0 + i];
+      const SiteRef r = find_site<NS>(st, occ);
+      const int64_t j = occ - r.offset;
+      l_src[q] = reinterpret_cast<const float4*>(r.X) + (j / r.group) * vec;
+      float c = r.coef ? r.coef[j] : 1.f;
+      if (r.scale) c *= *r.scale;
+      if (r.scale2) c *= *r.scale2;
+      l_coef[q] = c;
+    }
+  }
+  const uint32_t first_key = __shfl_sync(0xffffffffu, l_key[0], 0);
+  const uint32_t last_key = __shfl_sync(0xffffffffu, l_key[(n - 1) / 32], (n - 1) & 31);
+  const uint32_t pad = static_cast<uint32_t>(padding_idx);  // -1 -> 0xffffffff never matches
+  const bool has_pad = padding_idx >= 0;
+  if (has_pad && first_key == pad) return;  // sentinel keys sort last: the whole chunk is dead
+  const bool lead_open = c0 > 0 && skeys[c0 - 1] == first_key;           // run started earlier
+  const bool trail_open = c0 + n < total && skeys[c0 + n] == last_key;   // run continues
+
+  float4 acc[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t cur = first_key;
+  bool cur_is_lead = lead_open;
+  uint32_t phase = 0;
+  const uint32_t row_bytes = static_cast<uint32_t>(vec) * 16u;
+
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    for (int r0 = 0; r0 < 32 && q * 32 + r0 < n; r0 += group_rows) {
+      const bool mine = lane >= r0 && lane < r0 + group_rows && q * 32 + lane < n && !(has_pad && l_key[q] == pad);
+      const uint32_t live_mask = __ballot_sync(0xffffffffu, mine);
+      if (live_mask != 0u) {
+        ptx::fence_proxy_async_smem();         // the stage's earlier generic reads precede the async writes
+        if (lane == 0) ptx::mbar_arrive_expect_tx(bar, __popc(live_mask) * row_bytes);
+        __syncwarp();
+        if (mine) ptx::bulk_copy_g2s(buf + (lane - r0) * vec, l_src[q], row_bytes, bar);
+        ptx::mbar_wait(bar, phase);
+        phase ^= 1u;
+      }
+      const int r_end = min(min(r0 + group_rows, 32), n - q * 32);
+      for (int r = r0; r < r_end; ++r) {
+        const uint32_t k = __shfl_sync(0xffffffffu, l_key[q], r);
+        const float cf = __shfl_sync(0xffffffffu, l_coef[q], r);
+        if (k != cur) {
+          // close the run `cur` (it ends inside this chunk)
+          if (!(has_pad && cur == pad)) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              const int col = v * 32 + lane;
+              if (col < vec) {
+                if (cur_is_lead) {
+                  partial[(chunk * 2 + 0) * vec + col] = acc[v];
+                } else {
+                  float4* dst = dW + static_cast<int64_t>(cur) * vec + col;
+                  float4 o = acc[v];
+                  if (accumulate) {
+                    const float4 old = *dst;
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *dst = o;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          cur = k;
+          cur_is_lead = false;
+        }
+        // (a dead occurrence -- sentinel key -- contributed cf * 0 in the register version)
+        const bool live = (live_mask >> r) & 1u;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int col = v * 32 + lane;
+          const float4 x = (live && col < vec) ? buf[(r - r0) * vec + col] : make_float4(0.f, 0.f, 0.f, 0.f);
+          acc[v].x = fmaf(cf, x.x, acc[v].x);
+          acc[v].y = fmaf(cf, x.y, acc[v].y);
+          acc[v].z = fmaf(cf, x.z, acc[v].z);
+          acc[v].w = fmaf(cf, x.w, acc[v].w);
+        }
+      }
+      __syncwarp();                            // every lane has read the stage before it is refilled
+    }
+  }
+  // close the last run of the chunk
+  if (!(has_pad && cur == pad)) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = v * 32 + lane;
+      if (col < vec) {
+        if (cur_is_lead) {
+          partial[(chunk * 2 + 0) * vec + col] = acc[v];       // continues from the left
+        } else if (trail_open) {
+          partial[(chunk * 2 + 1) * vec + col] = acc[v];       // starts here, continues right
+        } else {
+          float4* dst = dW + static_cast<int64_t>(cur) * vec + col;
+          float4 o = acc[v];
+          if (accumulate) {
+            const float4 old = *dst;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *dst = o;
+        }
+      }
+    }
+  }
+  rg::pdl_trigger();
+}
+
 // ---- 5. runs that cross chunk edges --------------------------------------------------
 // One warp per chunk edge b (between chunks b-1 and b).  The warp owns the run iff the
 // edge is the FIRST edge that run crosses; it then walks right summing partials.
@@ -1428,9 +1584,36 @@ extern "C" int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_ho
   const int accumulate = zero_fill == RECGURU_DW_ACCUMULATE ? 1 : 0;
   const unsigned grid = static_cast<unsigned>(ceil_div(n_chunks, kReduceWarps));
   const int vpl = (vec + 31) / 32;
+  // RECGURU_REDUCE=regs: the register-staged chunk_reduce_kernel (A/B timing); default: TMA-staged
+  static int env_reduce_regs = -1;
+  if (env_reduce_regs < 0) {
+    const char* e = getenv("RECGURU_REDUCE");
+    env_reduce_regs = (e && e[0] == 'r') ? 1 : 0;
+  }
+  const bool reduce_tma = env_reduce_regs == 0;
+  const int group_rows = static_cast<int>(rg::min64(32, kCrStageBytes / (vec * 16)));
+  const unsigned grid_tma = static_cast<unsigned>(ceil_div(n_chunks, kCrWarps));
+#define RG_LAUNCH_REDUCE_TMA(V, NSV)                                                          \
+  do {                                                                                        \
+    static rg::PerDeviceOnce once;                                                            \
+    const int dev = rg::current_device();                                                     \
+    if (once.need(dev)) {                                                                     \
+      const cudaError_t ea = cudaFuncSetAttribute(chunk_reduce_tma_kernel<V, NSV>,            \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, kCrWarps * kCrStageBytes); \
+      RG_REQUIRE(ea == cudaSuccess, RECGURU_E_CUDA, "embedding_bwd: cudaFuncSetAttribute: %s", \
+                 cudaGetErrorString(ea));                                                     \
+      once.done(dev);                                                                         \
+    }                                                                                         \
+    rg::launch_pdl((chunk_reduce_tma_kernel<V, NSV>), grid_tma, kCrWarps * 32, kCrWarps * kCrStageBytes, st, tab, sk, \
+                   sv, n_live, vec, group_rows, pad_key, accumulate, dW4, partial);            \
+  } while (0)
 #define RG_LAUNCH_REDUCE(V)                                                                   \
   do {                                                                                        \
-    if (n_sites <= 1)                                                                         \
+    if (reduce_tma) {                                                                         \
+      if (n_sites <= 1) RG_LAUNCH_REDUCE_TMA(V, 1);                                           \
+      else if (n_sites <= 3) RG_LAUNCH_REDUCE_TMA(V, 3);                                      \
+      else RG_LAUNCH_REDUCE_TMA(V, RECGURU_MAX_SITES);                                        \
+    } else if (n_sites <= 1)                                                                  \
       rg::launch_pdl((chunk_reduce_kernel<V, 1>), grid, kReduceWarps * 32, 0, st, tab, sk, sv, n_live, vec, pad_key, \
                                                                     accumulate, dW4, partial);    \
     else if (n_sites <= 3)                                                                    \
@@ -1458,6 +1641,7 @@ extern "C" int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_ho
       return RECGURU_E_UNSUPPORTED;
   }
 #undef RG_LAUNCH_REDUCE
+#undef RG_LAUNCH_REDUCE_TMA
   return RECGURU_OK;
 }
 

@@ -114,6 +114,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ---- TMA -------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared (bytes a multiple of 16, both addresses 16-byte aligned);
+// completes `bytes` of transaction count on `bar`.
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
