@@ -370,7 +370,7 @@ def bench_train(D: Dist, args, peaks):
                      "sampled_score_loss_fwd": ("sampled_score_rows_kernel" if hp.score_rows else "sampled_score_fwd",),
                      "sampled_score_bwd_dh": ("sampled_score_bwd_dh",),
                      "sampled_score_bwd_dh_standalone": ("sampled_score_bwd_dh",),
-                     "embedding_bwd_apply": ("chunk_reduce_kernel", "span_fixup_kernel")}
+                     "embedding_bwd_apply": ("chunk_reduce_tma_kernel", "span_fixup_kernel")}
     roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
             "frac": stages[dom]["frac_of_hbm_peak"], "traffic": ncu_traffic(*stage_kernels[dom]),
             "traffic_source": "profiles/r02_traffic.json (ncu --set full, DRAM read+write per launch)",

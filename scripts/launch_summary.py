@@ -10,8 +10,8 @@ from collections import OrderedDict
 PER_STEP = OrderedDict([
     ("pad_mask_count_kernel", 1), ("zero_fill_kernel", 1), ("row_count_kernel", 1), ("compact_scan_kernel", 1),
     ("row_scatter_kernel", 1), ("radix_hist_kernel", 2), ("radix_scan_rows_kernel", 2), ("radix_scatter_kernel", 2),
-    ("gather_pe_mask_kernel", 1), ("sampled_score_fwd_sparse_kernel", 1), ("loss_finalize_kernel", 1),
-    ("chunk_reduce_kernel", 1), ("span_fixup_kernel", 1)])
+    ("gather_pe_mask_kernel", 1), ("sampled_score_rows_kernel", 1), ("loss_finalize_kernel", 1),
+    ("chunk_reduce_tma_kernel", 1), ("span_fixup_kernel", 1)])
 
 rows = list(csv.reader(open(sys.argv[1], errors="replace")))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
