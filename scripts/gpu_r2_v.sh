@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m recguru_b200.build > /dev/null
+echo "== tests"
+timeout 900 python -m pytest tests/test_gpu_train_path.py tests/test_gpu_hotpath.py tests/test_gpu_topologies.py tests/test_gpu_full_size.py tests/test_gpu_table_adam.py -m gpu -q --no-header -x 2>&1 | tail -4
+echo "== timing"
+timeout 120 python scripts/score_rows_bench.py | tail -1
+timeout 600 python bench.py --only train --skip-cpu --steps 100 > gpurun_out/r2_bench_v.json 2> gpurun_out/r2_bench_v.err; echo "rc=$?"; tail -2 gpurun_out/r2_bench_v.err
+python - <<'PY'
+import json
+j=json.loads(open("gpurun_out/r2_bench_v.json").read().strip().splitlines()[-1])
+print("train", round(j["value"]), "seqs/s", round(j["ms_per_step"],4), "roof", j["roofline"]["frac"], j["roofline"]["kernel"], j["roofline"]["whole_step"])
+for k,v in j["stages"].items(): print("  ", k, v["ms"], v["frac_of_hbm_peak"])
+print("dense", j["dense_batch"]["ms_per_step"], j["dense_batch"]["k2_table_backward"])
+PY
