@@ -36,6 +36,9 @@ gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restri
   float* s_mask = reinterpret_cast<float*>(smem_raw + tok_per_block);
 
   const int64_t tok0 = static_cast<int64_t>(blockIdx.x) * tok_per_block;
+  // position of the tile's first token: ONE 64-bit modulo per thread; the per-element `tok % L` it
+  // replaces (eight emulated 64-bit divisions per thread) was a third of the kernel's issue slots
+  const uint32_t l0 = static_cast<uint32_t>(tok0 % L);
   for (int t = threadIdx.x; t < tok_per_block; t += kGatherThreads) {
     const int64_t tok = tok0 + t;
     int id = 0;
@@ -68,7 +71,7 @@ gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restri
     for (int u = 0; u < kGatherUnroll; ++u) {
       const int64_t tok = tok0 + tl[u];
       if (tok < n_tokens) {
-        const int l = static_cast<int>(tok % L);
+        const int l = static_cast<int>((l0 + static_cast<uint32_t>(tl[u])) % static_cast<uint32_t>(L));
         const float4 p = __ldg(pe + static_cast<int64_t>(l) * vec + vv[u]);
         const float m = s_mask[tl[u]];
         float4 r = row[u];
