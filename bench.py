@@ -1339,6 +1339,11 @@ def main():
                 line["catalog_cfg5_scaling"] = "strong"
         else:
             c = cat.get("cfg5") or cat.get("cfg4")
+            if c is None:                   # --only cfg1,cfg3 (a debugging subset): the topology records alone
+                emit({"train_topologies": topo})
+                if D.dist is not None:
+                    D.dist.destroy_process_group()
+                return
             line = {"metric": c["metric"], "value": c["value"], "unit": c["unit"], "n_gpus": D.world,
                     "steps": c["steps"], "warmup": c["warmup"], "ms_per_step": c["ms_per_step"],
                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",

@@ -197,6 +197,12 @@ int recguru_embedding_bwd_plan_stage(const recguru_lookup_site_t* sites, int n_s
 int recguru_embedding_bwd_plan_live_rows(const recguru_lookup_site_t* sites, int n_sites, int64_t V1,
                                          void* workspace, int64_t workspace_bytes,
                                          const uint32_t** live_rows, const uint32_t** n_live_rows);
+/* The same list without a plan, for steps whose lookup sites do not share one mask (RecGURU: the inputs
+ * and the loss are masked by different id tensors, AutoEnc4Rec_cross.py:98-128): live_rows[0 .. *n_live_rows)
+ * = ascending i with mask[i] != 0.  Three launches; workspace = recguru_live_rows_workspace_bytes(n_rows). */
+int64_t recguru_live_rows_workspace_bytes(int64_t n_rows);
+int recguru_live_rows(const float* mask, int64_t n_rows, uint32_t* live_rows, uint32_t* n_live_rows,
+                      void* workspace, int64_t workspace_bytes, recguru_stream_t stream);
 int recguru_embedding_bwd_apply(const recguru_lookup_site_t* sites_host, int n_sites, int64_t d,
                                 int64_t V1, float* dW, int zero_fill, void* workspace,
                                 int64_t workspace_bytes, recguru_stream_t stream);

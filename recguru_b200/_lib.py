@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "librecguru_b200.so"
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_SITES = 8
 LOSS_KINDS = {"bpr": 0, "bpr_sas": 1, "sce": 2}
 LOSS_SKIP_MASKED = 0x100
@@ -91,6 +91,8 @@ SIGNATURES = {
                                                    C.c_int, c_ptr]),
     "recguru_embedding_bwd_plan_live_rows": (C.c_int, [C.POINTER(LookupSite), C.c_int, c_i64, c_ptr, c_i64,
                                                        C.POINTER(c_ptr), C.POINTER(c_ptr)]),
+    "recguru_live_rows_workspace_bytes": (c_i64, [c_i64]),
+    "recguru_live_rows": (C.c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "recguru_sample_negatives_devstep": (C.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
                                                    c_i64, C.c_uint64, c_ptr, c_ptr, c_ptr]),
     "recguru_sample_negatives_csr": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,

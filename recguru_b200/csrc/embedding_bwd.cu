@@ -239,6 +239,38 @@ row_count_kernel(const float* __restrict__ live, int64_t n_rows, uint32_t* __res
   rg::pdl_trigger();
 }
 
+// The ascending list of rows with live != 0 on its own (row_count + compact_scan + this): the list the
+// row-mode plan leaves as a by-product, for steps whose lookup sites do NOT share one mask.
+__global__ void __launch_bounds__(kSortThreads)
+rows_only_scatter_kernel(const float* __restrict__ live, int64_t n_rows, const uint32_t* __restrict__ tile_offset,
+                         uint32_t* __restrict__ live_rows) {
+  rg::pdl_wait();
+  __shared__ uint32_t s_w[kSortThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t rank[kCompactItems];   // 0xffffffff = dead
+  uint32_t run = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    const bool lv = i < n_rows && live[i] != 0.f;
+    const uint32_t b = __ballot_sync(0xffffffffu, lv);
+    rank[j] = lv ? run + __popc(b & lt_mask) : 0xffffffffu;
+    run += __popc(b);
+  }
+  if (lane == 0) s_w[warp] = run;
+  __syncthreads();
+  uint32_t base = tile_offset[blockIdx.x];
+#pragma unroll
+  for (int w = 0; w < kSortThreads / 32; ++w)
+    if (w < warp) base += s_w[w];
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j)
+    if (rank[j] != 0xffffffffu) live_rows[base + rank[j]] = static_cast<uint32_t>(warp0 + j * 32 + lane);
+  rg::pdl_trigger();
+}
+
 template <int NS>
 __global__ void __launch_bounds__(kSortThreads)
 row_scatter_kernel(SiteTable st, const float* __restrict__ live, int64_t n_rows, int64_t padding_idx,
@@ -1557,6 +1589,39 @@ extern "C" int recguru_embedding_bwd_plan_padmask(const recguru_lookup_site_t* s
   RG_REQUIRE(mask_ids != nullptr && mask_out != nullptr, RECGURU_E_SHAPE, "embedding_bwd_plan_padmask: null pointer");
   return rg::plan_impl("embedding_bwd_plan_padmask", sites_host, n_sites, V1, padding_idx, workspace,
                        workspace_bytes, mask_ids, pad_index, mask_out, count3, RECGURU_PLAN_ALL, stream);
+}
+
+extern "C" int64_t recguru_live_rows_workspace_bytes(int64_t n_rows) {
+  if (n_rows < 0) return RECGURU_E_SHAPE;
+  return rg::align_up(rg::ceil_div(n_rows > 0 ? n_rows : 1, rg::kCompactTile) * 4, 256);
+}
+
+// live_rows[0 .. *n_live_rows) = ascending indices i with mask[i] != 0 (three launches: tile counts, one-CTA
+// scan, stable scatter).  Same list as recguru_embedding_bwd_plan_live_rows, without a plan.
+extern "C" int recguru_live_rows(const float* mask, int64_t n_rows, uint32_t* live_rows, uint32_t* n_live_rows,
+                                 void* workspace, int64_t workspace_bytes, recguru_stream_t stream) {
+  using namespace rg;
+  RG_REQUIRE(n_rows >= 0 && n_rows < (1ll << 32), RECGURU_E_SHAPE, "live_rows: bad n_rows");
+  RG_REQUIRE(n_live_rows != nullptr, RECGURU_E_SHAPE, "live_rows: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_rows == 0) {
+    const cudaError_t e = cudaMemsetAsync(n_live_rows, 0, 4, st);
+    RG_REQUIRE(e == cudaSuccess, RECGURU_E_CUDA, "live_rows: %s", cudaGetErrorString(e));
+    return RECGURU_OK;
+  }
+  RG_REQUIRE(mask && live_rows, RECGURU_E_SHAPE, "live_rows: null pointer");
+  const int64_t need = recguru_live_rows_workspace_bytes(n_rows);
+  RG_REQUIRE(workspace && workspace_bytes >= need, RECGURU_E_WORKSPACE, "live_rows: workspace %lld < %lld",
+             (long long)workspace_bytes, (long long)need);
+  uint32_t* tile_cnt = static_cast<uint32_t*>(workspace);
+  const unsigned tiles = static_cast<unsigned>(ceil_div(n_rows, kCompactTile));
+  rg::launch_pdl((row_count_kernel), tiles, kSortThreads, 0, st, mask, n_rows, tile_cnt);
+  RG_CHECK_LAUNCH("row_count");
+  rg::launch_pdl((compact_scan_kernel), 1, 1024, 0, st, tile_cnt, static_cast<int>(tiles), n_live_rows);
+  RG_CHECK_LAUNCH("compact_scan");
+  rg::launch_pdl((rows_only_scatter_kernel), tiles, kSortThreads, 0, st, mask, n_rows, tile_cnt, live_rows);
+  RG_CHECK_LAUNCH("rows_only_scatter");
+  return RECGURU_OK;
 }
 
 // Stage B: (optional zero fill,) chunked segmented reduce + span fix-up over the plan that

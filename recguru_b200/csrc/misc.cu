@@ -184,7 +184,7 @@ __global__ void zero_u64_kernel(unsigned long long* p, int n) {
 
 }  // namespace rg
 
-extern "C" int recguru_abi_version(void) { return 5; }
+extern "C" int recguru_abi_version(void) { return 6; }
 extern "C" const char* recguru_last_error(void) { return rg::t_error; }
 extern "C" int64_t recguru_launch_count(void) { return rg::g_launches.load(); }
 

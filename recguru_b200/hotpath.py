@@ -125,6 +125,11 @@ class TrainStep:
         # per live position, instead of compacting the mask per CTA (RECGURU_SCORE_ROWS=0: A/B timing)
         self.score_rows = self.fuse_dh and os.environ.get("RECGURU_SCORE_ROWS", "1") != "0"
         self._rows_ready = torch.cuda.Event()
+        # (steps whose sites do not share one mask: the list of the LOSS mask from recguru_live_rows)
+        self._rows_buf = torch.empty(n, dtype=torch.int32, device=dev)
+        self._nrows_buf = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._rows_ws = torch.empty(max(256, int(ops._lib.load().recguru_live_rows_workspace_bytes(n))),
+                                    dtype=torch.uint8, device=dev)
         self.begin_step()
 
     # -- step timeline (debug) -----------------------------------------------------------
@@ -240,6 +245,10 @@ class TrainStep:
                 ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, stage=ops.PLAN_COMPACT)
                 rows = ops.raw_embedding_bwd_plan_live_rows(sites, self.V1, self.ws_bwd)
                 self._compacted = (pos, neg)
+            elif self.score_rows and not self._planned and self._cnt_state == 1:
+                # serial schedule, several mask sources: the loss mask's live rows on this stream
+                ops.raw_live_rows(mask.view(-1), self._rows_buf, self._nrows_buf, self._rows_ws)
+                rows = (self._rows_buf.data_ptr(), self._nrows_buf.data_ptr())
             ops.raw_sampled_score_loss(h, self.weight, pos, neg, mask, self.kind, bufs=self.sbuf,
                                        skip_masked=True, dh_out=self.dh, live_count=self._cnt,
                                        grad_scale=grad_loss, live_rows=rows)
@@ -348,6 +357,12 @@ class TrainStep:
                 self._rows_src = loss_src
                 ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd, stage=ops.PLAN_SORT)
             else:
+                if self.score_rows and mask is None and self._cnt_state != 0:
+                    # several mask sources: the live rows of the LOSS mask from their own three small kernels
+                    ops.raw_live_rows(loss_live, self._rows_buf, self._nrows_buf, self._rows_ws)
+                    self._rows_ready.record(self._side)
+                    self._live_rows = (self._rows_buf.data_ptr(), self._nrows_buf.data_ptr())
+                    self._rows_src = loss_src
                 ops.raw_embedding_bwd_plan(sites, self.V1, self.padding_idx, self.ws_bwd)
             if not self.dense_grad:
                 self.epoch += 1

@@ -292,6 +292,29 @@ def raw_embedding_bwd_plan_live_rows(sites: Sequence[Site], V1: int, workspace: 
     return int(rows.value), int(n_rows.value)
 
 
+def raw_live_rows(mask: Tensor, rows_out: Optional[Tensor] = None, n_rows_out: Optional[Tensor] = None,
+                  workspace: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """``rows[0 .. n_rows[0])`` = ascending flat indices with ``mask != 0`` (int32 storage read as uint32).
+    Returns ``(rows, n_rows)``; pass ``(rows.data_ptr(), n_rows.data_ptr())`` as ``live_rows`` to
+    :func:`raw_sampled_score_loss`."""
+    lib = _lib.load()
+    mask = _need(mask, torch.float32, "mask")
+    n = mask.numel()
+    dev = mask.device
+    if rows_out is None:
+        rows_out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    if n_rows_out is None:
+        n_rows_out = torch.empty(1, dtype=torch.int32, device=dev)
+    if rows_out.dtype != torch.int32 or rows_out.numel() < n or n_rows_out.dtype != torch.int32:
+        raise RuntimeError("recguru: rows_out must be an int32 tensor with one entry per mask element")
+    need = int(lib.recguru_live_rows_workspace_bytes(n))
+    if workspace is None or workspace.numel() < need:
+        workspace = _workspace(need, dev)
+    check(lib.recguru_live_rows(_ptr(mask), n, _ptr(rows_out), _ptr(n_rows_out), _ptr(workspace), workspace.numel(),
+                                _stream()), "live_rows")
+    return rows_out, n_rows_out
+
+
 def raw_embedding_bwd_plan(sites: Sequence[Site], V1: int, padding_idx: int, workspace: Tensor,
                            mask_ids: Optional[Tensor] = None, pad_index: int = 0,
                            count3: Optional[Tensor] = None, stage: int = PLAN_ALL) -> None:

@@ -339,6 +339,9 @@ def test_score_over_live_row_list_bit_identical(ops, kind, d, K, frac):
     n_live = int(ws[rows[1] - base: rows[1] - base + 4].view(torch.int32).item())
     got_rows = ws[rows[0] - base: rows[0] - base + 4 * n_live].view(torch.int32).cpu()
     assert torch.equal(got_rows.long(), torch.nonzero(ids.view(-1) != 0).view(-1))
+    # the same list without a plan (recguru_live_rows)
+    rows2, n2 = ops.raw_live_rows(m)
+    assert int(n2.item()) == n_live and torch.equal(rows2[:n_live].cpu(), got_rows)
     dh1 = torch.full((n, d), float("nan"), device="cuda")
     p1, n1, aux1, dp1, dn1 = ops.raw_sampled_score_loss(h, W, pos, neg, m, kind, skip_masked=True, dh_out=dh1,
                                                         live_count=count3, grad_scale=go)
