@@ -903,7 +903,8 @@ def bench_topology(D: Dist, args, peaks, which: str):
         variants = [("recon_sce_k30", 30, "sce"), ("bpr_sas_k5", 5, "bpr_sas")]
     else:
         cfg = CFG3
-        variants = [("recon_sce_k30", cfg["K"], cfg["kind"])]
+        # reconstruction phase (K = n_negs = 30, sampled softmax) and the BPR phase (K = 5, BPRLoss; tools/utils.py:12,:126)
+        variants = [("recon_sce_k30", cfg["K"], cfg["kind"]), ("bpr_k5", 5, "bpr")]
     B, L, d, n_items = cfg["B"], cfg["L"], cfg["d"], cfg["n_items"]
     pe = modules.sinusoid_table(max(L, 256), d)[0].to(dev)
     for vname, K, kind in variants:
@@ -931,12 +932,14 @@ def bench_topology(D: Dist, args, peaks, which: str):
         else:
             Wa = synth.item_table(n_items, d, seed=synth.SEED_WEIGHTS).to(dev)
             Wb = synth.item_table(n_items, d, seed=synth.SEED_WEIGHTS + 1).to(dev)
-            rg_ = RecGuruStep(Wa, Wb, pe, B, L, K, kind)
+            recommend = kind != "sce"      # BPR phase: recommend_forward masks dec_in by itself (AutoEnc4Rec_cross.py:150-160)
+            rg_ = RecGuruStep(Wa, Wb, pe, B, L, K, kind, recommend=recommend)
             bsa, bsb = mk(synth.SEED_DATA), mk(synth.SEED_DATA + 5000)
             graphs = [rg_.capture_run(a["tb"], b["tb"], a["h"], b["h"], a["g"], b["g"]) for a, b in zip(bsa, bsb)]
             ab = 0
             for st_, b0 in ((rg_.dom[0], bsa[0]["tb"]), (rg_.dom[1], bsb[0]["tb"])):
-                m_out, m_enc = (b0.dec_out != 0).float(), (b0.enc_in != 0).float()
+                m_out = (b0.dec_out != 0).float()
+                m_enc = ((b0.dec_in if recommend else b0.enc_in) != 0).float()
                 live, distinct = _site_stats([(b0.enc_in, m_out, 1), (b0.dec_in, m_enc, 1), (b0.dec_out, m_out, 1),
                                               (b0.n_items, m_out, K)], None)
                 ab += st_.algorithmic_bytes(distinct, live, int(m_out.sum()))["total"]
@@ -965,8 +968,9 @@ def bench_topology(D: Dist, args, peaks, which: str):
         torch.cuda.empty_cache()
     conf = {"cfg1": "configs[0] AutoRec single-domain hot-path step: 10k items, L=50, d=64, B=256; input sites enc_in + "
                     "dec_in; reconstruction (K=30 sampled softmax) and BPR fine-tune (K=5 BPRLoss_sas)",
-            "cfg3": "configs[2] RecGURU two-domain hot-path step (reconstruction phase): 2 x 500k items, L=100, d=128, "
-                    "B=1024 per domain, K=30 sampled softmax, tables without padding_idx, 4 lookup sites per domain"}
+            "cfg3": "configs[2] RecGURU two-domain hot-path step: 2 x 500k items, L=100, d=128, B=1024 per domain, tables "
+                    "without padding_idx, 4 lookup sites per domain; reconstruction phase (K=30 sampled softmax) and "
+                    "BPR phase (K=5 BPRLoss)"}
     return {"config": {"workload": conf[which], **cfg}, "launch_mode": "cuda_graph (one graph per rotating batch)",
             "variants": out}
 
