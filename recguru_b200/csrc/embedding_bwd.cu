@@ -282,6 +282,9 @@ row_scatter_kernel(SiteTable st, const float* __restrict__ live, int64_t n_rows,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kCompactTile + warp * (32 * kCompactItems);
   const uint32_t lt_mask = (1u << lane) - 1u;
+  // (requested together with the mask words: one round trip less in the kernel's dependent chain)
+  const uint32_t tile_base = tile_offset[blockIdx.x];
+  const uint32_t p_live = *n_live_rows;
   uint32_t rank[kCompactItems];   // 0xffffffff = dead
   uint32_t run = 0;
 #pragma unroll
@@ -294,11 +297,10 @@ row_scatter_kernel(SiteTable st, const float* __restrict__ live, int64_t n_rows,
   }
   if (lane == 0) s_w[warp] = run;
   __syncthreads();
-  uint32_t base = tile_offset[blockIdx.x];
+  uint32_t base = tile_base;
 #pragma unroll
   for (int w = 0; w < kSortThreads / 32; ++w)
     if (w < warp) base += s_w[w];
-  const uint32_t p_live = *n_live_rows;
   uint32_t g_total = 0;
 #pragma unroll
   for (int s2 = 0; s2 < NS; ++s2)
@@ -427,6 +429,24 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   const int bins = 1 << bits;
   const uint32_t mask = bins - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Every global load of the tile -- digit totals, the tile's scanned bases, keys, values -- is
+  // requested here, one round trip behind the live count: on a padded batch the kernel is 52 CTAs
+  // whose duration is its chain of dependent loads (it was five of them).
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kSortTile + warp * (32 * kSortItems);
+  uint32_t key[kSortItems];
+  uint32_t val_in[kSortItems];
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const int64_t i = warp0 + j * 32 + lane;
+    key[j] = i < total ? keys_in[i] : 0xffffffffu;
+    val_in[j] = (!kFirstPass && i < total) ? vals_in[i] : 0u;
+  }
+  uint32_t bb[kMaxBins / kSortThreads];
+#pragma unroll
+  for (int q = 0; q < kMaxBins / kSortThreads; ++q) {
+    const int b = q * kSortThreads + threadIdx.x;
+    bb[q] = b < bins ? block_base[static_cast<int64_t>(b) * gridDim.x + blockIdx.x] : 0u;
+  }
   for (int b = threadIdx.x; b < (kSortThreads / 32) * kMaxBins; b += kSortThreads)
     (&s_cnt[0][0])[b] = 0;
   {
@@ -452,15 +472,12 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
   __syncthreads();
 
-  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kSortTile + warp * (32 * kSortItems);
-  uint32_t key[kSortItems];
   uint32_t rank[kSortItems];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const int64_t i = warp0 + j * 32 + lane;
     const bool valid = i < total;
-    key[j] = valid ? keys_in[i] : 0xffffffffu;
     const uint32_t dig = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;  // invalid: own group
     const uint32_t peers = __match_any_sync(0xffffffffu, dig);
     const int leader = __ffs(peers) - 1;
@@ -474,8 +491,11 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
   __syncthreads();
   // per-digit exclusive prefix over the warps of this CTA, seeded with the global base
-  for (int b = threadIdx.x; b < bins; b += kSortThreads) {
-    uint32_t run = s_base[b] + block_base[static_cast<int64_t>(b) * gridDim.x + blockIdx.x];
+#pragma unroll
+  for (int q = 0; q < kMaxBins / kSortThreads; ++q) {
+    const int b = q * kSortThreads + threadIdx.x;
+    if (b >= bins) break;
+    uint32_t run = s_base[b] + bb[q];
 #pragma unroll
     for (int w = 0; w < kSortThreads / 32; ++w) {
       const uint32_t c = s_cnt[w][b];
@@ -491,7 +511,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
       const uint32_t dig = (key[j] >> shift) & mask;
       const uint32_t dst = s_cnt[warp][dig] + rank[j];
       keys_out[dst] = key[j];
-      vals_out[dst] = static_cast<OutVal>(kFirstPass ? static_cast<uint32_t>(i) : vals_in[i]);
+      vals_out[dst] = static_cast<OutVal>(kFirstPass ? static_cast<uint32_t>(i) : val_in[j]);
       if (keys_out64) keys_out64[dst] = static_cast<int64_t>(key[j]);
     }
   }
