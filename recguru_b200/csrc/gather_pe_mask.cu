@@ -22,8 +22,10 @@ namespace rg {
 constexpr int kGatherThreads = 256;
 constexpr int kGatherUnroll = 8;
 
-template <int VEC>  // float4 per row (d/4); 0 = runtime
-__global__ void __launch_bounds__(kGatherThreads)
+// DROP: the fused-dropout instantiation (its Philox state costs registers: the plain kernel, compiled
+// without it, fits five CTAs per SM instead of four)
+template <int VEC, bool DROP>  // VEC = float4 per row (d/4); 0 = runtime
+__global__ void __launch_bounds__(kGatherThreads, DROP ? 4 : 5)
 gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restrict__ ids,
                       const float4* __restrict__ pe, const float* __restrict__ mask_in,
                       int64_t pad_index, int64_t n_tokens, int L, int vec_rt,
@@ -81,7 +83,7 @@ gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restri
         r.w = __fmul_rn(__fadd_rn(r.w, p.w), m);
         // fused nn.Dropout (Transformer/transformer.py:104-106), bit-compatible with torch's kernel and
         // generator stream; rows under the mask are (signed) zeros whatever is drawn: no Philox there
-        if (drop.keep_p > 0.f && m != 0.f) r = torch_dropout4(r, tok * vec + vv[u], drop);
+        if (DROP && drop.keep_p > 0.f && m != 0.f) r = torch_dropout4(r, tok * vec + vv[u], drop);
         st_stream_f4(out + tok * vec + vv[u], r);
       }
     }
@@ -214,8 +216,14 @@ static int gather_pe_mask_impl(const float* weight, int64_t V1, int64_t d,
   const float4* pe4 = reinterpret_cast<const float4*>(pe);
   float4* o4 = reinterpret_cast<float4*>(out);
 #define RG_LAUNCH_GATHER(V)                                                              \
-  rg::launch_pdl((gather_pe_mask_kernel<V>), static_cast<unsigned>(blocks), kGatherThreads, smem, st,  \
-      w4, ids, pe4, mask_in, pad_index, n_tokens, static_cast<int>(L), vec, o4, mask_out, drop)
+  do {                                                                                   \
+    if (drop.keep_p > 0.f)                                                               \
+      rg::launch_pdl((gather_pe_mask_kernel<V, true>), static_cast<unsigned>(blocks), kGatherThreads, smem, st,  \
+          w4, ids, pe4, mask_in, pad_index, n_tokens, static_cast<int>(L), vec, o4, mask_out, drop);  \
+    else                                                                                 \
+      rg::launch_pdl((gather_pe_mask_kernel<V, false>), static_cast<unsigned>(blocks), kGatherThreads, smem, st, \
+          w4, ids, pe4, mask_in, pad_index, n_tokens, static_cast<int>(L), vec, o4, mask_out, drop);  \
+  } while (0)
   switch (vec) {
     case 8: RG_LAUNCH_GATHER(8); break;
     case 16: RG_LAUNCH_GATHER(16); break;
