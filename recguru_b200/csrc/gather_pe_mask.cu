@@ -22,10 +22,11 @@ namespace rg {
 constexpr int kGatherThreads = 256;
 constexpr int kGatherUnroll = 8;
 
-// DROP: the fused-dropout instantiation (its Philox state costs registers: the plain kernel, compiled
-// without it, fits five CTAs per SM instead of four)
+// DROP: the fused-dropout instantiation.  Compiled without the Philox path the plain kernel is 10 %
+// faster (30.1 -> 26.8 us at cfg2) at the same four CTAs per SM; forcing five or six CTAs per SM
+// (48 / 40 registers) made K1 no faster and the step slower (the plan branch beside it starves).
 template <int VEC, bool DROP>  // VEC = float4 per row (d/4); 0 = runtime
-__global__ void __launch_bounds__(kGatherThreads, DROP ? 4 : 5)
+__global__ void __launch_bounds__(kGatherThreads, 4)
 gather_pe_mask_kernel(const float4* __restrict__ weight, const int64_t* __restrict__ ids,
                       const float4* __restrict__ pe, const float* __restrict__ mask_in,
                       int64_t pad_index, int64_t n_tokens, int L, int vec_rt,
