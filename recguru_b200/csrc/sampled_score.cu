@@ -437,7 +437,8 @@ sampled_score_fwd_sparse_kernel(const float4* __restrict__ h, const float4* __re
 // the outputs of the dead ones.  The loss partials are per warp (positions t = warp, warp + W, ..),
 // reduced in a fixed order.
 constexpr int kRowsWarps = 8;
-template <int VEC>
+// ONE: 1+K <= 8 (one 8-row step per position: no step loop, the table rows stay in registers for dh)
+template <int VEC, bool ONE>
 __global__ void __launch_bounds__(kRowsWarps * 32, VEC <= 32 ? 4 : 2)
 sampled_score_rows_kernel(const float4* __restrict__ h, const float4* __restrict__ weight,
                           const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
@@ -457,7 +458,7 @@ sampled_score_rows_kernel(const float4* __restrict__ h, const float4* __restrict
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane / LANES, sub = lane % LANES;
   const int C = K + 1;
-  const bool one_step = C <= 8;
+  constexpr bool one_step = ONE;
   const uint32_t n_live = __ldg(n_live_rows);
   const uint32_t gw = blockIdx.x * kRowsWarps + warp, nw = gridDim.x * kRowsWarps;
   float sc = dh_scale ? __ldg(dh_scale) : 1.f;
@@ -472,7 +473,7 @@ sampled_score_rows_kernel(const float4* __restrict__ h, const float4* __restrict
 #pragma unroll
     for (int v = 0; v < VPL; ++v) hv[v] = ld_stream_f4(h + i * VEC + v * LANES + sub);
     float4 w[UN][VPL];
-    for (int c0 = 0; c0 < C; c0 += 8) {
+    for (int c0 = 0; c0 < (ONE ? 1 : C); c0 += 8) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int c = c0 + u * G + g;
@@ -502,7 +503,7 @@ sampled_score_rows_kernel(const float4* __restrict__ h, const float4* __restrict
       float4 acc[VPL];
 #pragma unroll
       for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c0 = 0; c0 < C; c0 += 8) {
+      for (int c0 = 0; c0 < (ONE ? 1 : C); c0 += 8) {
         float cf[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
@@ -972,9 +973,14 @@ static int sampled_score_loss_fwd_impl(const float* h, const float* weight, int6
 #define RG_LAUNCH_SCORE(V)                                                                       \
   do {                                                                                           \
     if (live_rows != nullptr) {                                                                  \
-      rg::launch_pdl((sampled_score_rows_kernel<V>), static_cast<unsigned>(blocks), kRowsWarps * 32, 0, st,   \
-          h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,     \
-          reinterpret_cast<float4*>(dh), dh_scale, live_count, live_rows, n_live_rows);            \
+      if (K + 1 <= 8)                                                                            \
+        rg::launch_pdl((sampled_score_rows_kernel<V, true>), static_cast<unsigned>(blocks), kRowsWarps * 32, 0, st, \
+            h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,   \
+            reinterpret_cast<float4*>(dh), dh_scale, live_count, live_rows, n_live_rows);          \
+      else                                                                                       \
+        rg::launch_pdl((sampled_score_rows_kernel<V, false>), static_cast<unsigned>(blocks), kRowsWarps * 32, 0, st, \
+            h4, w4, pos, neg, n_pos, static_cast<int>(K), mask, kind, p_out, n_out, dp_unit, dn_unit, part,   \
+            reinterpret_cast<float4*>(dh), dh_scale, live_count, live_rows, n_live_rows);          \
     } else if (skip_masked) {                                                                    \
       RG_SPARSE_VARIANTS(V)                                                                      \
       RG_LAUNCH_SPARSE(V, 1024);                                                                 \
