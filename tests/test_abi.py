@@ -62,6 +62,33 @@ def test_argument_validation_without_gpu(built_lib):
         _lib.check(-2, "demo")
 
 
+def test_round2_entry_points_validate_without_gpu(built_lib):
+    """The entry points added in round 2 check their arguments before any CUDA call as well."""
+    import ctypes as C
+    from recguru_b200 import _lib
+    lib = _lib.load()
+    # live-row list without a plan
+    assert lib.recguru_live_rows_workspace_bytes(-1) == -1
+    assert lib.recguru_live_rows_workspace_bytes(204800) >= 4 * 200
+    assert lib.recguru_live_rows(None, 8, None, None, None, 0, None) == -1          # n_live_rows is null
+    assert b"null" in lib.recguru_last_error()
+    # two-stage plan: a stage outside {ALL, COMPACT, SORT}; live-row pointers need row mode
+    site = (_lib.LookupSite * 1)()
+    site[0].group = 1                                    # an empty site (count 0): valid, nothing to plan
+    assert lib.recguru_embedding_bwd_plan_stage(site, 1, 100, 0, None, 0, 7, None) == -1
+    assert b"stage" in lib.recguru_last_error()
+    rows, n_rows = C.c_void_p(), C.c_void_p()
+    rc = lib.recguru_embedding_bwd_plan_live_rows(site, 1, 100, None, 0, C.byref(rows), C.byref(n_rows))
+    assert rc == -2 and b"mask" in lib.recguru_last_error()                           # no sites with a shared mask
+    # scoring over a live-row list: the list pointers are mandatory, the kind must skip masked positions
+    assert lib.recguru_sampled_score_loss_fwd_dh_rows(None, None, 10, 32, None, None, 4, 2, None, 0, None, None, None,
+                                                      None, None, None, 0, None, None, None, None, None, None) == -1
+    assert b"live_rows" in lib.recguru_last_error()
+    # dropout parameters
+    assert lib.recguru_dropout(None, None, 16, 32, 1.5, 0, 0, 1024, None, None) == -1
+    assert b"dropout" in lib.recguru_last_error()
+
+
 def test_sources_are_sm100a_only():
     from recguru_b200 import build
     assert "arch=compute_100a,code=sm_100a" in build.NVCC_FLAGS
